@@ -1,0 +1,240 @@
+/*
+ * magma_b200.h -- C ABI of the B200-native MagmaClustR hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers/sizes to CALLER-OWNED HOST
+ * memory (unless the name ends in _dev), returns an int status and never throws:
+ *     0  ok
+ *    <0  argument / CUDA error   (mb_last_error() gives the text)
+ *    >0  numerical failure       (e.g. jitter retries exhausted; per-task `info` arrays say where)
+ *
+ * It replaces, for the batched-over-tasks GP numerics, what the reference reaches through
+ * its own FFI (`.Call` symbols registered in /root/reference/src/init.c:17-30) and the R
+ * functions above it.  Each declaration cites the reference interface it stands for.
+ * INTEGRATION.md shows the R-side `.Call` shim a maintainer would add.
+ *
+ * Conventions
+ *   - matrices are column-major doubles with explicit leading dimension where one is given;
+ *     symmetric results are returned full (both triangles), like chol2inv().
+ *   - ragged tasks are CSR: task t owns rows offs[t] .. offs[t+1]-1 of X (row-major rows x D),
+ *     y, and grid_index (0-based position of each row in the sorted union grid,
+ *     = match(db$Reference, all_input) - 1 computed by the caller).
+ *   - hyper-parameters are log-scale doubles laid out per mb_kernel (below); a table of
+ *     per-task HPs is row-major n_tasks x n_hp.
+ *   - one caller thread per context; contexts are independent.
+ */
+#ifndef MAGMA_B200_H
+#define MAGMA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_MAX_TERMS 4
+#define MB_MAX_HP 12
+#define MB_MAX_CLUSTERS 16
+
+/* base kernels, /root/reference/R/kernels.R:164-398 */
+enum { MB_KERN_SE = 0, MB_KERN_PERIO = 1, MB_KERN_RQ = 2, MB_KERN_LIN = 3 };
+
+/*
+ * A kernel string of the reference's grammar "(k1 * k2 * ...) + k + k ..."
+ * (/root/reference/R/kernel-to-matrices.R:163-340): `types[0..n_prod-1]` are multiplied, the
+ * remaining terms are added.  HP layout, in term order: SE (variance, lengthscale);
+ * PERIO (variance, lengthscale, period); RQ (variance, lengthscale, scale); LIN (slope, offset);
+ * then `noise` last when has_noise != 0.  n_hp is the total (filled by mb_kernel_parse).
+ */
+typedef struct mb_kernel {
+  int32_t n_terms;
+  int32_t n_prod;
+  int32_t types[MB_MAX_TERMS];
+  int32_t has_noise;
+  int32_t n_hp;
+} mb_kernel;
+
+typedef struct mb_context mb_context;
+
+/* ---- context -------------------------------------------------------------------------- */
+int mb_create(mb_context** ctx, int device);
+int mb_destroy(mb_context* ctx);
+const char* mb_last_error(void);
+/* parse "SE * RQ + PERIO" (kernel-to-matrices.R:163-204); has_noise appends the noise HP */
+int mb_kernel_parse(const char* kern, int has_noise, mb_kernel* out);
+/* name of HP `p` of a kernel ("se_variance", ..., "noise"); NULL when out of range */
+const char* mb_kernel_hp_name(const mb_kernel* k, int p);
+/* counters: kernels launched by this context since creation (bench.py `gpu_launches`) */
+int64_t mb_launch_count(mb_context* ctx);
+
+/* optional sum-all-reduce over ranks of `count` doubles in DEVICE memory, called on the
+ * context's stream after it was synchronised (multi-GPU sharding).  The hook
+ * must return 0 and leave the reduced values in place. */
+typedef int (*mb_allreduce_fn)(void* user, void* dev_ptr, int64_t count);
+int mb_set_allreduce(mb_context* ctx, mb_allreduce_fn fn, void* user, int rank, int world);
+
+/* ---- the five legacy builders: /root/reference/src/code.cpp, src/init.c:17-24 ----------
+ * m1 is n1 x d, m2 is n2 x d, out is n1 x n2, all column-major (R numeric matrices). */
+int mb_cpp_dist(mb_context*, const double* m1, int n1, const double* m2, int n2, int d, double* out);
+int mb_cpp_prod(mb_context*, const double* m1, int n1, const double* m2, int n2, int d, double* out);
+int mb_cpp_perio(mb_context*, const double* m1, int n1, const double* m2, int n2, int d, double period, double* out);
+int mb_cpp_perio_deriv(mb_context*, const double* m1, int n1, const double* m2, int n2, int d, double period, double* out);
+int mb_cpp_noise(mb_context*, const double* m1, int n1, const double* m2, int n2, int d, double noise, double* out);
+
+/* ---- kern_to_cov / kern_to_inv / chol_inv_jitter --------------------------------------- */
+/* kern_to_cov(input, kern, hp, deriv, input_2) (kernel-to-matrices.R:71-503).  x1: n1 x d,
+ * x2: n2 x d or NULL (= x1), ROW-major points.  deriv = -1 for the covariance, else the HP
+ * index whose derivative matrix is wanted.  out: n1 x n2 column-major. */
+int mb_kern_to_cov(mb_context*, const mb_kernel* k, const double* hp, const double* x1, int n1,
+                   const double* x2, int n2, int d, int deriv, double* out);
+/* list_kern_to_cov / list_kern_to_inv (kernel-to-matrices.R:586-652) over CSR tasks.
+ * hp: n_tasks x n_hp (hp_shared = 0) or one row (hp_shared = 1).  out: blocks of n_t x n_t
+ * column-major, block t at out + out_offs[t] (out_offs has n_tasks entries, caller-computed).
+ * inverse != 0 applies chol_inv_jitter(pen_diag); retries[t] (may be NULL) receives the
+ * number of jitter escalations of task t. */
+int mb_list_kern_to_mat(mb_context*, const mb_kernel* k, int64_t n_tasks, const int64_t* offs,
+                        int d, const double* X, const double* hp, int hp_shared, int deriv,
+                        int inverse, double pen_diag, const int64_t* out_offs, double* out,
+                        int32_t* retries);
+/* chol_inv_jitter(mat, pen_diag) (kernel-to-matrices.R:670-680): inverse of mat + cumulative
+ * jitter; reads the upper triangle only, like chol().  n_retry receives the retry count and
+ * jitter_total the diagonal shift actually applied (both may be NULL). */
+int mb_chol_inv_jitter(mb_context*, const double* mat, int n, int ld, double pen_diag,
+                       double* inv, int32_t* n_retry, double* jitter_total);
+
+/* ---- resident dataset (what `db` is to e_step/m_step) ---------------------------------- */
+/* Upload the prepared training table: tasks in the caller's (string-sorted) order, rows in
+ * Reference order, union grid (U points, row-major U x d) in Reference order. */
+int mb_upload_dataset(mb_context*, int64_t n_tasks, const int64_t* offs, int d, const double* X,
+                      const double* y, const int32_t* grid_index, int32_t n_grid,
+                      const double* grid_X);
+
+/* ---- Magma: e_step / m_step / logL_monitoring / train_magma ---------------------------- */
+/* e_step (em-magma.R:25-82).  hp_0: kern_0 HPs (no noise); hp_i: n_tasks x n_hp (or one row
+ * when hp_i_shared); m_0: U.  post_mean: U, post_cov: U x U (column-major, full).
+ * info (may be NULL, 3 ints): jitter retries of inv_0, of post_cov, and max over tasks. */
+int mb_e_step(mb_context*, const mb_kernel* kern_0, const double* hp_0, const mb_kernel* kern_i,
+              const double* hp_i, int hp_i_shared, const double* m_0, double pen_diag,
+              double* post_mean, double* post_cov, int32_t* info);
+
+/* logL_GP_mod + gr_GP_mod (likelihoods.R:155-174, gradients-likelihoods.R:71-97) for every
+ * task of the resident dataset in one launch, with mean = post_mean[t_i], post_cov[t_i,t_i]
+ * gathered from the U-grid arrays.  f: n_tasks, g: n_tasks x n_hp (NULL = values only). */
+int mb_logL_GP_mod_tasks(mb_context*, const mb_kernel* kern_i, const double* hp_i, int hp_i_shared,
+                         const double* post_mean, const double* post_cov, double pen_diag,
+                         double* f, double* g, int32_t* retries);
+/* the same pair for ONE matrix-sized problem given explicitly (mean process, cluster
+ * processes): x n x d row-major, y, mean (n), post_cov n x n. */
+int mb_logL_GP_mod(mb_context*, const mb_kernel* k, const double* hp, const double* x, int n, int d,
+                   const double* y, const double* mean, const double* post_cov, double pen_diag,
+                   double* f, double* g);
+
+/* m_step (em-magma.R:119-235): L-BFGS-B (factr 1e13, maxit 25, lmm 5) for hp_0 and for hp_i
+ * (one shared optimisation when shared_hp, else n_tasks independent problems advanced in
+ * lock-step on the device).  hp_0 / hp_i are updated in place.  stats (may be NULL, 4 ints):
+ * objective evaluations of hp_0, lock-step rounds for the tasks, total task evaluations,
+ * tasks that ended with a non-zero optim `convergence` code. */
+int mb_m_step(mb_context*, const mb_kernel* kern_0, double* hp_0, const mb_kernel* kern_i,
+              double* hp_i, int shared_hp, const double* m_0, const double* post_mean,
+              const double* post_cov, double pen_diag, int64_t* stats);
+
+/* logL_monitoring (likelihoods.R:253-312). */
+int mb_logL_monitoring(mb_context*, const mb_kernel* kern_0, const double* hp_0,
+                       const mb_kernel* kern_i, const double* hp_i, int hp_i_shared,
+                       const double* m_0, const double* post_mean, const double* post_cov,
+                       double pen_diag, double* logL);
+
+/* One EM iteration of train_magma's loop body (training.R:905-1030) on the resident dataset,
+ * everything kept on the device between the three phases: e_step, m_step (HPs updated in
+ * place), logL_monitoring with the new HPs.  post_mean/post_cov may be NULL (not copied
+ * back).  stats as in mb_m_step. */
+int mb_em_step(mb_context*, const mb_kernel* kern_0, double* hp_0, const mb_kernel* kern_i,
+               double* hp_i, int shared_hp, const double* m_0, double pen_diag, double* logL,
+               double* post_mean, double* post_cov, int64_t* stats);
+
+/* The whole EM loop with the reference's convergence rule (training.R:978-1029).
+ * seq_logL: n_iter_max doubles; n_iter: iterations done; converged: 0/1. */
+int mb_train_magma(mb_context*, const mb_kernel* kern_0, double* hp_0, const mb_kernel* kern_i,
+                   double* hp_i, int shared_hp, const double* m_0, double pen_diag,
+                   int n_iter_max, double cv_threshold, double* seq_logL, int32_t* n_iter,
+                   int32_t* converged, double* post_mean, double* post_cov);
+
+/* hyperposterior (prediction.R:670-707): e_step on a caller-given grid (data U grid_inputs),
+ * with per-row positions in THAT grid. */
+int mb_hyperposterior(mb_context*, const mb_kernel* kern_0, const double* hp_0,
+                      const mb_kernel* kern_i, const double* hp_i, int hp_i_shared,
+                      int32_t n_grid, const double* grid_X, const int32_t* grid_index,
+                      const double* m_0, double pen_diag, double* post_mean, double* post_cov);
+
+/* pred_magma (prediction.R:1146-1197) for one new task: obs n_obs x d, pred n_pred x d (both
+ * row-major, Reference order), mean_obs/mean_pred and the three post_cov blocks gathered by
+ * the caller from the hyper-posterior (column-major, ld = rows).  hp includes noise when
+ * k->has_noise.  pred_cov may be NULL (only Mean and Var = diag + exp(noise) are formed). */
+int mb_pred_magma(mb_context*, const mb_kernel* k, const double* hp, const double* x_obs, int n_obs,
+                  const double* y_obs, const double* x_pred, int n_pred, int d,
+                  const double* mean_obs, const double* mean_pred, const double* cov_obs,
+                  const double* cov_pred, const double* cov_crossed, double pen_diag,
+                  double* pred_mean, double* pred_var, double* pred_cov);
+
+/* ---- MagmaClust ------------------------------------------------------------------------ */
+/* ve_step (vem-magmaclust.R:32-150): K hyper-posteriors weighted by tau (n_tasks x K,
+ * row-major).  hp_k: K x n_hp(kern_k); m_k: K x U.  post_mean: K x U; post_cov: K blocks
+ * of U x U.  When update != 0 the mixture is recomputed by update_mixture with prop_mixture
+ * (K) and written to tau_out (n_tasks x K), else tau is copied. */
+int mb_ve_step(mb_context*, int n_clusters, const mb_kernel* kern_k, const double* hp_k,
+               const mb_kernel* kern_i, const double* hp_i, int hp_i_shared, const double* m_k,
+               const double* tau, const double* prop_mixture, int update, double pen_diag,
+               double* post_mean, double* post_cov, double* tau_out);
+/* update_mixture (vem-magmaclust.R:330-396), rounded to 5 decimals like the reference. */
+int mb_update_mixture(mb_context*, int n_clusters, const mb_kernel* kern_i, const double* hp_i,
+                      int hp_i_shared, const double* post_mean, const double* post_cov,
+                      const double* prop_mixture, double pen_diag, double* tau_out);
+/* elbo_clust_multi_GP + gr_clust_multi_GP for every task (elbos.R:18-55,
+ * gradients-elbos.R:17-70). */
+int mb_elbo_clust_tasks(mb_context*, int n_clusters, const mb_kernel* kern_i, const double* hp_i,
+                        int hp_i_shared, const double* post_mean, const double* post_cov,
+                        const double* tau, double pen_diag, double* f, double* g);
+/* vm_step (vem-magmaclust.R:191-303): m_k, hp_k, hp_i updated in place; prop_mixture out. */
+int mb_vm_step(mb_context*, int n_clusters, const mb_kernel* kern_k, double* hp_k,
+               const mb_kernel* kern_i, double* hp_i, int shared_hp_k, int shared_hp_i,
+               double* m_k, const double* post_mean, const double* post_cov, const double* tau,
+               double pen_diag, double* prop_mixture, int64_t* stats);
+/* elbo_monitoring_VEM (elbos.R:200-272). */
+int mb_elbo_monitoring(mb_context*, int n_clusters, const mb_kernel* kern_k, const double* hp_k,
+                       const mb_kernel* kern_i, const double* hp_i, int hp_i_shared,
+                       const double* m_k, const double* post_mean, const double* post_cov,
+                       const double* tau, const double* prop_mixture, double pen_diag,
+                       double* elbo);
+
+/* ---- device-resident EM state and timing (measurement support; no reference counterpart:
+ * the reference keeps hp_0 / hp_i in R tibbles between iterations, training.R:896-1030) ------ */
+/* Store hp_0, the hp_i table (n_tasks x n_hp) and m_0 (U) on the device as the pristine
+ * starting state of mb_em_step_resident. */
+int mb_set_state(mb_context*, const mb_kernel* kern_0, const double* hp_0, const mb_kernel* kern_i,
+                 const double* hp_i, const double* m_0);
+/* One EM iteration exactly like mb_em_step but with the HPs taken from / left in device
+ * memory; restart != 0 first restores the pristine state.  Only logL and stats come back. */
+int mb_em_step_resident(mb_context*, const mb_kernel* kern_0, const mb_kernel* kern_i, int shared_hp,
+                        double pen_diag, int restart, double* logL, int64_t* stats);
+int mb_get_state(mb_context*, const mb_kernel* kern_0, double* hp_0, const mb_kernel* kern_i,
+                 double* hp_i);
+/* CUDA-event timing on the library's own stream: which = 0 records the start event, 1 the stop
+ * event; mb_timer_ms synchronises on the stop event and returns the elapsed device time. */
+int mb_timer(mb_context*, int which);
+int mb_timer_ms(mb_context*, double* ms);
+/* Per-kernel event timing of the dominant kernel (k_task_objective).  enable != 0 brackets every
+ * launch with events.  mb_profile_read returns out[0] = summed device ms, out[1] = launches,
+ * out[2] = task evaluations (active CTAs) since the last read, and resets the counters. */
+int mb_profile(mb_context*, int enable);
+int mb_profile_read(mb_context*, double* out3);
+/* Write `bytes` of device memory (L2 flush between timed iterations). */
+int mb_flush_l2(mb_context*, int64_t bytes);
+
+/* ---- optimiser, exposed for tests: optim(method="L-BFGS-B") on a built-in test function
+ * (0 = Rosenbrock n=2), run by the same state machine the M step uses (host build). */
+int mb_lbfgsb_selftest(int which, double* x, int n, double factr, int maxit, double* fval,
+                       int32_t* n_eval, int32_t* fail);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAGMA_B200_H */

@@ -1,0 +1,1230 @@
+// api.cu -- context, device workspaces and the extern "C" entry points of include/magma_b200.h.
+// Host code here only orchestrates: every number is produced by the kernels of tasks.cu,
+// dense.cu and lbfgsb_dev.cu.  There is no CPU fallback: without a CUDA device every call fails.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "lbfgsb.h"
+#include "tasks.cuh"
+
+// ---- launchers defined in the other translation units ------------------------------------
+cudaError_t launch_task_objective(TaskObjArgs a, int n_launch, cudaStream_t st);
+cudaError_t launch_task_inverse(TaskInvArgs a, int n_ctas, cudaStream_t st);
+cudaError_t launch_task_cov(TaskData db, DevKern kd, const double* hp, int64_t hp_stride,
+                            int deriv, double* out, const int64_t* out_offs, cudaStream_t st);
+int task_max_ctas_per_sm(int nmax, int D);
+cudaError_t launch_dense_cov(const DevKern& kd, const double* hp_host, const double* x1, int n1,
+                             const double* x2, int n2, int D, int deriv, int with_noise,
+                             double* out, int64_t rs, int64_t cs, cudaStream_t st);
+cudaError_t launch_legacy_builder(int which, const double* m1, int n1, const double* m2, int n2,
+                                  int d, double par, double* out, cudaStream_t st);
+cudaError_t launch_dense_cholinv(const double* src, int ld_src, double* A, double* B, int n,
+                                 double pen, int* info, double* out, cudaStream_t st);
+cudaError_t launch_dense_chol_logdiag(const double* src, double* W, int n, int* info, double* out,
+                                      cudaStream_t st);
+cudaError_t launch_dense_lu_logdet(const double* src, double* W, int n, int* done, double* out,
+                                   cudaStream_t st);
+cudaError_t launch_gemm(int m, int n, int k, const double* A, int64_t ars, int64_t acs,
+                        const double* B, int64_t brs, int64_t bcs, double* C, int64_t ldc,
+                        double alpha, const double* Cin, double beta, cudaStream_t st);
+cudaError_t launch_gemv(int m, int n, const double* A, int64_t ld, const double* x,
+                        const double* y0, double* y, cudaStream_t st);
+int dense_obj_nparts(int n);
+cudaError_t launch_dense_obj(const DevKern& kd, const double* hp_host, const double* x, int n,
+                             int D, const double* A, const double* S, const double* T,
+                             const double* al, const double* r, const double* logdet,
+                             int from_chol, int want_grad, double* part, double* res,
+                             cudaStream_t st);
+cudaError_t launch_reduce_partials(int64_t count, int nparts, const double* base,
+                                   const double* part, int64_t part_stride, double* out,
+                                   cudaStream_t st);
+cudaError_t launch_sum_sequential(const double* v, int64_t n, int64_t stride, double* out,
+                                  cudaStream_t st);
+cudaError_t launch_colsum_sequential(const double* v, int64_t n, int P, double* out,
+                                     cudaStream_t st);
+cudaError_t launch_axpby(int64_t n, double a, const double* x, double b, const double* y,
+                         double* out, cudaStream_t st);
+cudaError_t launch_fill(int64_t n, double v, double* out, cudaStream_t st);
+cudaError_t launch_diag(int n, const double* M, int64_t ld, double add, double* out,
+                        cudaStream_t st);
+cudaError_t launch_lbfgsb_init(LbfgsbState* st, int64_t m, int n, const double* x0,
+                               int64_t x0_stride, double factr, double pgtol, int maxit,
+                               cudaStream_t s);
+cudaError_t launch_lbfgsb_advance(LbfgsbState* st, int64_t m, int n, const double* f,
+                                  const double* g, int* n_active, cudaStream_t s);
+cudaError_t launch_lbfgsb_export(const LbfgsbState* st, int64_t m, int n, double* x,
+                                 int64_t x_stride, int* fail, int* nfgv, cudaStream_t s);
+
+// ---- errors -------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void mb_set_error(const char* file, int line, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s:%d: %s", file, line, msg);
+}
+extern "C" const char* mb_last_error(void) { return g_err; }
+#define MB_FAIL(code, msg) do { mb_set_error(__FILE__, __LINE__, msg); return code; } while (0)
+#define MB_TRY(call) do { int r_ = (call); if (r_ != 0) return r_; } while (0)
+
+// ---- device buffers -------------------------------------------------------------------------
+struct DBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); mb_set_error(__FILE__, __LINE__, "cudaMalloc failed"); return -3; }
+    cap = want;
+    return 0;
+  }
+  template <class T> T* as() { return (T*)p; }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct DenseWs {   // workspace of one dense n x n problem
+  DBuf Kmat, A, B, T, S, vecs, part, res, info, done;
+  int n = 0;
+  double* r() { return vecs.as<double>(); }
+  double* al() { return vecs.as<double>() + n; }
+  double* tmp() { return vecs.as<double>() + 2 * (size_t)n; }
+  int ensure(int nn) {
+    n = nn;
+    size_t m = (size_t)nn * nn * sizeof(double);
+    if (Kmat.ensure(m) || A.ensure(m) || B.ensure(m) || T.ensure(m) || S.ensure(m)) return -3;
+    if (vecs.ensure(4 * (size_t)nn * sizeof(double))) return -3;
+    if (part.ensure((size_t)dense_obj_nparts(nn) * (1 + MB_MAX_HP) * sizeof(double))) return -3;
+    if (res.ensure(32 * sizeof(double)) || info.ensure(8 * sizeof(int))) return -3;
+    if (done.ensure((size_t)nn * sizeof(int))) return -3;
+    return 0;
+  }
+  void release() { Kmat.release(); A.release(); B.release(); T.release(); S.release(); vecs.release();
+                   part.release(); res.release(); info.release(); done.release(); }
+};
+
+struct mb_context {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t st = nullptr, st2 = nullptr;
+  int64_t launches = 0;
+  int logdet_chol = 0;
+  // resident dataset
+  bool have_db = false;
+  TaskData db;
+  int64_t n_rows = 0;
+  int U = 0;
+  DBuf d_offs, d_X, d_y, d_gidx, d_gridX;
+  std::vector<int64_t> h_offs;
+  // workspaces
+  DenseWs ws0, ws1;                 // ws0: mean/cluster process on st2 ; ws1: generic on st
+  DBuf hp_i, hp_k, f_t, g_t, retries, lb, counters, part_inv, part_w, sums, pm, pc, m0, tau,
+      inv0, post_inv, weighted, fails, nfgv, scratch;
+  double* h_pin = nullptr;          // pinned host scratch (256 doubles)
+  int* h_pin_i = nullptr;           // pinned host ints (1024)
+  // resident EM state (mb_set_state): pristine + working HP tables
+  DBuf st_hp_i0, st_hp_i;
+  double st_hp_00[MB_MAX_HP], st_hp_0[MB_MAX_HP];
+  bool have_state = false;
+  // timing / profiling
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  bool prof_on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
+  size_t prof_used = 0;
+  double prof_ms = 0.0;
+  int64_t prof_launches = 0, prof_evals = 0;
+  // multi-GPU hook
+  mb_allreduce_fn ar = nullptr;
+  void* ar_user = nullptr;
+  int rank = 0, world = 1;
+};
+
+#define CU(call) MB_CUDA_OK(call)
+#define LAUNCH(ctx, call) do { CU(call); (ctx)->launches++; } while (0)
+
+// launch of the dominant kernel, optionally bracketed by events (mb_profile)
+static int launch_obj(mb_context* c, const TaskObjArgs& a, int n_launch, cudaStream_t st,
+                      bool profiled = false) {
+  if (!c->prof_on || !profiled) { LAUNCH(c, launch_task_objective(a, n_launch, st)); return 0; }
+  if (c->prof_used == c->prof_ev.size()) {
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    c->prof_ev.push_back({e0, e1});
+  }
+  auto& ev = c->prof_ev[c->prof_used++];
+  CU(cudaEventRecord(ev.first, st));
+  LAUNCH(c, launch_task_objective(a, n_launch, st));
+  CU(cudaEventRecord(ev.second, st));
+  return 0;
+}
+static int prof_collect(mb_context* c) {
+  for (size_t i = 0; i < c->prof_used; ++i) {
+    float ms = 0;
+    CU(cudaEventSynchronize(c->prof_ev[i].second));
+    CU(cudaEventElapsedTime(&ms, c->prof_ev[i].first, c->prof_ev[i].second));
+    c->prof_ms += ms;
+    c->prof_launches++;
+  }
+  c->prof_used = 0;
+  return 0;
+}
+
+static int ctx_allreduce(mb_context* c, void* dev, int64_t count, cudaStream_t s) {
+  if (c->world <= 1 || !c->ar) return 0;
+  CU(cudaStreamSynchronize(s));
+  if (c->ar(c->ar_user, dev, count) != 0) MB_FAIL(-5, "allreduce hook failed");
+  return 0;
+}
+
+// ---- context ----------------------------------------------------------------------------------
+extern "C" int mb_create(mb_context** out, int device) {
+  if (!out) MB_FAIL(-1, "null ctx pointer");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    MB_FAIL(-2, "no CUDA device: the magma_b200 library has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) MB_FAIL(-1, "bad device index");
+  CU(cudaSetDevice(device));
+  mb_context* c = new mb_context();
+  c->device = device;
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  CU(cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, lo));
+  CU(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, hi));
+  CU(cudaMallocHost((void**)&c->h_pin, 256 * sizeof(double)));
+  CU(cudaMallocHost((void**)&c->h_pin_i, 1024 * sizeof(int)));
+  CU(cudaEventCreate(&c->ev_t0));
+  CU(cudaEventCreate(&c->ev_t1));
+  const char* env = getenv("MB_LOGDET_CHOL");
+  c->logdet_chol = (env && env[0] == '1') ? 1 : 0;
+  *out = c;
+  return 0;
+}
+
+extern "C" int mb_destroy(mb_context* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  DBuf* bufs[] = {&c->d_offs, &c->d_X, &c->d_y, &c->d_gidx, &c->d_gridX, &c->hp_i, &c->hp_k, &c->f_t,
+                  &c->g_t, &c->retries, &c->lb, &c->counters, &c->part_inv, &c->part_w, &c->sums,
+                  &c->pm, &c->pc, &c->m0, &c->tau, &c->inv0, &c->post_inv, &c->weighted, &c->fails,
+                  &c->nfgv, &c->scratch};
+  for (DBuf* b : bufs) b->release();
+  c->st_hp_i0.release();
+  c->st_hp_i.release();
+  for (auto& ev : c->prof_ev) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+  if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+  c->ws0.release();
+  c->ws1.release();
+  if (c->h_pin) cudaFreeHost(c->h_pin);
+  if (c->h_pin_i) cudaFreeHost(c->h_pin_i);
+  if (c->st) cudaStreamDestroy(c->st);
+  if (c->st2) cudaStreamDestroy(c->st2);
+  delete c;
+  return 0;
+}
+
+extern "C" int64_t mb_launch_count(mb_context* c) { return c ? c->launches : 0; }
+
+extern "C" int mb_set_allreduce(mb_context* c, mb_allreduce_fn fn, void* user, int rank, int world) {
+  if (!c) MB_FAIL(-1, "null ctx");
+  c->ar = fn; c->ar_user = user; c->rank = rank; c->world = world;
+  return 0;
+}
+
+// ---- kernel strings ---------------------------------------------------------------------------
+extern "C" int mb_kernel_parse(const char* kern, int has_noise, mb_kernel* out) {
+  if (!kern || !out) MB_FAIL(-1, "null argument");
+  memset(out, 0, sizeof(*out));
+  std::vector<std::string> tok;
+  std::string cur;
+  for (const char* p = kern;; ++p) {
+    if (*p == ' ' || *p == 0) { if (!cur.empty()) tok.push_back(cur); cur.clear(); if (!*p) break; }
+    else cur.push_back(*p);
+  }
+  if (tok.empty() || tok[0] == "+" || tok[0] == "*")
+    MB_FAIL(-1, "The string in 'kern' should start with a kernel not an operator.");
+  bool seen_plus = false, expect_kernel = true;
+  int nhp = 0;
+  for (size_t i = 0; i < tok.size(); ++i) {
+    const std::string& s = tok[i];
+    if (expect_kernel) {
+      int type;
+      if (s == "SE") type = MB_KERN_SE; else if (s == "PERIO") type = MB_KERN_PERIO;
+      else if (s == "RQ") type = MB_KERN_RQ; else if (s == "LIN") type = MB_KERN_LIN;
+      else MB_FAIL(-1, "Incorrect character string specified in the 'kern' argument.");
+      if (out->n_terms >= MB_MAX_TERMS) MB_FAIL(-1, "too many kernel terms");
+      for (int q = 0; q < out->n_terms; ++q)
+        if (out->types[q] == type) MB_FAIL(-1, "a kernel type may appear once (HP names are unique)");
+      out->types[out->n_terms++] = type;
+      if (!seen_plus) out->n_prod = out->n_terms;
+      nhp += mb_term_nhp(type);
+      expect_kernel = false;
+    } else {
+      if (s == "+") seen_plus = true;
+      else if (s == "*") {
+        if (seen_plus) MB_FAIL(-1, "Incorrect character string specified in 'kern'. The '*' operators should come before '+' operators.");
+      } else MB_FAIL(-1, "Incorrect character string specified in the 'kern' argument.");
+      expect_kernel = true;
+    }
+  }
+  if (expect_kernel) MB_FAIL(-1, "Incorrect character string specified in 'kern'.");
+  out->has_noise = has_noise ? 1 : 0;
+  out->n_hp = nhp + out->has_noise;
+  if (out->n_hp > MB_MAX_HP) MB_FAIL(-1, "too many hyper-parameters");
+  return 0;
+}
+
+extern "C" const char* mb_kernel_hp_name(const mb_kernel* k, int p) {
+  static const char* names[4][3] = {{"se_variance", "se_lengthscale", nullptr},
+                                    {"perio_variance", "perio_lengthscale", "period"},
+                                    {"rq_variance", "rq_lengthscale", "rq_scale"},
+                                    {"lin_slope", "lin_offset", nullptr}};
+  if (!k || p < 0 || p >= k->n_hp) return nullptr;
+  int off = 0;
+  for (int t = 0; t < k->n_terms; ++t) {
+    int np = mb_term_nhp(k->types[t]);
+    if (p < off + np) return names[k->types[t]][p - off];
+    off += np;
+  }
+  return "noise";
+}
+
+// ---- helpers ------------------------------------------------------------------------------------
+static int h2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+  return 0;
+}
+static int d2h(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+static int check_ctx(mb_context* c) {
+  if (!c) MB_FAIL(-1, "null context");
+  CU(cudaSetDevice(c->device));
+  return 0;
+}
+
+// ---- legacy builders --------------------------------------------------------------------------
+static int legacy(mb_context* c, int which, const double* m1, int n1, const double* m2, int n2,
+                  int d, double par, double* out) {
+  MB_TRY(check_ctx(c));
+  if (!m1 || !m2 || !out || n1 < 0 || n2 < 0 || d < 0) MB_FAIL(-1, "bad argument");
+  if (n1 == 0 || n2 == 0) return 0;
+  size_t b1 = (size_t)n1 * d * 8, b2 = (size_t)n2 * d * 8, bo = (size_t)n1 * n2 * 8;
+  MB_TRY(c->scratch.ensure(b1 + b2 + bo + 64));
+  double* d1 = c->scratch.as<double>();
+  double* d2 = d1 + (size_t)n1 * d;
+  double* dout = d2 + (size_t)n2 * d;
+  MB_TRY(h2d(d1, m1, b1, c->st));
+  MB_TRY(h2d(d2, m2, b2, c->st));
+  LAUNCH(c, launch_legacy_builder(which, d1, n1, d2, n2, d, par, dout, c->st));
+  MB_TRY(d2h(out, dout, bo, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+extern "C" int mb_cpp_dist(mb_context* c, const double* m1, int n1, const double* m2, int n2, int d, double* out) { return legacy(c, 0, m1, n1, m2, n2, d, 0.0, out); }
+extern "C" int mb_cpp_perio(mb_context* c, const double* m1, int n1, const double* m2, int n2, int d, double period, double* out) { return legacy(c, 1, m1, n1, m2, n2, d, period, out); }
+extern "C" int mb_cpp_perio_deriv(mb_context* c, const double* m1, int n1, const double* m2, int n2, int d, double period, double* out) { return legacy(c, 2, m1, n1, m2, n2, d, period, out); }
+extern "C" int mb_cpp_prod(mb_context* c, const double* m1, int n1, const double* m2, int n2, int d, double* out) { return legacy(c, 3, m1, n1, m2, n2, d, 0.0, out); }
+extern "C" int mb_cpp_noise(mb_context* c, const double* m1, int n1, const double* m2, int n2, int d, double noise, double* out) { return legacy(c, 4, m1, n1, m2, n2, d, noise, out); }
+
+// ---- kern_to_cov ------------------------------------------------------------------------------
+extern "C" int mb_kern_to_cov(mb_context* c, const mb_kernel* k, const double* hp, const double* x1,
+                              int n1, const double* x2, int n2, int d, int deriv, double* out) {
+  MB_TRY(check_ctx(c));
+  if (!k || !hp || !x1 || !out || n1 < 0 || d < 1) MB_FAIL(-1, "bad argument");
+  if (deriv >= k->n_hp) MB_FAIL(-1, "deriv out of range");
+  if (!x2) { x2 = x1; n2 = n1; }
+  if (n1 == 0 || n2 == 0) return 0;
+  DevKern kd = make_devkern(k);
+  size_t b1 = (size_t)n1 * d * 8, b2 = (size_t)n2 * d * 8, bo = (size_t)n1 * n2 * 8;
+  MB_TRY(c->scratch.ensure(b1 + b2 + bo + 64));
+  double* d1 = c->scratch.as<double>();
+  double* d2 = d1 + (size_t)n1 * d;
+  double* dout = d2 + (size_t)n2 * d;
+  MB_TRY(h2d(d1, x1, b1, c->st));
+  MB_TRY(h2d(d2, x2, b2, c->st));
+  // column-major n1 x n2 output: element (i,j) at i + j*n1
+  LAUNCH(c, launch_dense_cov(kd, hp, d1, n1, d2, n2, d, deriv, 1, dout, 1, n1, c->st));
+  MB_TRY(d2h(out, dout, bo, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+// ---- dense chol_inv_jitter on device data -------------------------------------------------------
+// src (n x n, upper read) -> ws.A = inverse.  Synchronises `s`; returns >0 on numerical failure.
+static int dev_cholinv(mb_context* c, DenseWs& ws, const double* src, int n, double pen,
+                       cudaStream_t s, int* retries, double* jitter, double* sumlogdiag) {
+  LAUNCH(c, launch_dense_cholinv(src, n, ws.A.as<double>(), ws.B.as<double>(), n, pen,
+                                 ws.info.as<int>(), ws.res.as<double>() + 16, s));
+  MB_TRY(d2h(c->h_pin_i, ws.info.p, sizeof(int), s));
+  MB_TRY(d2h(c->h_pin + 200, ws.res.as<double>() + 16, 2 * sizeof(double), s));
+  CU(cudaStreamSynchronize(s));
+  if (retries) *retries = c->h_pin_i[0];
+  if (jitter) *jitter = c->h_pin[200];
+  if (sumlogdiag) *sumlogdiag = c->h_pin[201];
+  if (c->h_pin_i[0] < 0) MB_FAIL(1, "chol_inv_jitter: no positive-definite jitter found");
+  return 0;
+}
+
+extern "C" int mb_chol_inv_jitter(mb_context* c, const double* mat, int n, int ld, double pen_diag,
+                                  double* inv, int32_t* n_retry, double* jitter_total) {
+  MB_TRY(check_ctx(c));
+  if (!mat || !inv || n < 1 || ld < n) MB_FAIL(-1, "bad argument");
+  MB_TRY(c->ws1.ensure(n));
+  // column-major (ld) host matrix -> packed; symmetric so row/column-major agree, but the
+  // reference reads the UPPER triangle only: element (i,j), i <= j, sits at mat[i + j*ld].
+  std::vector<double> packed((size_t)n * n);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) packed[(size_t)i * n + j] = (i <= j) ? mat[i + (size_t)j * ld] : mat[j + (size_t)i * ld];
+  MB_TRY(h2d(c->ws1.Kmat.p, packed.data(), packed.size() * 8, c->st));
+  int retries = 0;
+  double jit = 0;
+  int rc = dev_cholinv(c, c->ws1, c->ws1.Kmat.as<double>(), n, pen_diag, c->st, &retries, &jit, nullptr);
+  if (n_retry) *n_retry = retries;
+  if (jitter_total) *jitter_total = jit;
+  if (rc != 0) return rc;
+  MB_TRY(d2h(inv, c->ws1.A.p, (size_t)n * n * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+// ---- dataset -------------------------------------------------------------------------------------
+extern "C" int mb_upload_dataset(mb_context* c, int64_t n_tasks, const int64_t* offs, int d,
+                                 const double* X, const double* y, const int32_t* grid_index,
+                                 int32_t n_grid, const double* grid_X) {
+  MB_TRY(check_ctx(c));
+  if (n_tasks < 1 || !offs || !X || !y || d < 1) MB_FAIL(-1, "bad argument");
+  int64_t rows = offs[n_tasks];
+  int nmax = 0;
+  for (int64_t t = 0; t < n_tasks; ++t) {
+    int64_t n = offs[t + 1] - offs[t];
+    if (n < 1) MB_FAIL(-1, "empty task");
+    if (n > nmax) nmax = (int)n;
+  }
+  if (grid_index)
+    for (int64_t r = 0; r < rows; ++r)
+      if (grid_index[r] < 0 || grid_index[r] >= n_grid) MB_FAIL(-1, "grid_index out of range");
+  MB_TRY(c->d_offs.ensure((n_tasks + 1) * 8));
+  MB_TRY(c->d_X.ensure((size_t)rows * d * 8));
+  MB_TRY(c->d_y.ensure((size_t)rows * 8));
+  MB_TRY(h2d(c->d_offs.p, offs, (n_tasks + 1) * 8, c->st));
+  MB_TRY(h2d(c->d_X.p, X, (size_t)rows * d * 8, c->st));
+  MB_TRY(h2d(c->d_y.p, y, (size_t)rows * 8, c->st));
+  if (grid_index) {
+    MB_TRY(c->d_gidx.ensure((size_t)rows * 4));
+    MB_TRY(h2d(c->d_gidx.p, grid_index, (size_t)rows * 4, c->st));
+  }
+  if (grid_X && n_grid > 0) {
+    MB_TRY(c->d_gridX.ensure((size_t)n_grid * d * 8));
+    MB_TRY(h2d(c->d_gridX.p, grid_X, (size_t)n_grid * d * 8, c->st));
+  }
+  CU(cudaStreamSynchronize(c->st));
+  c->h_offs.assign(offs, offs + n_tasks + 1);
+  c->db.offs = c->d_offs.as<int64_t>();
+  c->db.X = c->d_X.as<double>();
+  c->db.y = c->d_y.as<double>();
+  c->db.gidx = grid_index ? c->d_gidx.as<int32_t>() : nullptr;
+  c->db.D = d;
+  c->db.n_tasks = n_tasks;
+  c->db.nmax = nmax;
+  c->n_rows = rows;
+  c->U = n_grid;
+  c->have_db = true;
+  return 0;
+}
+
+static int need_db(mb_context* c, bool need_grid) {
+  MB_TRY(check_ctx(c));
+  if (!c->have_db) MB_FAIL(-1, "no dataset uploaded (mb_upload_dataset)");
+  if (c->db.nmax > TK_MAXN) MB_FAIL(-4, "a task has more than 96 points: the large-task path is not built yet");
+  if (need_grid && (!c->db.gidx || c->U < 1)) MB_FAIL(-1, "dataset was uploaded without a union grid");
+  return 0;
+}
+
+// upload an HP table (n_tasks x P, or one row when shared) -> device; returns stride
+static int put_hp_i(mb_context* c, const mb_kernel* k, const double* hp, int shared, int64_t* stride) {
+  size_t rows = shared ? 1 : (size_t)c->db.n_tasks;
+  MB_TRY(c->hp_i.ensure(rows * k->n_hp * 8 + 64));
+  MB_TRY(h2d(c->hp_i.p, hp, rows * k->n_hp * 8, c->st));
+  *stride = shared ? 0 : k->n_hp;
+  return 0;
+}
+
+// ---- list_kern_to_cov / list_kern_to_inv -------------------------------------------------------
+extern "C" int mb_list_kern_to_mat(mb_context* c, const mb_kernel* k, int64_t n_tasks,
+                                   const int64_t* offs, int d, const double* X, const double* hp,
+                                   int hp_shared, int deriv, int inverse, double pen_diag,
+                                   const int64_t* out_offs, double* out, int32_t* retries) {
+  MB_TRY(check_ctx(c));
+  if (!k || !offs || !X || !hp || !out_offs || !out || n_tasks < 1) MB_FAIL(-1, "bad argument");
+  if (deriv >= k->n_hp) MB_FAIL(-1, "deriv out of range");
+  int64_t rows = offs[n_tasks];
+  int nmax = 0;
+  size_t total = 0;
+  for (int64_t t = 0; t < n_tasks; ++t) {
+    int64_t n = offs[t + 1] - offs[t];
+    if (n > nmax) nmax = (int)n;
+    size_t end = (size_t)out_offs[t] + (size_t)n * n;
+    if (end > total) total = end;
+  }
+  if (inverse && nmax > TK_MAXN) MB_FAIL(-4, "a task has more than 96 points: the large-task path is not built yet");
+  DevKern kd = make_devkern(k);
+  DBuf b_offs, b_X, b_hp, b_oo, b_out, b_ret;
+  size_t hp_rows = hp_shared ? 1 : (size_t)n_tasks;
+  int rc = 0;
+  if (b_offs.ensure((n_tasks + 1) * 8) || b_X.ensure((size_t)rows * d * 8) ||
+      b_hp.ensure(hp_rows * k->n_hp * 8) || b_oo.ensure(n_tasks * 8) || b_out.ensure(total * 8) ||
+      b_ret.ensure(n_tasks * 4)) rc = -3;
+  auto cleanup = [&]() { b_offs.release(); b_X.release(); b_hp.release(); b_oo.release(); b_out.release(); b_ret.release(); };
+  if (rc) { cleanup(); return rc; }
+  cudaMemcpyAsync(b_offs.p, offs, (n_tasks + 1) * 8, cudaMemcpyHostToDevice, c->st);
+  cudaMemcpyAsync(b_X.p, X, (size_t)rows * d * 8, cudaMemcpyHostToDevice, c->st);
+  cudaMemcpyAsync(b_hp.p, hp, hp_rows * k->n_hp * 8, cudaMemcpyHostToDevice, c->st);
+  cudaMemcpyAsync(b_oo.p, out_offs, n_tasks * 8, cudaMemcpyHostToDevice, c->st);
+  TaskData db;
+  db.offs = b_offs.as<int64_t>(); db.X = b_X.as<double>(); db.y = b_X.as<double>(); db.gidx = nullptr;
+  db.D = d; db.n_tasks = n_tasks; db.nmax = nmax;
+  cudaError_t e;
+  if (!inverse) {
+    e = launch_task_cov(db, kd, b_hp.as<double>(), hp_shared ? 0 : k->n_hp, deriv, b_out.as<double>(),
+                        b_oo.as<int64_t>(), c->st);
+  } else {
+    if (deriv >= 0) { cleanup(); MB_FAIL(-1, "inverse of a derivative matrix is not part of the hot path"); }
+    TaskInvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.db = db; a.kd = kd; a.hp = b_hp.as<double>(); a.hp_stride = hp_shared ? 0 : k->n_hp;
+    a.pen = pen_diag; a.K = 1; a.inv_out = b_out.as<double>(); a.inv_offs = b_oo.as<int64_t>();
+    a.retries = b_ret.as<int32_t>();
+    int g = c->sm_count * task_max_ctas_per_sm(nmax, d);
+    if (g > n_tasks) g = (int)n_tasks;
+    e = launch_task_inverse(a, g, c->st);
+  }
+  c->launches++;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, b_out.p, total * 8, cudaMemcpyDeviceToHost, c->st);
+  std::vector<int32_t> hret;
+  if (e == cudaSuccess && inverse) {
+    hret.resize(n_tasks);
+    e = cudaMemcpyAsync(hret.data(), b_ret.p, n_tasks * 4, cudaMemcpyDeviceToHost, c->st);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
+  cleanup();
+  if (e != cudaSuccess) { mb_set_error(__FILE__, __LINE__, cudaGetErrorString(e)); return -2; }
+  if (inverse) {
+    int bad = 0;
+    for (int64_t t = 0; t < n_tasks; ++t) { if (retries) retries[t] = hret[t]; if (hret[t] < 0) bad = 1; }
+    if (bad) MB_FAIL(1, "chol_inv_jitter: no positive-definite jitter found for at least one task");
+  }
+  return 0;
+}
+
+// ================================================================================================
+// Device-resident building blocks of the EM / VEM steps
+// ================================================================================================
+
+// logL_GP_mod (+ gradient) of one n x n problem whose data already sit on the device.
+// Enqueues everything on `s` and leaves res[0..P] in ws.res (device) + an async copy in
+// hres (pinned, 1 + MB_MAX_HP doubles) and the jitter info in hinfo; the caller synchronises.
+static int dense_obj_enqueue(mb_context* c, DenseWs& ws, const DevKern& kd, const double* hp_host,
+                             const double* X, int n, int D, const double* y, const double* mean,
+                             const double* S, double pen, int want_grad, cudaStream_t s,
+                             double* hres, int* hinfo) {
+  LAUNCH(c, launch_dense_cov(kd, hp_host, X, n, X, n, D, -1, 1, ws.Kmat.as<double>(), n, 1, s));
+  LAUNCH(c, launch_dense_cholinv(ws.Kmat.as<double>(), n, ws.A.as<double>(), ws.B.as<double>(), n,
+                                 pen, ws.info.as<int>(), ws.res.as<double>() + 16, s));
+  const double* logdet;
+  if (c->logdet_chol) {
+    logdet = ws.res.as<double>() + 17;
+  } else {
+    LAUNCH(c, launch_dense_lu_logdet(ws.A.as<double>(), ws.B.as<double>(), n, ws.done.as<int>(),
+                                     ws.res.as<double>() + 18, s));
+    logdet = ws.res.as<double>() + 18;
+  }
+  LAUNCH(c, launch_axpby(n, 1.0, y, -1.0, mean, ws.r(), s));
+  LAUNCH(c, launch_gemv(n, n, ws.A.as<double>(), n, ws.r(), nullptr, ws.al(), s));
+  const double* T = nullptr;
+  if (want_grad && S) {
+    LAUNCH(c, launch_gemm(n, n, n, S, n, 1, ws.A.as<double>(), n, 1, ws.B.as<double>(), n, 1.0, nullptr, 0.0, s));
+    LAUNCH(c, launch_gemm(n, n, n, ws.A.as<double>(), n, 1, ws.B.as<double>(), n, 1, ws.T.as<double>(), n, 1.0, nullptr, 0.0, s));
+    T = ws.T.as<double>();
+  }
+  LAUNCH(c, launch_dense_obj(kd, hp_host, X, n, D, ws.A.as<double>(), S, T, ws.al(), ws.r(), logdet,
+                             c->logdet_chol, want_grad, ws.part.as<double>(), ws.res.as<double>(), s));
+  c->launches++;  // launch_dense_obj issues two kernels
+  MB_TRY(d2h(hres, ws.res.p, (1 + MB_MAX_HP) * sizeof(double), s));
+  MB_TRY(d2h(hinfo, ws.info.p, sizeof(int), s));
+  return 0;
+}
+
+struct EStepOut { double* post_mean; double* post_cov; };  // device, K x U and K x U x U
+
+// E step / VE step core on the resident dataset.  All pointers are device pointers except the
+// HP vectors of the mean processes.  info3: retries inv_k (max), post (max), tasks (max).
+static int dev_e_step(mb_context* c, int K, const mb_kernel* kern_k, const double* hp_k_host,
+                      const DevKern& kdi, const double* hp_i_dev, int64_t hp_stride,
+                      const double* m_k_dev, const double* tau_dev, const double* gridX, int U,
+                      const int32_t* gidx_override, double pen, double* post_mean, double* post_cov,
+                      int32_t* info3) {
+  DevKern kdk = make_devkern(kern_k);
+  const size_t UU = (size_t)U * U;
+  MB_TRY(c->ws1.ensure(U));
+  MB_TRY(c->inv0.ensure(K * UU * 8));
+  MB_TRY(c->post_inv.ensure(K * UU * 8));
+  MB_TRY(c->weighted.ensure((size_t)K * U * 8));
+  MB_TRY(c->retries.ensure(c->db.n_tasks * 4));
+  int max_r0 = 0, max_rp = 0;
+  // inverse prior covariances on st2 (independent of the task work on st)
+  for (int k = 0; k < K; ++k) {
+    LAUNCH(c, launch_dense_cov(kdk, hp_k_host + (size_t)k * kdk.n_hp, gridX, U, gridX, U, c->db.D, -1, 1,
+                               c->ws1.Kmat.as<double>(), U, 1, c->st2));
+    int r = 0;
+    int rc = dev_cholinv(c, c->ws1, c->ws1.Kmat.as<double>(), U, pen, c->st2, &r, nullptr, nullptr);
+    if (rc != 0) return rc;
+    if (r > max_r0) max_r0 = r;
+    CU(cudaMemcpyAsync(c->inv0.as<double>() + k * UU, c->ws1.A.p, UU * 8, cudaMemcpyDeviceToDevice, c->st2));
+  }
+  // task inverses + deterministic partial sums
+  int G = c->sm_count * task_max_ctas_per_sm(c->db.nmax, c->db.D);
+  if (G > c->db.n_tasks) G = (int)c->db.n_tasks;
+  const size_t cap = (size_t)2 << 30;
+  while (G > 1 && (size_t)G * K * UU * 8 > cap) G = (G + 1) / 2;
+  MB_TRY(c->part_inv.ensure((size_t)G * K * UU * 8));
+  MB_TRY(c->part_w.ensure((size_t)G * K * U * 8));
+  CU(cudaMemsetAsync(c->part_inv.p, 0, (size_t)G * K * UU * 8, c->st));
+  CU(cudaMemsetAsync(c->part_w.p, 0, (size_t)G * K * U * 8, c->st));
+  TaskInvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.db = c->db;
+  if (gidx_override) a.db.gidx = gidx_override;
+  a.kd = kdi; a.hp = hp_i_dev; a.hp_stride = hp_stride; a.pen = pen; a.K = K; a.tau = tau_dev; a.U = U;
+  a.part_inv = c->part_inv.as<double>(); a.part_w = c->part_w.as<double>();
+  a.retries = c->retries.as<int32_t>();
+  LAUNCH(c, launch_task_inverse(a, G, c->st));
+  CU(cudaStreamSynchronize(c->st2));
+  // post_inv_k = inv_k (+) sum_i tau_ik inv_i ; weighted_k = inv_k m_k (+) sum_i tau_ik inv_i y_i
+  if (c->world > 1) {
+    LAUNCH(c, launch_reduce_partials(K * UU, G, nullptr, c->part_inv.as<double>(), K * UU, c->post_inv.as<double>(), c->st));
+    LAUNCH(c, launch_reduce_partials((int64_t)K * U, G, nullptr, c->part_w.as<double>(), (int64_t)K * U, c->weighted.as<double>(), c->st));
+    MB_TRY(ctx_allreduce(c, c->post_inv.p, K * UU, c->st));
+    MB_TRY(ctx_allreduce(c, c->weighted.p, (int64_t)K * U, c->st));
+    LAUNCH(c, launch_axpby(K * UU, 1.0, c->inv0.as<double>(), 1.0, c->post_inv.as<double>(), c->post_inv.as<double>(), c->st));
+    for (int k = 0; k < K; ++k)
+      LAUNCH(c, launch_gemv(U, U, c->inv0.as<double>() + k * UU, U, m_k_dev + (size_t)k * U,
+                            c->weighted.as<double>() + (size_t)k * U, c->weighted.as<double>() + (size_t)k * U, c->st));
+  } else {
+    LAUNCH(c, launch_reduce_partials(K * UU, G, c->inv0.as<double>(), c->part_inv.as<double>(), K * UU, c->post_inv.as<double>(), c->st));
+    // weighted: start from inv_k m_k, then the partials in order
+    MB_TRY(c->sums.ensure((size_t)K * U * 8 + 256));
+    for (int k = 0; k < K; ++k)
+      LAUNCH(c, launch_gemv(U, U, c->inv0.as<double>() + k * UU, U, m_k_dev + (size_t)k * U, nullptr,
+                            c->sums.as<double>() + (size_t)k * U, c->st));
+    LAUNCH(c, launch_reduce_partials((int64_t)K * U, G, c->sums.as<double>(), c->part_w.as<double>(), (int64_t)K * U, c->weighted.as<double>(), c->st));
+  }
+  for (int k = 0; k < K; ++k) {
+    int r = 0;
+    int rc = dev_cholinv(c, c->ws1, c->post_inv.as<double>() + k * UU, U, pen, c->st, &r, nullptr, nullptr);
+    if (rc != 0) return rc;
+    if (r > max_rp) max_rp = r;
+    CU(cudaMemcpyAsync(post_cov + k * UU, c->ws1.A.p, UU * 8, cudaMemcpyDeviceToDevice, c->st));
+    LAUNCH(c, launch_gemv(U, U, post_cov + k * UU, U, c->weighted.as<double>() + (size_t)k * U, nullptr,
+                          post_mean + (size_t)k * U, c->st));
+  }
+  // task retry statistics
+  std::vector<int32_t> hr(c->db.n_tasks);
+  MB_TRY(d2h(hr.data(), c->retries.p, c->db.n_tasks * 4, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  int max_rt = 0;
+  for (int32_t v : hr) { if (v < 0) MB_FAIL(1, "chol_inv_jitter: no positive-definite jitter found for a task"); if (v > max_rt) max_rt = v; }
+  if (info3) { info3[0] = max_r0; info3[1] = max_rp; info3[2] = max_rt; }
+  return 0;
+}
+
+static TaskObjArgs make_obj_args(mb_context* c, const DevKern& kd, const double* hp_dev, int64_t stride,
+                                 int mode, int want_grad, double pen, int K, const double* mean,
+                                 const double* cov, const double* tau, double* f, double* g) {
+  TaskObjArgs a;
+  memset(&a, 0, sizeof(a));
+  a.db = c->db; a.kd = kd; a.hp = hp_dev; a.hp_stride = stride; a.mode = mode; a.want_grad = want_grad;
+  a.logdet_chol = c->logdet_chol; a.pen = pen;
+  a.hpst.K = K; a.hpst.U = c->U; a.hpst.mean = mean; a.hpst.cov = cov; a.hpst.tau = tau;
+  a.f = f; a.g = g; a.retries = nullptr;
+  return a;
+}
+
+// Sum over tasks of a task objective (+ gradient) with one shared HP vector: returns f and g on
+// the host.  Used by the shared-HP M steps and by the monitoring sums.
+static int shared_obj_eval(mb_context* c, TaskObjArgs a, const double* hp_host, int P, int want_grad,
+                           double* f_out, double* g_out) {
+  MB_TRY(c->hp_i.ensure(MB_MAX_HP * 8));
+  MB_TRY(h2d(c->hp_i.p, hp_host, P * 8, c->st));
+  a.hp = c->hp_i.as<double>(); a.hp_stride = 0; a.want_grad = want_grad;
+  MB_TRY(launch_obj(c, a, (int)c->db.n_tasks, c->st));
+  MB_TRY(c->sums.ensure(64 * 8));
+  LAUNCH(c, launch_sum_sequential(a.f, c->db.n_tasks, 1, c->sums.as<double>(), c->st));
+  if (want_grad) LAUNCH(c, launch_colsum_sequential(a.g, c->db.n_tasks, P, c->sums.as<double>() + 1, c->st));
+  MB_TRY(ctx_allreduce(c, c->sums.p, 1 + (want_grad ? P : 0), c->st));
+  MB_TRY(d2h(c->h_pin, c->sums.p, (1 + P) * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  *f_out = c->h_pin[0];
+  if (want_grad) for (int p = 0; p < P; ++p) g_out[p] = c->h_pin[1 + p];
+  return 0;
+}
+
+// Lock-step batched L-BFGS-B over all tasks on the device (`a` describes the objective) while an
+// optional list of single problems (mean / cluster processes) is optimised by host state
+// machines whose evaluations run on st2, overlapped with the task launches.
+struct SingleProblem {
+  LbfgsbState s;
+  DevKern kd;
+  const double* X; int n; int D;
+  const double* y; const double* mean; const double* S;
+  int evals = 0;
+};
+
+static int run_single_eval(mb_context* c, SingleProblem& sp, double pen, double* f, double* g) {
+  double* hres = c->h_pin + 32;
+  int* hinfo = c->h_pin_i + 8;
+  MB_TRY(dense_obj_enqueue(c, c->ws0, sp.kd, sp.s.x, sp.X, sp.n, sp.D, sp.y, sp.mean, sp.S, pen, 1,
+                           c->st2, hres, hinfo));
+  CU(cudaStreamSynchronize(c->st2));
+  sp.evals++;
+  *f = (hinfo[0] < 0) ? NAN : hres[0];
+  for (int p = 0; p < sp.kd.n_hp; ++p) g[p] = hres[1 + p];
+  return 0;
+}
+
+static int optimise(mb_context* c, std::vector<SingleProblem>& singles, bool tasks_on,
+                    TaskObjArgs a, double* hp_i_dev, int P_i, double pen, int64_t* stats) {
+  const int64_t M = c->db.n_tasks;
+  int rounds = 0;
+  bool tasks_active = tasks_on;
+  if (tasks_on) {
+    MB_TRY(c->lb.ensure(M * sizeof(LbfgsbState)));
+    MB_TRY(c->counters.ensure(4096 * sizeof(int)));
+    CU(cudaMemsetAsync(c->counters.p, 0, 4096 * sizeof(int), c->st));
+    LAUNCH(c, launch_lbfgsb_init(c->lb.as<LbfgsbState>(), M, P_i, hp_i_dev, P_i, 1e13, 0.0, 25, c->st));
+    a.lb = c->lb.as<LbfgsbState>();
+    a.hp = nullptr;
+    a.want_grad = 1;
+  }
+  size_t cur = 0;  // singles are optimised one after the other (they share ws0)
+  while (tasks_active || cur < singles.size()) {
+    if (tasks_active) {
+      if (rounds >= 4095) MB_FAIL(2, "L-BFGS-B lock-step did not terminate");
+      MB_TRY(launch_obj(c, a, (int)M, c->st, true));
+      LAUNCH(c, launch_lbfgsb_advance(c->lb.as<LbfgsbState>(), M, P_i, a.f, a.g, c->counters.as<int>() + rounds, c->st));
+      MB_TRY(d2h(c->h_pin_i, c->counters.as<int>() + rounds, sizeof(int), c->st));
+    }
+    if (cur < singles.size()) {
+      SingleProblem& sp = singles[cur];
+      if (!sp.s.active) { cur++; }
+      else {
+        double f, g[MB_MAX_HP];
+        MB_TRY(run_single_eval(c, sp, pen, &f, g));
+        lb_advance(&sp.s, f, g);
+        if (!sp.s.active) cur++;
+      }
+    }
+    if (tasks_active) {
+      CU(cudaStreamSynchronize(c->st));
+      rounds++;
+      if (c->h_pin_i[0] == 0) tasks_active = false;
+    }
+  }
+  if (tasks_on) {
+    MB_TRY(c->fails.ensure(M * 4));
+    MB_TRY(c->nfgv.ensure(M * 4));
+    LAUNCH(c, launch_lbfgsb_export(c->lb.as<LbfgsbState>(), M, P_i, hp_i_dev, P_i, c->fails.as<int>(), c->nfgv.as<int>(), c->st));
+    std::vector<int> hf(M), hn(M);
+    MB_TRY(d2h(hf.data(), c->fails.p, M * 4, c->st));
+    MB_TRY(d2h(hn.data(), c->nfgv.p, M * 4, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    int64_t tot = 0, bad = 0;
+    for (int64_t t = 0; t < M; ++t) { tot += hn[t]; if (hf[t] != 0) bad++; }
+    if (stats) { stats[1] = rounds; stats[2] = tot; stats[3] = bad; }
+    c->prof_evals += tot;
+  }
+  return 0;
+}
+
+// ---- Magma -----------------------------------------------------------------------------------
+// device state of one EM step: hp_i table, m_0, post_mean, post_cov
+static int ensure_em_buffers(mb_context* c, int K) {
+  const size_t UU = (size_t)c->U * c->U;
+  MB_TRY(c->pm.ensure((size_t)K * c->U * 8));
+  MB_TRY(c->pc.ensure(K * UU * 8));
+  MB_TRY(c->m0.ensure((size_t)K * c->U * 8));
+  MB_TRY(c->f_t.ensure((size_t)c->db.n_tasks * (K > 1 ? K : 1) * 8));
+  MB_TRY(c->g_t.ensure((size_t)c->db.n_tasks * MB_MAX_HP * 8));
+  MB_TRY(c->ws0.ensure(c->U));
+  return 0;
+}
+
+extern "C" int mb_e_step(mb_context* c, const mb_kernel* kern_0, const double* hp_0,
+                         const mb_kernel* kern_i, const double* hp_i, int hp_i_shared,
+                         const double* m_0, double pen_diag, double* post_mean, double* post_cov,
+                         int32_t* info) {
+  MB_TRY(need_db(c, true));
+  if (!kern_0 || !hp_0 || !kern_i || !hp_i || !m_0 || !post_mean || !post_cov) MB_FAIL(-1, "null argument");
+  MB_TRY(ensure_em_buffers(c, 1));
+  int64_t stride;
+  MB_TRY(put_hp_i(c, kern_i, hp_i, hp_i_shared, &stride));
+  MB_TRY(h2d(c->m0.p, m_0, (size_t)c->U * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  MB_TRY(dev_e_step(c, 1, kern_0, hp_0, make_devkern(kern_i), c->hp_i.as<double>(), stride,
+                    c->m0.as<double>(), nullptr, c->d_gridX.as<double>(), c->U, nullptr, pen_diag,
+                    c->pm.as<double>(), c->pc.as<double>(), info));
+  MB_TRY(d2h(post_mean, c->pm.p, (size_t)c->U * 8, c->st));
+  MB_TRY(d2h(post_cov, c->pc.p, (size_t)c->U * c->U * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+extern "C" int mb_hyperposterior(mb_context* c, const mb_kernel* kern_0, const double* hp_0,
+                                 const mb_kernel* kern_i, const double* hp_i, int hp_i_shared,
+                                 int32_t n_grid, const double* grid_X, const int32_t* grid_index,
+                                 const double* m_0, double pen_diag, double* post_mean,
+                                 double* post_cov) {
+  MB_TRY(check_ctx(c));
+  if (!c->have_db) MB_FAIL(-1, "no dataset uploaded");
+  if (c->db.nmax > TK_MAXN) MB_FAIL(-4, "a task has more than 96 points: the large-task path is not built yet");
+  if (!grid_X || !grid_index || n_grid < 1 || !m_0 || !post_mean || !post_cov) MB_FAIL(-1, "bad argument");
+  for (int64_t r = 0; r < c->n_rows; ++r)
+    if (grid_index[r] < 0 || grid_index[r] >= n_grid) MB_FAIL(-1, "grid_index out of range");
+  const size_t UU = (size_t)n_grid * n_grid;
+  DBuf gX, gi, pm, pc, m0;
+  int rc = 0;
+  if (gX.ensure((size_t)n_grid * c->db.D * 8) || gi.ensure(c->n_rows * 4) || pm.ensure((size_t)n_grid * 8) ||
+      pc.ensure(UU * 8) || m0.ensure((size_t)n_grid * 8)) rc = -3;
+  if (!rc) {
+    cudaMemcpyAsync(gX.p, grid_X, (size_t)n_grid * c->db.D * 8, cudaMemcpyHostToDevice, c->st);
+    cudaMemcpyAsync(gi.p, grid_index, c->n_rows * 4, cudaMemcpyHostToDevice, c->st);
+    cudaMemcpyAsync(m0.p, m_0, (size_t)n_grid * 8, cudaMemcpyHostToDevice, c->st);
+    int64_t stride;
+    rc = put_hp_i(c, kern_i, hp_i, hp_i_shared, &stride);
+    if (!rc) rc = (cudaStreamSynchronize(c->st) == cudaSuccess) ? 0 : -2;
+    if (!rc) rc = dev_e_step(c, 1, kern_0, hp_0, make_devkern(kern_i), c->hp_i.as<double>(), stride,
+                             m0.as<double>(), nullptr, gX.as<double>(), n_grid, gi.as<int32_t>(), pen_diag,
+                             pm.as<double>(), pc.as<double>(), nullptr);
+    if (!rc) {
+      cudaMemcpyAsync(post_mean, pm.p, (size_t)n_grid * 8, cudaMemcpyDeviceToHost, c->st);
+      cudaMemcpyAsync(post_cov, pc.p, UU * 8, cudaMemcpyDeviceToHost, c->st);
+      if (cudaStreamSynchronize(c->st) != cudaSuccess) { mb_set_error(__FILE__, __LINE__, "copy back failed"); rc = -2; }
+    }
+  }
+  gX.release(); gi.release(); pm.release(); pc.release(); m0.release();
+  return rc;
+}
+
+extern "C" int mb_logL_GP_mod_tasks(mb_context* c, const mb_kernel* kern_i, const double* hp_i,
+                                    int hp_i_shared, const double* post_mean, const double* post_cov,
+                                    double pen_diag, double* f, double* g, int32_t* retries) {
+  MB_TRY(need_db(c, true));
+  if (!kern_i || !hp_i || !post_mean || !post_cov || !f) MB_FAIL(-1, "null argument");
+  MB_TRY(ensure_em_buffers(c, 1));
+  int64_t stride;
+  MB_TRY(put_hp_i(c, kern_i, hp_i, hp_i_shared, &stride));
+  MB_TRY(h2d(c->pm.p, post_mean, (size_t)c->U * 8, c->st));
+  MB_TRY(h2d(c->pc.p, post_cov, (size_t)c->U * c->U * 8, c->st));
+  DevKern kd = make_devkern(kern_i);
+  TaskObjArgs a = make_obj_args(c, kd, c->hp_i.as<double>(), stride, TK_OBJ_MOD, g != nullptr, pen_diag, 1,
+                                c->pm.as<double>(), c->pc.as<double>(), nullptr, c->f_t.as<double>(),
+                                c->g_t.as<double>());
+  MB_TRY(c->retries.ensure(c->db.n_tasks * 4));
+  a.retries = c->retries.as<int32_t>();
+  MB_TRY(launch_obj(c, a, (int)c->db.n_tasks, c->st));
+  MB_TRY(d2h(f, c->f_t.p, c->db.n_tasks * 8, c->st));
+  if (g) MB_TRY(d2h(g, c->g_t.p, (size_t)c->db.n_tasks * kd.n_hp * 8, c->st));
+  if (retries) MB_TRY(d2h(retries, c->retries.p, c->db.n_tasks * 4, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+extern "C" int mb_logL_GP_mod(mb_context* c, const mb_kernel* k, const double* hp, const double* x,
+                              int n, int d, const double* y, const double* mean,
+                              const double* post_cov, double pen_diag, double* f, double* g) {
+  MB_TRY(check_ctx(c));
+  if (!k || !hp || !x || !y || !mean || !post_cov || !f || n < 1 || d < 1) MB_FAIL(-1, "bad argument");
+  MB_TRY(c->ws0.ensure(n));
+  MB_TRY(c->scratch.ensure(((size_t)n * d + 2 * (size_t)n) * 8 + 64));
+  double* dX = c->scratch.as<double>();
+  double* dy = dX + (size_t)n * d;
+  double* dm = dy + n;
+  MB_TRY(h2d(dX, x, (size_t)n * d * 8, c->st2));
+  MB_TRY(h2d(dy, y, (size_t)n * 8, c->st2));
+  MB_TRY(h2d(dm, mean, (size_t)n * 8, c->st2));
+  MB_TRY(h2d(c->ws0.S.p, post_cov, (size_t)n * n * 8, c->st2));
+  double* hres = c->h_pin + 32;
+  int* hinfo = c->h_pin_i + 8;
+  MB_TRY(dense_obj_enqueue(c, c->ws0, make_devkern(k), hp, dX, n, d, dy, dm, c->ws0.S.as<double>(),
+                           pen_diag, g != nullptr, c->st2, hres, hinfo));
+  CU(cudaStreamSynchronize(c->st2));
+  if (hinfo[0] < 0) MB_FAIL(1, "chol_inv_jitter: no positive-definite jitter found");
+  *f = hres[0];
+  if (g) for (int p = 0; p < k->n_hp; ++p) g[p] = hres[1 + p];
+  return 0;
+}
+
+// M step on device state: hp_0 (host vector, in/out), hp_i table on device (in/out)
+static int dev_m_step(mb_context* c, const mb_kernel* kern_0, double* hp_0, const mb_kernel* kern_i,
+                      double* hp_i_dev, int shared_hp, const double* m0_dev, const double* pm_dev,
+                      const double* pc_dev, double pen, int64_t* stats) {
+  DevKern kd0 = make_devkern(kern_0), kdi = make_devkern(kern_i);
+  if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+  std::vector<SingleProblem> singles(1);
+  SingleProblem& sp = singles[0];
+  sp.kd = kd0; sp.X = c->d_gridX.as<double>(); sp.n = c->U; sp.D = c->db.D;
+  sp.y = pm_dev; sp.mean = m0_dev; sp.S = pc_dev;
+  lb_init(&sp.s, kd0.n_hp, hp_0, 1e13, 0.0, 25);
+  TaskObjArgs a = make_obj_args(c, kdi, hp_i_dev, kdi.n_hp, TK_OBJ_MOD, 1, pen, 1, pm_dev, pc_dev, nullptr,
+                                c->f_t.as<double>(), c->g_t.as<double>());
+  if (!shared_hp) {
+    MB_TRY(optimise(c, singles, true, a, hp_i_dev, kdi.n_hp, pen, stats));
+  } else {
+    MB_TRY(optimise(c, singles, false, a, hp_i_dev, kdi.n_hp, pen, stats));
+    // one optimisation of the summed objective (em-magma.R:172-196), HPs of the first task
+    LbfgsbState s;
+    double x0[MB_MAX_HP];
+    MB_TRY(d2h(x0, hp_i_dev, kdi.n_hp * 8, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    lb_init(&s, kdi.n_hp, x0, 1e13, 0.0, 25);
+    int evals = 0;
+    while (s.active) {
+      double f, g[MB_MAX_HP];
+      MB_TRY(shared_obj_eval(c, a, s.x, kdi.n_hp, 1, &f, g));
+      lb_advance(&s, f, g);
+      evals++;
+    }
+    std::vector<double> tab((size_t)c->db.n_tasks * kdi.n_hp);
+    for (int64_t t = 0; t < c->db.n_tasks; ++t)
+      for (int p = 0; p < kdi.n_hp; ++p) tab[t * kdi.n_hp + p] = s.x[p];
+    MB_TRY(h2d(hp_i_dev, tab.data(), tab.size() * 8, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    if (stats) { stats[1] = evals; stats[2] = (int64_t)evals * c->db.n_tasks; stats[3] = s.fail != 0; }
+  }
+  for (int p = 0; p < kd0.n_hp; ++p) hp_0[p] = sp.s.x[p];
+  if (stats) stats[0] = sp.evals;
+  return 0;
+}
+
+static int dev_logL_monitoring(mb_context* c, const mb_kernel* kern_0, const double* hp_0,
+                               const mb_kernel* kern_i, const double* hp_i_dev, int64_t stride,
+                               const double* m0_dev, const double* pm_dev, const double* pc_dev,
+                               double pen, double* logL) {
+  DevKern kd0 = make_devkern(kern_0), kdi = make_devkern(kern_i);
+  double* hres = c->h_pin + 32;
+  int* hinfo = c->h_pin_i + 8;
+  MB_TRY(dense_obj_enqueue(c, c->ws0, kd0, hp_0, c->d_gridX.as<double>(), c->U, c->db.D, pm_dev, m0_dev,
+                           pc_dev, pen, 0, c->st2, hres, hinfo));
+  TaskObjArgs a = make_obj_args(c, kdi, hp_i_dev, stride, TK_OBJ_MOD, 0, pen, 1, pm_dev, pc_dev, nullptr,
+                                c->f_t.as<double>(), c->g_t.as<double>());
+  MB_TRY(launch_obj(c, a, (int)c->db.n_tasks, c->st));
+  MB_TRY(c->sums.ensure(64 * 8));
+  LAUNCH(c, launch_sum_sequential(a.f, c->db.n_tasks, 1, c->sums.as<double>(), c->st));
+  MB_TRY(ctx_allreduce(c, c->sums.p, 1, c->st));
+  // det term: chol(post_cov) without jitter (likelihoods.R:303-307)
+  LAUNCH(c, launch_dense_chol_logdiag(pc_dev, c->ws1.A.as<double>(), c->U, c->ws1.info.as<int>(),
+                                      c->sums.as<double>() + 8, c->st));
+  MB_TRY(d2h(c->h_pin, c->sums.p, 16 * 8, c->st));
+  MB_TRY(d2h(c->h_pin_i, c->ws1.info.p, sizeof(int), c->st));
+  CU(cudaStreamSynchronize(c->st));
+  CU(cudaStreamSynchronize(c->st2));
+  if (c->h_pin_i[0] != 0) MB_FAIL(1, "chol(post_cov) failed in logL_monitoring (no jitter is applied there)");
+  double ll_0 = (hinfo[0] < 0) ? NAN : hres[0];
+  *logL = -ll_0 - c->h_pin[0] + c->h_pin[8];
+  return 0;
+}
+
+extern "C" int mb_m_step(mb_context* c, const mb_kernel* kern_0, double* hp_0, const mb_kernel* kern_i,
+                         double* hp_i, int shared_hp, const double* m_0, const double* post_mean,
+                         const double* post_cov, double pen_diag, int64_t* stats) {
+  MB_TRY(need_db(c, true));
+  if (!kern_0 || !hp_0 || !kern_i || !hp_i || !m_0 || !post_mean || !post_cov) MB_FAIL(-1, "null argument");
+  MB_TRY(ensure_em_buffers(c, 1));
+  const int P = kern_i->n_hp;
+  MB_TRY(c->hp_k.ensure((size_t)c->db.n_tasks * P * 8));
+  MB_TRY(h2d(c->hp_k.p, hp_i, (size_t)c->db.n_tasks * P * 8, c->st));
+  MB_TRY(h2d(c->m0.p, m_0, (size_t)c->U * 8, c->st));
+  MB_TRY(h2d(c->pm.p, post_mean, (size_t)c->U * 8, c->st));
+  MB_TRY(h2d(c->pc.p, post_cov, (size_t)c->U * c->U * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  MB_TRY(dev_m_step(c, kern_0, hp_0, kern_i, c->hp_k.as<double>(), shared_hp, c->m0.as<double>(),
+                    c->pm.as<double>(), c->pc.as<double>(), pen_diag, stats));
+  MB_TRY(d2h(hp_i, c->hp_k.p, (size_t)c->db.n_tasks * P * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+extern "C" int mb_logL_monitoring(mb_context* c, const mb_kernel* kern_0, const double* hp_0,
+                                  const mb_kernel* kern_i, const double* hp_i, int hp_i_shared,
+                                  const double* m_0, const double* post_mean, const double* post_cov,
+                                  double pen_diag, double* logL) {
+  MB_TRY(need_db(c, true));
+  if (!kern_0 || !hp_0 || !kern_i || !hp_i || !m_0 || !post_mean || !post_cov || !logL) MB_FAIL(-1, "null argument");
+  MB_TRY(ensure_em_buffers(c, 1));
+  MB_TRY(c->ws1.ensure(c->U));
+  int64_t stride;
+  MB_TRY(put_hp_i(c, kern_i, hp_i, hp_i_shared, &stride));
+  MB_TRY(h2d(c->m0.p, m_0, (size_t)c->U * 8, c->st));
+  MB_TRY(h2d(c->pm.p, post_mean, (size_t)c->U * 8, c->st));
+  MB_TRY(h2d(c->pc.p, post_cov, (size_t)c->U * c->U * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return dev_logL_monitoring(c, kern_0, hp_0, kern_i, c->hp_i.as<double>(), stride, c->m0.as<double>(),
+                             c->pm.as<double>(), c->pc.as<double>(), pen_diag, logL);
+}
+
+// e_step + m_step + logL_monitoring with every intermediate kept on the device
+static int dev_em_step(mb_context* c, const mb_kernel* kern_0, double* hp_0, const mb_kernel* kern_i,
+                       double* hp_i_dev, int shared_hp, const double* m0_dev, double pen, double* logL,
+                       int64_t* stats) {
+  DevKern kdi = make_devkern(kern_i);
+  MB_TRY(dev_e_step(c, 1, kern_0, hp_0, kdi, hp_i_dev, kdi.n_hp, m0_dev, nullptr, c->d_gridX.as<double>(),
+                    c->U, nullptr, pen, c->pm.as<double>(), c->pc.as<double>(), nullptr));
+  MB_TRY(dev_m_step(c, kern_0, hp_0, kern_i, hp_i_dev, shared_hp, m0_dev, c->pm.as<double>(),
+                    c->pc.as<double>(), pen, stats));
+  MB_TRY(dev_logL_monitoring(c, kern_0, hp_0, kern_i, hp_i_dev, kdi.n_hp, m0_dev, c->pm.as<double>(),
+                             c->pc.as<double>(), pen, logL));
+  return 0;
+}
+
+extern "C" int mb_em_step(mb_context* c, const mb_kernel* kern_0, double* hp_0, const mb_kernel* kern_i,
+                          double* hp_i, int shared_hp, const double* m_0, double pen_diag, double* logL,
+                          double* post_mean, double* post_cov, int64_t* stats) {
+  MB_TRY(need_db(c, true));
+  if (!kern_0 || !hp_0 || !kern_i || !hp_i || !m_0 || !logL) MB_FAIL(-1, "null argument");
+  MB_TRY(ensure_em_buffers(c, 1));
+  const int P = kern_i->n_hp;
+  MB_TRY(c->hp_k.ensure((size_t)c->db.n_tasks * P * 8));
+  MB_TRY(h2d(c->hp_k.p, hp_i, (size_t)c->db.n_tasks * P * 8, c->st));
+  MB_TRY(h2d(c->m0.p, m_0, (size_t)c->U * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  MB_TRY(dev_em_step(c, kern_0, hp_0, kern_i, c->hp_k.as<double>(), shared_hp, c->m0.as<double>(), pen_diag, logL, stats));
+  MB_TRY(d2h(hp_i, c->hp_k.p, (size_t)c->db.n_tasks * P * 8, c->st));
+  if (post_mean) MB_TRY(d2h(post_mean, c->pm.p, (size_t)c->U * 8, c->st));
+  if (post_cov) MB_TRY(d2h(post_cov, c->pc.p, (size_t)c->U * c->U * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+extern "C" int mb_train_magma(mb_context* c, const mb_kernel* kern_0, double* hp_0, const mb_kernel* kern_i,
+                              double* hp_i, int shared_hp, const double* m_0, double pen_diag,
+                              int n_iter_max, double cv_threshold, double* seq_logL, int32_t* n_iter,
+                              int32_t* converged, double* post_mean, double* post_cov) {
+  MB_TRY(need_db(c, true));
+  if (!kern_0 || !hp_0 || !kern_i || !hp_i || !m_0 || !seq_logL || !n_iter || !converged) MB_FAIL(-1, "null argument");
+  MB_TRY(ensure_em_buffers(c, 1));
+  const int P = kern_i->n_hp, P0 = kern_0->n_hp;
+  const size_t tab = (size_t)c->db.n_tasks * P * 8;
+  MB_TRY(c->hp_k.ensure(2 * tab));
+  double* cur = c->hp_k.as<double>();
+  double* nxt = cur + (size_t)c->db.n_tasks * P;
+  MB_TRY(h2d(cur, hp_i, tab, c->st));
+  MB_TRY(h2d(c->m0.p, m_0, (size_t)c->U * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  double ll = -INFINITY;
+  *converged = 0;
+  *n_iter = 0;
+  std::vector<double> htab((size_t)c->db.n_tasks * P);
+  for (int it = 1; it <= n_iter_max; ++it) {
+    // work on a copy so that a NaN M step leaves the last valid HPs in place (training.R:956-963)
+    CU(cudaMemcpyAsync(nxt, cur, tab, cudaMemcpyDeviceToDevice, c->st));
+    double h0[MB_MAX_HP];
+    for (int p = 0; p < P0; ++p) h0[p] = hp_0[p];
+    double new_ll;
+    MB_TRY(dev_em_step(c, kern_0, h0, kern_i, nxt, shared_hp, c->m0.as<double>(), pen_diag, &new_ll, nullptr));
+    MB_TRY(d2h(htab.data(), nxt, tab, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    bool bad = false;
+    for (int p = 0; p < P0; ++p) if (isnan(h0[p])) bad = true;
+    for (double v : htab) if (isnan(v)) { bad = true; break; }
+    if (bad) break;
+    double diff = new_ll - ll;
+    if (isnan(diff)) diff = -INFINITY;
+    for (int p = 0; p < P0; ++p) hp_0[p] = h0[p];
+    std::swap(cur, nxt);
+    ll = new_ll;
+    seq_logL[it - 1] = ll;
+    *n_iter = it;
+    double eps = diff / fabs(ll);
+    if (isnan(eps)) eps = 1.0;
+    if (fabs(eps) < cv_threshold) { *converged = 1; break; }
+  }
+  MB_TRY(d2h(hp_i, cur, tab, c->st));
+  if (post_mean) MB_TRY(d2h(post_mean, c->pm.p, (size_t)c->U * 8, c->st));
+  if (post_cov) MB_TRY(d2h(post_cov, c->pc.p, (size_t)c->U * c->U * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+// ---- resident state, timers, profiling -----------------------------------------------------------
+extern "C" int mb_set_state(mb_context* c, const mb_kernel* kern_0, const double* hp_0,
+                            const mb_kernel* kern_i, const double* hp_i, const double* m_0) {
+  MB_TRY(need_db(c, true));
+  if (!kern_0 || !hp_0 || !kern_i || !hp_i || !m_0) MB_FAIL(-1, "null argument");
+  MB_TRY(ensure_em_buffers(c, 1));
+  const size_t tab = (size_t)c->db.n_tasks * kern_i->n_hp * 8;
+  MB_TRY(c->st_hp_i0.ensure(tab));
+  MB_TRY(c->st_hp_i.ensure(tab));
+  MB_TRY(h2d(c->st_hp_i0.p, hp_i, tab, c->st));
+  MB_TRY(h2d(c->st_hp_i.p, hp_i, tab, c->st));
+  MB_TRY(h2d(c->m0.p, m_0, (size_t)c->U * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  for (int p = 0; p < kern_0->n_hp; ++p) c->st_hp_00[p] = c->st_hp_0[p] = hp_0[p];
+  c->have_state = true;
+  return 0;
+}
+
+extern "C" int mb_em_step_resident(mb_context* c, const mb_kernel* kern_0, const mb_kernel* kern_i,
+                                   int shared_hp, double pen_diag, int restart, double* logL,
+                                   int64_t* stats) {
+  MB_TRY(need_db(c, true));
+  if (!c->have_state) MB_FAIL(-1, "mb_set_state was not called");
+  if (!kern_0 || !kern_i || !logL) MB_FAIL(-1, "null argument");
+  const size_t tab = (size_t)c->db.n_tasks * kern_i->n_hp * 8;
+  if (restart) {
+    CU(cudaMemcpyAsync(c->st_hp_i.p, c->st_hp_i0.p, tab, cudaMemcpyDeviceToDevice, c->st));
+    for (int p = 0; p < kern_0->n_hp; ++p) c->st_hp_0[p] = c->st_hp_00[p];
+  }
+  return dev_em_step(c, kern_0, c->st_hp_0, kern_i, c->st_hp_i.as<double>(), shared_hp, c->m0.as<double>(),
+                     pen_diag, logL, stats);
+}
+
+extern "C" int mb_get_state(mb_context* c, const mb_kernel* kern_0, double* hp_0, const mb_kernel* kern_i,
+                            double* hp_i) {
+  MB_TRY(need_db(c, true));
+  if (!c->have_state) MB_FAIL(-1, "mb_set_state was not called");
+  for (int p = 0; p < kern_0->n_hp; ++p) hp_0[p] = c->st_hp_0[p];
+  MB_TRY(d2h(hp_i, c->st_hp_i.p, (size_t)c->db.n_tasks * kern_i->n_hp * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+extern "C" int mb_timer(mb_context* c, int which) {
+  MB_TRY(check_ctx(c));
+  CU(cudaEventRecord(which ? c->ev_t1 : c->ev_t0, c->st));
+  return 0;
+}
+extern "C" int mb_timer_ms(mb_context* c, double* ms) {
+  MB_TRY(check_ctx(c));
+  float f = 0;
+  CU(cudaEventSynchronize(c->ev_t1));
+  CU(cudaEventElapsedTime(&f, c->ev_t0, c->ev_t1));
+  *ms = f;
+  return 0;
+}
+extern "C" int mb_profile(mb_context* c, int enable) {
+  MB_TRY(check_ctx(c));
+  c->prof_on = enable != 0;
+  return 0;
+}
+extern "C" int mb_profile_read(mb_context* c, double* out3) {
+  MB_TRY(check_ctx(c));
+  MB_TRY(prof_collect(c));
+  out3[0] = c->prof_ms; out3[1] = (double)c->prof_launches; out3[2] = (double)c->prof_evals;
+  c->prof_ms = 0; c->prof_launches = 0; c->prof_evals = 0;
+  return 0;
+}
+extern "C" int mb_flush_l2(mb_context* c, int64_t bytes) {
+  MB_TRY(check_ctx(c));
+  static thread_local DBuf flush;
+  MB_TRY(flush.ensure((size_t)bytes));
+  CU(cudaMemsetAsync(flush.p, 1, (size_t)bytes, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+// ---- pred_magma --------------------------------------------------------------------------------
+cudaError_t launch_pred_var(const DevKern& kd, const double* hp_host, const double* xp, int np, int D,
+                            const double* sdiag, const double* C, const double* GC, int no,
+                            double noise, double* out, cudaStream_t st);
+
+extern "C" int mb_pred_magma(mb_context* c, const mb_kernel* k, const double* hp, const double* x_obs,
+                             int n_obs, const double* y_obs, const double* x_pred, int n_pred, int d,
+                             const double* mean_obs, const double* mean_pred, const double* cov_obs,
+                             const double* cov_pred, const double* cov_crossed, double pen_diag,
+                             double* pred_mean, double* pred_var, double* pred_cov) {
+  MB_TRY(check_ctx(c));
+  if (!k || !hp || !x_obs || !y_obs || !x_pred || !mean_obs || !mean_pred || !cov_obs || !cov_pred ||
+      !cov_crossed || !pred_mean || !pred_var || n_obs < 1 || n_pred < 1 || d < 1)
+    MB_FAIL(-1, "bad argument");
+  DevKern kd = make_devkern(k);
+  const int no = n_obs, np = n_pred;
+  const bool full = pred_cov != nullptr;
+  MB_TRY(c->ws1.ensure(no));
+  size_t need = ((size_t)no * d + (size_t)np * d + 3 * (size_t)no + 4 * (size_t)np + (size_t)no * no +
+                 3 * (size_t)no * np + (full ? 2 * (size_t)np * np : 0)) * 8 + 256;
+  MB_TRY(c->scratch.ensure(need));
+  double* p = c->scratch.as<double>();
+  double* dXo = p; p += (size_t)no * d;
+  double* dXp = p; p += (size_t)np * d;
+  double* dyo = p; p += no;
+  double* dmo = p; p += no;
+  double* dvec = p; p += no;
+  double* dmp = p; p += np;
+  double* dmean = p; p += np;
+  double* dbase = p; p += np;                 // diag(K_pred + S_pred)
+  double* dvar = p; p += np;
+  double* dSo = p; p += (size_t)no * no;
+  double* dC = p; p += (size_t)no * np;       // C(i,j) at i + j*no (column-major, like the host block)
+  double* dCh = p; p += (size_t)no * np;
+  double* dGC = p; p += (size_t)no * np;      // Gamma^{-1} C, row-major no x np
+  double* dKp = full ? p : nullptr; p += full ? (size_t)np * np : 0;
+  double* dSp = full ? p : nullptr;
+  cudaStream_t s = c->st;
+  MB_TRY(h2d(dXo, x_obs, (size_t)no * d * 8, s));
+  MB_TRY(h2d(dXp, x_pred, (size_t)np * d * 8, s));
+  MB_TRY(h2d(dyo, y_obs, (size_t)no * 8, s));
+  MB_TRY(h2d(dmo, mean_obs, (size_t)no * 8, s));
+  MB_TRY(h2d(dmp, mean_pred, (size_t)np * 8, s));
+  MB_TRY(h2d(dSo, cov_obs, (size_t)no * no * 8, s));
+  MB_TRY(h2d(dCh, cov_crossed, (size_t)no * np * 8, s));
+  std::vector<double> sdiag;
+  if (full) MB_TRY(h2d(dSp, cov_pred, (size_t)np * np * 8, s));
+  else {
+    sdiag.resize(np);
+    for (int j = 0; j < np; ++j) sdiag[j] = cov_pred[(size_t)j * np + j];
+    MB_TRY(h2d(dvar, sdiag.data(), (size_t)np * 8, s));
+  }
+  // Gamma = K(obs; hp with noise) + S_obs  (prediction.R:1147)
+  LAUNCH(c, launch_dense_cov(kd, hp, dXo, no, dXo, no, d, -1, 1, c->ws1.Kmat.as<double>(), no, 1, s));
+  LAUNCH(c, launch_axpby((int64_t)no * no, 1.0, c->ws1.Kmat.as<double>(), 1.0, dSo, c->ws1.Kmat.as<double>(), s));
+  MB_TRY(dev_cholinv(c, c->ws1, c->ws1.Kmat.as<double>(), no, pen_diag, s, nullptr, nullptr, nullptr));
+  const double* Ginv = c->ws1.A.as<double>();
+  // C = K(obs, pred; noise removed) + S_crossed  (prediction.R:1174-1181)
+  LAUNCH(c, launch_dense_cov(kd, hp, dXo, no, dXp, np, d, -1, 0, dC, 1, no, s));
+  LAUNCH(c, launch_axpby((int64_t)no * np, 1.0, dC, 1.0, dCh, dC, s));
+  // mean = mu_pred + C' Gamma^{-1} (y - mu_obs)  (prediction.R:1184-1186)
+  LAUNCH(c, launch_axpby(no, 1.0, dyo, -1.0, dmo, dmo, s));
+  LAUNCH(c, launch_gemv(no, no, Ginv, no, dmo, nullptr, dvec, s));
+  LAUNCH(c, launch_gemm(np, 1, no, dC, no, 1, dvec, 1, 1, dmean, 1, 1.0, dmp, 1.0, s));
+  LAUNCH(c, launch_gemm(no, np, no, Ginv, no, 1, dC, 1, no, dGC, np, 1.0, nullptr, 0.0, s));
+  const double noise = kd.has_noise ? exp(hp[kd.n_hp - 1]) : 0.0;
+  if (full) {
+    // cov = K(pred) + S_pred - C' Gamma^{-1} C  (prediction.R:1189)
+    LAUNCH(c, launch_dense_cov(kd, hp, dXp, np, dXp, np, d, -1, 0, dKp, np, 1, s));
+    LAUNCH(c, launch_axpby((int64_t)np * np, 1.0, dKp, 1.0, dSp, dKp, s));
+    LAUNCH(c, launch_gemm(np, np, no, dC, no, 1, dGC, np, 1, dKp, np, -1.0, dKp, 1.0, s));
+    LAUNCH(c, launch_diag(np, dKp, np, noise, dvar, s));
+    MB_TRY(d2h(pred_cov, dKp, (size_t)np * np * 8, s));
+  } else {
+    // only the diagonal of the same expression
+    LAUNCH(c, launch_pred_var(kd, hp, dXp, np, d, dvar, dC, dGC, no, noise, dbase, s));
+    dvar = dbase;
+  }
+  MB_TRY(d2h(pred_mean, dmean, (size_t)np * 8, s));
+  MB_TRY(d2h(pred_var, dvar, (size_t)np * 8, s));
+  CU(cudaStreamSynchronize(s));
+  return 0;
+}

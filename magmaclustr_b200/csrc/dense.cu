@@ -1,0 +1,438 @@
+// dense.cu -- kernels for ONE matrix-sized problem on the union grid (mean process, cluster
+// processes, prediction): covariance build, chol_inv_jitter, log-determinants, products and
+// the logL_GP_mod / gr_GP_mod reductions.  Matrices are row-major n x n in global memory
+// (L2-resident at U = 201: 323 KB); symmetric ones are stored full.
+//
+// Reference path replaced: kern_to_inv(all_inputs, kern_0, hp_0) and chol_inv_jitter(post_inv)
+// in e_step (/root/reference/R/em-magma.R:33,48-57), logL_GP_mod/gr_GP_mod on the mean
+// process (R/em-magma.R:157-166; R/likelihoods.R:155-174; R/gradients-likelihoods.R:71-97),
+// chol(post_cov) of logL_monitoring (R/likelihoods.R:303-307) and the matrix algebra of
+// pred_magma (R/prediction.R:1146-1189).
+#include "linalg.cuh"
+
+struct HpVal { double v[MB_MAX_HP]; };
+
+// out[i*rs + j*cs] = cov (deriv < 0) or d cov / d hp[deriv], x1: n1 x D, x2: n2 x D row-major.
+__global__ void k_dense_cov(DevKern kd, HpVal hp, const double* x1, int n1, const double* x2,
+                            int n2, int D, int deriv, int with_noise, double* out, int64_t rs,
+                            int64_t cs) {
+  const int64_t tot = (int64_t)n1 * n2;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < tot;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    int i = (int)(e / n2), j = (int)(e % n2);
+    double dv[MB_MAX_HP];
+    double v;
+    if (deriv < 0) v = cov_eval<false>(kd, hp.v, x1 + (size_t)i * D, x2 + (size_t)j * D, D,
+                                       with_noise != 0, nullptr);
+    else { cov_eval<true>(kd, hp.v, x1 + (size_t)i * D, x2 + (size_t)j * D, D, with_noise != 0, dv);
+           v = dv[deriv]; }
+    out[i * rs + j * cs] = v;
+  }
+}
+
+// The five native builders of /root/reference/src/code.cpp; inputs and output column-major.
+__global__ void k_legacy_builder(int which, const double* m1, int n1, const double* m2, int n2,
+                                 int d, double par, double* out) {
+  const int64_t tot = (int64_t)n1 * n2;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < tot;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    int r1 = (int)(e % n1), r2 = (int)(e / n1);
+    double total = 0.0;
+    for (int c = 0; c < d; ++c) {
+      double a = m1[r1 + (size_t)c * n1], b = m2[r2 + (size_t)c * n2];
+      if (which == 0) { double df = a - b; total += df * df; }                 // cpp_dist
+      else if (which == 1) { double sn = sin(MB_PI / exp(par) * fabs(a - b)); total += sn * sn; }
+      else if (which == 2) { double ang = MB_PI / exp(par) * fabs(a - b);      // cpp_perio_deriv
+                             total += 2 * sin(ang) * cos(ang) * ang; }
+      else if (which == 3) total += a * b;                                     // cpp_prod
+      else total += fabs(a - b);                                               // cpp_noise
+    }
+    if (which == 4) total = (total < 0.000001) ? exp(par) : 0.0;
+    out[e] = total;
+  }
+}
+
+// chol_inv_jitter of one matrix by a single CTA.  src: n x n (upper triangle read), A: result
+// (full symmetric inverse), B: scratch.  info[0] = retries (-1: gave up), out[0] = total
+// jitter, out[1] = sum log diag(R) of the successful factorisation.
+__global__ void __launch_bounds__(1024) k_dense_cholinv(const double* src, int ld_src,
+                                                        double* A, double* B, int n, double pen,
+                                                        int max_retry, int* info, double* out) {
+  __shared__ double red[32];
+  int retries = 0;
+  double total = 0.0;
+  for (;;) {
+    double p = pen;
+    total = 0.0;
+    for (int r = 0; r <= retries; ++r) { total += p; p = 10 * p; }
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      int i = e / n, j = e % n;
+      if (j < i) continue;
+      double v = src[(size_t)i * ld_src + j];
+      if (i == j) {
+        double q = pen;
+        for (int r = 0; r <= retries; ++r) { v += q; q = 10 * q; }
+      }
+      A[(size_t)i * n + j] = v;
+    }
+    __syncthreads();
+    if (blk_chol_upper(A, n, n) == 0) break;
+    __syncthreads();
+    if (++retries > max_retry) {
+      if (threadIdx.x == 0) { info[0] = -1; out[0] = total; out[1] = NAN; }
+      return;
+    }
+  }
+  double v[1] = {0.0};
+  for (int j = threadIdx.x; j < n; j += blockDim.x) v[0] += log(A[(size_t)j * n + j]);
+  blk_reduce_sum<1>(v, red);
+  if (threadIdx.x == 0) { info[0] = retries; out[0] = total; out[1] = v[0]; }
+  blk_tri_inv_upper(A, B, n, n);
+  blk_lauum_upper(B, A, n, n);
+}
+
+// sum log diag chol(src) with NO jitter (likelihoods.R:303-307); info[0] = 0 or failing pivot.
+__global__ void __launch_bounds__(1024) k_dense_chol_logdiag(const double* src, double* W, int n,
+                                                             int* info, double* out) {
+  __shared__ double red[32];
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) W[e] = src[e];
+  __syncthreads();
+  int r = blk_chol_upper(W, n, n);
+  if (r != 0) { if (threadIdx.x == 0) { info[0] = r; out[0] = NAN; } return; }
+  double v[1] = {0.0};
+  for (int j = threadIdx.x; j < n; j += blockDim.x) v[0] += log(W[(size_t)j * n + j]);
+  blk_reduce_sum<1>(v, red);
+  if (threadIdx.x == 0) { info[0] = 0; out[0] = v[0]; }
+}
+
+// log|det src| through LU with partial pivoting (determinant(), likelihoods.R:37-41).
+__global__ void __launch_bounds__(1024) k_dense_lu_logdet(const double* src, double* W, int n,
+                                                          int* done, double* out) {
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) W[e] = src[e];
+  __syncthreads();
+  double ldet = blk_lu_logabsdet(W, n, n, done);
+  if (threadIdx.x == 0) out[0] = ldet;
+}
+
+// C[i*ldc + j] = sum_k A(i,k) B(k,j), A(i,k) = A[i*ars + k*acs], B(k,j) = B[k*brs + j*bcs];
+// optional C = beta*Cin + alpha*acc with Cin(i,j) = Cin[i*ldc + j].
+#define GT 64
+#define GK 16
+__global__ void __launch_bounds__(256) k_gemm(int m, int n, int kk, const double* A, int64_t ars,
+                                              int64_t acs, const double* B, int64_t brs,
+                                              int64_t bcs, double* C, int64_t ldc, double alpha,
+                                              const double* Cin, double beta) {
+  __shared__ double As[GK][GT + 1];
+  __shared__ double Bs[GK][GT + 1];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int i0 = blockIdx.y * GT, j0 = blockIdx.x * GT;
+  double acc[4][4] = {};
+  for (int k0 = 0; k0 < kk; k0 += GK) {
+    for (int e = threadIdx.x; e < GT * GK; e += 256) {
+      int r = e / GK, c = e % GK;  // A tile: 64 rows x 16 k
+      int gi = i0 + r, gk = k0 + c;
+      As[c][r] = (gi < m && gk < kk) ? A[gi * ars + gk * acs] : 0.0;
+      int bk = e / GT, bj = e % GT;  // B tile: 16 k x 64 cols
+      int gk2 = k0 + bk, gj = j0 + bj;
+      Bs[bk][bj] = (gk2 < kk && gj < n) ? B[gk2 * brs + gj * bcs] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) av[a] = As[k][ty * 4 + a];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bv[b] = Bs[k][tx * 4 + b];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] += av[a] * bv[b];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      int gi = i0 + ty * 4 + a, gj = j0 + tx * 4 + b;
+      if (gi < m && gj < n) {
+        double v = alpha * acc[a][b];
+        if (Cin) v += beta * Cin[gi * ldc + gj];
+        C[gi * ldc + gj] = v;
+      }
+    }
+}
+
+// y[i] = sum_k A[i*ld + k] x[k] (+ y0[i]); one warp per row, fixed summation tree.
+__global__ void k_gemv(int m, int n, const double* A, int64_t ld, const double* x,
+                       const double* y0, double* y) {
+  int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  int lane = threadIdx.x & 31;
+  if (row >= m) return;
+  double s = 0.0;
+  for (int k = lane; k < n; k += 32) s += A[row * ld + k] * x[k];
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) y[row] = y0 ? y0[row] + s : s;
+}
+
+// Partial sums for logL_GP_mod / gr_GP_mod of one n x n problem:
+//   part[b][0]      = sum A o S                       (likelihoods.R:171)
+//   part[b][1 + p]  = sum W o dK_p,  W = al al' + T - A   (T = A S A; T NULL for the marginal form)
+// over the elements handled by CTA b (both triangles, like the reference's full trace).
+__global__ void __launch_bounds__(256) k_dense_obj_partials(
+    DevKern kd, HpVal hp, const double* x, int n, int D, const double* A, const double* S,
+    const double* T, const double* al, int want_grad, double* part) {
+  __shared__ double red[4 * 32];
+  const int P = kd.n_hp;
+  double tr = 0.0;
+  double gacc[MB_MAX_HP];
+#pragma unroll
+  for (int p = 0; p < MB_MAX_HP; ++p) gacc[p] = 0.0;
+  const int64_t tot = (int64_t)n * n;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < tot;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    int i = (int)(e / n), j = (int)(e % n);
+    double a = A[e];
+    if (S) tr += a * S[e];
+    if (want_grad) {
+      double w = al[i] * al[j] - a;
+      if (T) w += T[e];
+      double dv[MB_MAX_HP];
+      cov_eval<true>(kd, hp.v, x + (size_t)i * D, x + (size_t)j * D, D, true, dv);
+      for (int p = 0; p < P; ++p) gacc[p] += w * dv[p];
+    }
+  }
+  double* out = part + (size_t)blockIdx.x * (1 + MB_MAX_HP);
+  {
+    double v[4] = {tr, 0, 0, 0};
+    blk_reduce_sum<4>(v, red);
+    if (threadIdx.x == 0) out[0] = v[0];
+  }
+  for (int p0 = 0; p0 < P; p0 += 4) {
+    double v[4];
+    for (int q = 0; q < 4; ++q) v[q] = (p0 + q < P) ? gacc[p0 + q] : 0.0;
+    blk_reduce_sum<4>(v, red);
+    if (threadIdx.x == 0)
+      for (int q = 0; q < 4 && p0 + q < P; ++q) out[1 + p0 + q] = v[q];
+  }
+}
+
+// Final scalars: f = 0.5 (n log 2pi - logdetA + r'al) + 0.5 tr ;  g_p = -0.5 sum_b part[b][1+p].
+// res[0] = f, res[1..P] = g.  logdet[0] = log|det A| (LU) or, when from_chol, sum log diag R.
+__global__ void k_dense_obj_final(int n, int P, int nparts, const double* part, const double* r,
+                                  const double* al, const double* logdet, int from_chol,
+                                  int add_trace, double* res) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double quad = 0.0;
+  for (int i = 0; i < n; ++i) quad += r[i] * al[i];
+  double tr = 0.0;
+  for (int b = 0; b < nparts; ++b) tr += part[(size_t)b * (1 + MB_MAX_HP)];
+  double ldA = from_chol ? -2.0 * logdet[0] : logdet[0];
+  double f = 0.5 * (n * 1.8378770664093453 - ldA + quad);
+  if (add_trace) f = f + 0.5 * tr;
+  res[0] = f;
+  for (int p = 0; p < P; ++p) {
+    double s = 0.0;
+    for (int b = 0; b < nparts; ++b) s += part[(size_t)b * (1 + MB_MAX_HP) + 1 + p];
+    res[1 + p] = -0.5 * s;
+  }
+}
+
+// ---- small utilities -------------------------------------------------------------------
+// out[e] = base[e] + sum_g part[g][e], g ascending (deterministic): post_inv = inv_0 (+) sum_i.
+__global__ void k_reduce_partials(int64_t count, int nparts, const double* base,
+                                  const double* part, int64_t part_stride, double* out) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < count;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    double acc = base ? base[e] : 0.0;
+    for (int g = 0; g < nparts; ++g) acc += part[(size_t)g * part_stride + e];
+    out[e] = acc;
+  }
+}
+
+// out[0] = sum_i v[i] in index order by one thread (the reference's sapply(...) %>% sum()).
+__global__ void k_sum_sequential(const double* v, int64_t n, int64_t stride, double* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s = 0.0;
+  for (int64_t i = 0; i < n; ++i) s += v[i * stride];
+  out[0] = s;
+}
+
+// column sums of a row-major M x P table in row order (sapply(...) %>% rowSums()).
+__global__ void k_colsum_sequential(const double* v, int64_t n, int P, double* out) {
+  int p = threadIdx.x;
+  if (blockIdx.x != 0 || p >= P) return;
+  double s = 0.0;
+  for (int64_t i = 0; i < n; ++i) s += v[i * P + p];
+  out[p] = s;
+}
+
+__global__ void k_axpby(int64_t n, double a, const double* x, double b, const double* y,
+                        double* out) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
+       e += (int64_t)gridDim.x * blockDim.x)
+    out[e] = a * x[e] + (y ? b * y[e] : 0.0);
+}
+
+__global__ void k_fill(int64_t n, double v, double* out) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
+       e += (int64_t)gridDim.x * blockDim.x)
+    out[e] = v;
+}
+
+// diag extraction (+ add): out[i] = M[i*ld + i] + add
+__global__ void k_diag(int n, const double* M, int64_t ld, double add, double* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = M[i * ld + i] + add;
+}
+
+// gather: out[i*no + j] = M[ri[i]*ld + ci[j]]
+__global__ void k_gather2(const double* M, int64_t ld, const int32_t* ri, int nr,
+                          const int32_t* ci, int nc, double* out) {
+  const int64_t tot = (int64_t)nr * nc;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < tot;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    int i = (int)(e / nc), j = (int)(e % nc);
+    out[e] = M[(size_t)ri[i] * ld + ci[j]];
+  }
+}
+
+// Var_j = k(x_j, x_j) + S_jj - sum_i C_ij (Gamma^{-1} C)_ij + exp(noise): the diagonal of
+// prediction.R:1189 plus :1194, without forming the G x G matrix.  C column-major no x np,
+// GC row-major no x np.
+__global__ void k_pred_var(DevKern kd, HpVal hp, const double* xp, int np, int D,
+                           const double* sdiag, const double* C, const double* GC, int no,
+                           double noise, double* out) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= np) return;
+  double kjj = cov_eval<false>(kd, hp.v, xp + (size_t)j * D, xp + (size_t)j * D, D, false, nullptr);
+  double s = 0.0;
+  for (int i = 0; i < no; ++i) s += C[i + (size_t)j * no] * GC[(size_t)i * np + j];
+  out[j] = ((kjj + sdiag[j]) - s) + noise;
+}
+
+// ---- launchers ---------------------------------------------------------------------------
+static inline int grid_for(int64_t n, int threads, int cap = 148 * 8) {
+  int64_t g = (n + threads - 1) / threads;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+cudaError_t launch_dense_cov(const DevKern& kd, const double* hp_host, const double* x1, int n1,
+                             const double* x2, int n2, int D, int deriv, int with_noise,
+                             double* out, int64_t rs, int64_t cs, cudaStream_t st) {
+  HpVal h;
+  for (int p = 0; p < MB_MAX_HP; ++p) h.v[p] = p < kd.n_hp ? hp_host[p] : 0.0;
+  k_dense_cov<<<grid_for((int64_t)n1 * n2, 256), 256, 0, st>>>(kd, h, x1, n1, x2, n2, D, deriv,
+                                                               with_noise, out, rs, cs);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_legacy_builder(int which, const double* m1, int n1, const double* m2, int n2,
+                                  int d, double par, double* out, cudaStream_t st) {
+  k_legacy_builder<<<grid_for((int64_t)n1 * n2, 256), 256, 0, st>>>(which, m1, n1, m2, n2, d, par,
+                                                                    out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dense_cholinv(const double* src, int ld_src, double* A, double* B, int n,
+                                 double pen, int* info, double* out, cudaStream_t st) {
+  k_dense_cholinv<<<1, 1024, 0, st>>>(src, ld_src, A, B, n, pen, 40, info, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dense_chol_logdiag(const double* src, double* W, int n, int* info, double* out,
+                                      cudaStream_t st) {
+  k_dense_chol_logdiag<<<1, 1024, 0, st>>>(src, W, n, info, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dense_lu_logdet(const double* src, double* W, int n, int* done, double* out,
+                                   cudaStream_t st) {
+  k_dense_lu_logdet<<<1, 1024, 0, st>>>(src, W, n, done, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemm(int m, int n, int k, const double* A, int64_t ars, int64_t acs,
+                        const double* B, int64_t brs, int64_t bcs, double* C, int64_t ldc,
+                        double alpha, const double* Cin, double beta, cudaStream_t st) {
+  dim3 grid((n + GT - 1) / GT, (m + GT - 1) / GT);
+  k_gemm<<<grid, 256, 0, st>>>(m, n, k, A, ars, acs, B, brs, bcs, C, ldc, alpha, Cin, beta);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemv(int m, int n, const double* A, int64_t ld, const double* x,
+                        const double* y0, double* y, cudaStream_t st) {
+  k_gemv<<<(m + 7) / 8, 256, 0, st>>>(m, n, A, ld, x, y0, y);
+  return cudaGetLastError();
+}
+
+int dense_obj_nparts(int n) { return grid_for((int64_t)n * n, 256, 148 * 2); }
+
+cudaError_t launch_dense_obj(const DevKern& kd, const double* hp_host, const double* x, int n,
+                             int D, const double* A, const double* S, const double* T,
+                             const double* al, const double* r, const double* logdet,
+                             int from_chol, int want_grad, double* part, double* res,
+                             cudaStream_t st) {
+  HpVal h;
+  for (int p = 0; p < MB_MAX_HP; ++p) h.v[p] = p < kd.n_hp ? hp_host[p] : 0.0;
+  int nparts = dense_obj_nparts(n);
+  k_dense_obj_partials<<<nparts, 256, 0, st>>>(kd, h, x, n, D, A, S, T, al, want_grad, part);
+  k_dense_obj_final<<<1, 32, 0, st>>>(n, want_grad ? kd.n_hp : 0, nparts, part, r, al, logdet,
+                                      from_chol, S != nullptr, res);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_partials(int64_t count, int nparts, const double* base,
+                                   const double* part, int64_t part_stride, double* out,
+                                   cudaStream_t st) {
+  k_reduce_partials<<<grid_for(count, 256), 256, 0, st>>>(count, nparts, base, part, part_stride,
+                                                          out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sum_sequential(const double* v, int64_t n, int64_t stride, double* out,
+                                  cudaStream_t st) {
+  k_sum_sequential<<<1, 32, 0, st>>>(v, n, stride, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_colsum_sequential(const double* v, int64_t n, int P, double* out,
+                                     cudaStream_t st) {
+  k_colsum_sequential<<<1, 32, 0, st>>>(v, n, P, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_axpby(int64_t n, double a, const double* x, double b, const double* y,
+                         double* out, cudaStream_t st) {
+  k_axpby<<<grid_for(n, 256), 256, 0, st>>>(n, a, x, b, y, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fill(int64_t n, double v, double* out, cudaStream_t st) {
+  k_fill<<<grid_for(n, 256), 256, 0, st>>>(n, v, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_diag(int n, const double* M, int64_t ld, double add, double* out,
+                        cudaStream_t st) {
+  k_diag<<<(n + 255) / 256, 256, 0, st>>>(n, M, ld, add, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather2(const double* M, int64_t ld, const int32_t* ri, int nr,
+                           const int32_t* ci, int nc, double* out, cudaStream_t st) {
+  k_gather2<<<grid_for((int64_t)nr * nc, 256), 256, 0, st>>>(M, ld, ri, nr, ci, nc, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pred_var(const DevKern& kd, const double* hp_host, const double* xp, int np, int D,
+                            const double* sdiag, const double* C, const double* GC, int no,
+                            double noise, double* out, cudaStream_t st) {
+  HpVal h;
+  for (int p = 0; p < MB_MAX_HP; ++p) h.v[p] = p < kd.n_hp ? hp_host[p] : 0.0;
+  k_pred_var<<<(np + 127) / 128, 128, 0, st>>>(kd, h, xp, np, D, sdiag, C, GC, no, noise, out);
+  return cudaGetLastError();
+}

@@ -1,0 +1,81 @@
+// lbfgsb_dev.cu -- device side of the lock-step batched L-BFGS-B: one thread per problem
+// advances the reverse-communication state machine of lbfgsb.h; states stay in HBM between
+// objective launches, so the M step never ships gradients to the host.
+// Compiled with -fmad=false so the sums match the host build and the Python oracle bit for bit.
+//
+// Reference: the per-task stats::optim(..., method = "L-BFGS-B", control = list(factr = 1e13,
+// maxit = 25)) calls of m_step / vm_step (/root/reference/R/em-magma.R:200-230,
+// R/vem-magmaclust.R:249-261).
+#include <cuda_runtime.h>
+
+#include "lbfgsb.h"
+
+__global__ void k_lbfgsb_init(LbfgsbState* st, int64_t m, int n, const double* x0,
+                              int64_t x0_stride, double factr, double pgtol, int maxit) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  lb_init(&st[t], n, x0 + t * x0_stride, factr, pgtol, maxit);
+}
+
+// Feed (f[t], g[t,:]) to every still-active problem; n_active[0] += problems still active.
+__global__ void k_lbfgsb_advance(LbfgsbState* st, int64_t m, int n, const double* f,
+                                 const double* g, int* n_active) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  LbfgsbState* s = &st[t];
+  if (!s->active) return;
+  double gl[LB_NP];
+  for (int p = 0; p < n; ++p) gl[p] = g[t * n + p];
+  lb_advance(s, f[t], gl);
+  if (s->active) atomicAdd(n_active, 1);
+}
+
+// x -> HP table; fail codes and evaluation counts out.
+__global__ void k_lbfgsb_export(const LbfgsbState* st, int64_t m, int n, double* x,
+                                int64_t x_stride, int* fail, int* nfgv) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  for (int p = 0; p < n; ++p) x[t * x_stride + p] = st[t].x[p];
+  if (fail) fail[t] = st[t].fail;
+  if (nfgv) nfgv[t] = st[t].nfgv;
+}
+
+cudaError_t launch_lbfgsb_init(LbfgsbState* st, int64_t m, int n, const double* x0,
+                               int64_t x0_stride, double factr, double pgtol, int maxit,
+                               cudaStream_t s) {
+  k_lbfgsb_init<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(st, m, n, x0, x0_stride, factr, pgtol,
+                                                            maxit);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_lbfgsb_advance(LbfgsbState* st, int64_t m, int n, const double* f,
+                                  const double* g, int* n_active, cudaStream_t s) {
+  k_lbfgsb_advance<<<(unsigned)((m + 63) / 64), 64, 0, s>>>(st, m, n, f, g, n_active);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_lbfgsb_export(const LbfgsbState* st, int64_t m, int n, double* x,
+                                 int64_t x_stride, int* fail, int* nfgv, cudaStream_t s) {
+  k_lbfgsb_export<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(st, m, n, x, x_stride, fail, nfgv);
+  return cudaGetLastError();
+}
+
+// ---- host self test (mb_lbfgsb_selftest) ----------------------------------------------------
+extern "C" int mb_lbfgsb_selftest(int which, double* x, int n, double factr, int maxit,
+                                  double* fval, int32_t* n_eval, int32_t* fail) {
+  if (which != 0 || n != 2) return -1;
+  LbfgsbState s;
+  lb_init(&s, n, x, factr, 0.0, maxit);
+  while (s.active) {
+    const double* v = s.x;
+    double f = 100 * (v[1] - v[0] * v[0]) * (v[1] - v[0] * v[0]) + (1 - v[0]) * (1 - v[0]);
+    double g[2] = {-400 * v[0] * (v[1] - v[0] * v[0]) - 2 * (1 - v[0]),
+                   200 * (v[1] - v[0] * v[0])};
+    lb_advance(&s, f, g);
+  }
+  for (int i = 0; i < n; ++i) x[i] = s.x[i];
+  *fval = s.f;
+  *n_eval = s.nfgv;
+  *fail = s.fail;
+  return 0;
+}

@@ -1,0 +1,360 @@
+// tasks.cu -- per-task fused kernels: one CTA per task, the task's N x N matrices resident in
+// shared memory from covariance construction to the objective/gradient scalars (nothing
+// but x, y, the gathered hyper-posterior block and P+1 doubles crosses HBM).
+//
+// Reference path replaced: list_kern_to_inv -> kern_to_inv -> kern_to_cov -> chol_inv_jitter
+// (/root/reference/R/kernel-to-matrices.R:553-562,633-652,670-680), the task loop of e_step
+// (R/em-magma.R:36-46,61-70) and ve_step (R/vem-magmaclust.R:68-98,113-127), logL_GP_mod +
+// gr_GP_mod (R/likelihoods.R:155-174, R/gradients-likelihoods.R:71-97), elbo_clust_multi_GP
+// + gr_clust_multi_GP (R/elbos.R:18-55, R/gradients-elbos.R:17-70) and update_mixture's
+// likelihood table (R/vem-magmaclust.R:344-381).
+#include "linalg.cuh"
+#include "tasks.cuh"
+
+#define LOG_2PI 1.8378770664093453
+
+struct TaskSmem {
+  double *A, *B, *C, *xs, *yv, *rv, *al, *c1, *be, *red;
+  int *gi, *done;
+};
+
+__host__ __device__ inline size_t task_smem_bytes(int nmax, int ld, int D) {
+  size_t dbl = (size_t)3 * nmax * ld + (size_t)nmax * D + 5 * (size_t)nmax + (MB_MAX_HP + 4) * 32;
+  return dbl * sizeof(double) + 2 * (size_t)nmax * sizeof(int) + 16;
+}
+
+__device__ inline TaskSmem carve(double* base, int nmax, int ld, int D) {
+  TaskSmem s;
+  s.A = base;
+  s.B = s.A + (size_t)nmax * ld;
+  s.C = s.B + (size_t)nmax * ld;
+  s.xs = s.C + (size_t)nmax * ld;
+  s.yv = s.xs + (size_t)nmax * D;
+  s.rv = s.yv + nmax;
+  s.al = s.rv + nmax;
+  s.c1 = s.al + nmax;
+  s.be = s.c1 + nmax;
+  s.red = s.be + nmax;
+  s.gi = (int*)(s.red + (MB_MAX_HP + 4) * 32);
+  s.done = s.gi + nmax;
+  return s;
+}
+
+// Upper triangle of K(x, x; hp) [+ Sadd] with the cumulative jitter of `retries` failed
+// attempts already on the diagonal (kernel-to-matrices.R:672-678: pen, then 10*pen, ... are
+// added one after the other to the same matrix).
+__device__ inline void build_cov_upper(double* A, int n, int ld, const double* xs, int D,
+                                       const DevKern& kd, const double* hp, const double* Sadd,
+                                       double pen, int retries) {
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    int i = e / n, j = e % n;
+    if (j < i) continue;
+    double v = cov_eval<false>(kd, hp, xs + i * D, xs + j * D, D, true, nullptr);
+    if (Sadd) v += Sadd[i * ld + j];
+    if (i == j) {
+      double p = pen;
+      for (int r = 0; r <= retries; ++r) { v += p; p = 10 * p; }
+    }
+    A[i * ld + j] = v;
+  }
+  __syncthreads();
+}
+
+// chol_inv_jitter on K(x; hp) [+ Sadd]: A <- full symmetric inverse, B destroyed.
+// Returns the retry count, or -1 after TK_MAX_RETRY failures.  *logdet_chol receives
+// sum_j log R_jj of the successful factorisation (same value in every thread).
+__device__ inline int task_inverse(TaskSmem& s, int n, int ld, int D, const DevKern& kd,
+                                   const double* hp, const double* Sadd, double pen,
+                                   double* logdet_chol) {
+  int retries = 0;
+  for (;;) {
+    build_cov_upper(s.A, n, ld, s.xs, D, kd, hp, Sadd, pen, retries);
+    if (blk_chol_upper(s.A, n, ld) == 0) break;
+    __syncthreads();
+    if (++retries > TK_MAX_RETRY) return -1;
+  }
+  double v[1] = {0.0};
+  for (int j = threadIdx.x; j < n; j += blockDim.x) v[0] += log(s.A[j * ld + j]);
+  blk_reduce_sum<1>(v, s.red);
+  *logdet_chol = v[0];
+  blk_tri_inv_upper(s.A, s.B, n, ld);
+  blk_lauum_upper(s.B, s.A, n, ld);
+  return retries;
+}
+
+__device__ inline void load_task(TaskSmem& s, const TaskData& db, int64_t row0, int n) {
+  for (int e = threadIdx.x; e < n * db.D; e += blockDim.x) s.xs[e] = db.X[row0 * db.D + e];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    s.yv[i] = db.y[row0 + i];
+    s.gi[i] = db.gidx ? db.gidx[row0 + i] : i;
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------
+// Objective + gradient, one CTA per (active) task.
+// ---------------------------------------------------------------------------------------
+extern __shared__ double4 task_smem_raw[];
+
+__global__ void __launch_bounds__(256) k_task_objective(TaskObjArgs a) {
+  const int64_t t = a.active ? a.active[blockIdx.x] : blockIdx.x;
+  const int64_t row0 = a.db.offs[t];
+  const int n = (int)(a.db.offs[t + 1] - row0);
+  const int ld = a.ld, D = a.db.D, P = a.kd.n_hp, K = a.hpst.K, U = a.hpst.U;
+  TaskSmem s = carve((double*)task_smem_raw, a.db.nmax, ld, D);
+  double hp[MB_MAX_HP];
+  {
+    const double* src = a.lb ? a.lb[t].x : a.hp + t * a.hp_stride;
+    for (int p = 0; p < P; ++p) hp[p] = src[p];
+  }
+  load_task(s, a.db, row0, n);
+  const int tid = threadIdx.x, nt = blockDim.x;
+
+  // gather S (post_cov block / c2) into C; r and c1 vectors
+  const double* Sadd = nullptr;
+  if (a.mode != TK_OBJ_MIX) {
+    for (int e = tid; e < n * n; e += nt) {
+      int i = e / n, j = e % n;
+      double v;
+      if (a.mode == TK_OBJ_ELBO) {
+        v = 0.0;  // corr2 += tau_k * (mu_k mu_k' + cov_k[t_i, t_i])   elbos.R:44-53
+        for (int k = 0; k < K; ++k) {
+          const double* mk = a.hpst.mean + (size_t)k * U;
+          const double* ck = a.hpst.cov + (size_t)k * U * U;
+          double tau = a.hpst.tau[t * K + k];
+          v = v + tau * (mk[s.gi[i]] * mk[s.gi[j]] + ck[(size_t)s.gi[i] * U + s.gi[j]]);
+        }
+      } else {
+        v = a.hpst.cov[(size_t)s.gi[i] * U + s.gi[j]];
+      }
+      s.C[i * ld + j] = v;
+    }
+    for (int i = tid; i < n; i += nt) {
+      if (a.mode == TK_OBJ_ELBO) {
+        double c = 0.0;
+        for (int k = 0; k < K; ++k)
+          c = c + a.hpst.tau[t * K + k] * a.hpst.mean[(size_t)k * U + s.gi[i]];
+        s.c1[i] = c;
+        s.rv[i] = s.yv[i];
+      } else {
+        s.rv[i] = s.yv[i] - a.hpst.mean[s.gi[i]];
+      }
+    }
+    __syncthreads();
+    if (a.mode == TK_OBJ_MARG) Sadd = s.C;
+  }
+
+  double ldchol;
+  int retries = task_inverse(s, n, ld, D, a.kd, hp, Sadd, a.pen, &ldchol);
+  if (a.retries && tid == 0) a.retries[t] = retries;
+  if (retries < 0) {
+    if (tid == 0) {
+      if (a.mode == TK_OBJ_MIX) for (int k = 0; k < K; ++k) a.f[t * K + k] = NAN;
+      else a.f[t] = NAN;
+      if (a.want_grad) for (int p = 0; p < P; ++p) a.g[t * P + p] = NAN;
+    }
+    return;
+  }
+  // log|det A|
+  double logdetA;
+  if (a.logdet_chol) {
+    logdetA = -2.0 * ldchol;
+  } else {
+    for (int e = tid; e < n * n; e += nt) {
+      int i = e / n, j = e % n;
+      s.B[i * ld + j] = s.A[i * ld + j];
+    }
+    __syncthreads();
+    logdetA = blk_lu_logabsdet(s.B, n, ld, s.done);
+  }
+
+  if (a.mode == TK_OBJ_MIX) {
+    // one inverse, K Gaussian terms (vem-magmaclust.R:360-379 recomputes it K times)
+    for (int k = 0; k < K; ++k) {
+      const double* mk = a.hpst.mean + (size_t)k * U;
+      const double* ck = a.hpst.cov + (size_t)k * U * U;
+      for (int i = tid; i < n; i += nt) s.rv[i] = s.yv[i] - mk[s.gi[i]];
+      __syncthreads();
+      blk_gemv(s.al, s.A, s.rv, n, ld);
+      double v[2] = {0.0, 0.0};
+      for (int i = tid; i < n; i += nt) v[0] += s.rv[i] * s.al[i];
+      for (int e = tid; e < n * n; e += nt) {
+        int i = e / n, j = e % n;
+        v[1] += s.A[i * ld + j] * ck[(size_t)s.gi[i] * U + s.gi[j]];
+      }
+      blk_reduce_sum<2>(v, s.red);
+      if (tid == 0) a.f[t * K + k] = 0.5 * (n * LOG_2PI - logdetA + v[0]) + 0.5 * v[1];
+    }
+    return;
+  }
+
+  blk_gemv(s.al, s.A, s.rv, n, ld);  // alpha = A r
+  if (a.mode == TK_OBJ_ELBO) blk_gemv(s.be, s.A, s.c1, n, ld);
+  {
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int i = tid; i < n; i += nt) {
+      v[0] += s.rv[i] * s.al[i];
+      if (a.mode == TK_OBJ_ELBO) v[2] += s.al[i] * s.c1[i];
+    }
+    if (a.mode != TK_OBJ_MARG)
+      for (int e = tid; e < n * n; e += nt) {
+        int i = e / n, j = e % n;
+        v[1] += s.A[i * ld + j] * s.C[i * ld + j];
+      }
+    blk_reduce_sum<3>(v, s.red);
+    if (tid == 0) {
+      double f = 0.5 * (n * LOG_2PI - logdetA + v[0]);
+      if (a.mode == TK_OBJ_MOD) f = f + 0.5 * v[1];
+      if (a.mode == TK_OBJ_ELBO) f = f - v[2] + 0.5 * v[1];
+      a.f[t] = f;
+    }
+  }
+  if (!a.want_grad) return;
+
+  // common term W:  MOD  aa' + A S A - A ;  ELBO (a - 2b) a' + A c2 A - A ;  MARG aa' - A
+  if (a.mode != TK_OBJ_MARG) {
+    blk_gemm_nn(s.B, s.C, s.A, n, ld);  // B = S A
+    blk_gemm_nn(s.C, s.A, s.B, n, ld);  // C = A S A
+  }
+  double gacc[MB_MAX_HP];
+#pragma unroll
+  for (int p = 0; p < MB_MAX_HP; ++p) gacc[p] = 0.0;
+  for (int e = tid; e < n * n; e += nt) {
+    int i = e / n, j = e % n;
+    if (j < i) continue;
+    double lhs_i = s.al[i], lhs_j = s.al[j];
+    if (a.mode == TK_OBJ_ELBO) { lhs_i -= 2 * s.be[i]; lhs_j -= 2 * s.be[j]; }
+    double w = lhs_i * s.al[j] - s.A[i * ld + j];
+    if (a.mode != TK_OBJ_MARG) w += s.C[i * ld + j];
+    if (i != j) {
+      double w2 = lhs_j * s.al[i] - s.A[j * ld + i];
+      if (a.mode != TK_OBJ_MARG) w2 += s.C[j * ld + i];
+      w += w2;
+    }
+    double dv[MB_MAX_HP];
+    cov_eval<true>(a.kd, hp, s.xs + i * D, s.xs + j * D, D, true, dv);
+    for (int p = 0; p < P; ++p) gacc[p] += w * dv[p];
+  }
+  // reduce P sums (in chunks of 4 to bound the scratch)
+  for (int p0 = 0; p0 < P; p0 += 4) {
+    double v[4];
+    for (int q = 0; q < 4; ++q) v[q] = (p0 + q < P) ? gacc[p0 + q] : 0.0;
+    blk_reduce_sum<4>(v, s.red);
+    if (tid == 0)
+      for (int q = 0; q < 4 && p0 + q < P; ++q) a.g[t * P + p0 + q] = -0.5 * v[q];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// E step: persistent CTAs, each owning a contiguous run of tasks and a private partial of
+// the K precision sums / weighted sums, accumulated in task order (deterministic).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_task_inverse(TaskInvArgs a) {
+  const int ld = a.ld, D = a.db.D, P = a.kd.n_hp, K = a.K, U = a.U;
+  TaskSmem s = carve((double*)task_smem_raw, a.db.nmax, ld, D);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int64_t per = (a.db.n_tasks + gridDim.x - 1) / gridDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * per;
+  const int64_t t1 = (t0 + per < a.db.n_tasks) ? t0 + per : a.db.n_tasks;
+  double* pinv = a.part_inv ? a.part_inv + (size_t)blockIdx.x * K * U * U : nullptr;
+  double* pw = a.part_w ? a.part_w + (size_t)blockIdx.x * K * U : nullptr;
+  for (int64_t t = t0; t < t1; ++t) {
+    const int64_t row0 = a.db.offs[t];
+    const int n = (int)(a.db.offs[t + 1] - row0);
+    double hp[MB_MAX_HP];
+    for (int p = 0; p < P; ++p) hp[p] = a.hp[t * a.hp_stride + p];
+    load_task(s, a.db, row0, n);
+    double ldchol;
+    int retries = task_inverse(s, n, ld, D, a.kd, hp, nullptr, a.pen, &ldchol);
+    if (a.retries && tid == 0) a.retries[t] = retries;
+    if (retries < 0) {
+      // poison: the caller reports the failure through retries[t] = -1
+      for (int e = tid; e < n * n; e += nt) s.A[(e / n) * ld + e % n] = NAN;
+      __syncthreads();
+    }
+    if (a.inv_out) {
+      double* o = a.inv_out + a.inv_offs[t];
+      for (int e = tid; e < n * n; e += nt) o[e] = s.A[(e % n) * ld + e / n];
+    }
+    if (pinv) {
+      blk_gemv(s.al, s.A, s.yv, n, ld);  // inv_i %*% y_i
+      for (int k = 0; k < K; ++k) {
+        const double tau = a.tau ? a.tau[t * K + k] : 1.0;
+        double* pk = pinv + (size_t)k * U * U;
+        for (int e = tid; e < n * n; e += nt) {
+          int i = e / n, j = e % n;
+          size_t c = (size_t)s.gi[i] * U + s.gi[j];
+          pk[c] = pk[c] + (a.tau ? tau * s.A[i * ld + j] : s.A[i * ld + j]);
+        }
+        double* wk = pw + (size_t)k * U;
+        for (int i = tid; i < n; i += nt)
+          wk[s.gi[i]] = wk[s.gi[i]] + (a.tau ? tau * s.al[i] : s.al[i]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// list_kern_to_cov: covariance or one derivative matrix per task, written column-major.
+__global__ void k_task_cov(TaskData db, DevKern kd, const double* hp, int64_t hp_stride,
+                           int deriv, double* out, const int64_t* out_offs) {
+  const int64_t t = blockIdx.x;
+  const int64_t row0 = db.offs[t];
+  const int n = (int)(db.offs[t + 1] - row0);
+  const int D = db.D;
+  double hpl[MB_MAX_HP];
+  for (int p = 0; p < kd.n_hp; ++p) hpl[p] = hp[t * hp_stride + p];
+  const double* x = db.X + row0 * D;
+  double* o = out + out_offs[t];
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    int i = e % n, j = e / n;  // column-major output, consecutive threads -> consecutive rows
+    double dv[MB_MAX_HP];
+    double v;
+    if (deriv < 0) v = cov_eval<false>(kd, hpl, x + i * D, x + j * D, D, true, nullptr);
+    else { cov_eval<true>(kd, hpl, x + i * D, x + j * D, D, true, dv); v = dv[deriv]; }
+    o[e] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------
+static int pick_threads(int nmax) { return nmax <= 16 ? 64 : (nmax <= 32 ? 128 : 256); }
+
+int task_pick_ld(int nmax) { return nmax | 1; }
+
+cudaError_t launch_task_objective(TaskObjArgs a, int n_launch, cudaStream_t st) {
+  if (n_launch <= 0) return cudaSuccess;
+  a.ld = task_pick_ld(a.db.nmax);
+  size_t smem = task_smem_bytes(a.db.nmax, a.ld, a.db.D);
+  cudaError_t e = cudaFuncSetAttribute(k_task_objective,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_task_objective<<<n_launch, pick_threads(a.db.nmax), smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_task_inverse(TaskInvArgs a, int n_ctas, cudaStream_t st) {
+  a.ld = task_pick_ld(a.db.nmax);
+  size_t smem = task_smem_bytes(a.db.nmax, a.ld, a.db.D);
+  cudaError_t e = cudaFuncSetAttribute(k_task_inverse,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_task_inverse<<<n_ctas, pick_threads(a.db.nmax), smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_task_cov(TaskData db, DevKern kd, const double* hp, int64_t hp_stride,
+                            int deriv, double* out, const int64_t* out_offs, cudaStream_t st) {
+  k_task_cov<<<(unsigned)db.n_tasks, 256, 0, st>>>(db, kd, hp, hp_stride, deriv, out, out_offs);
+  return cudaGetLastError();
+}
+
+int task_max_ctas_per_sm(int nmax, int D) {
+  int ld = task_pick_ld(nmax);
+  size_t smem = task_smem_bytes(nmax, ld, D);
+  int n = 0;
+  cudaFuncSetAttribute(k_task_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_task_inverse, pick_threads(nmax), smem);
+  return n > 0 ? n : 1;
+}

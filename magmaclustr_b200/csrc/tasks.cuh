@@ -1,0 +1,68 @@
+// tasks.cuh -- argument block of the per-task fused kernels (one CTA per task, the task's
+// matrices resident in shared memory).
+#pragma once
+#include "common.cuh"
+#include "lbfgsb.h"
+
+#define TK_MAXN 96        /* largest task handled by the shared-memory path */
+#define TK_MAX_RETRY 40   /* jitter escalations before giving up (R has no cap) */
+
+enum {
+  TK_OBJ_MOD = 0,    // logL_GP_mod / gr_GP_mod            likelihoods.R:155-174
+  TK_OBJ_ELBO = 1,   // elbo_clust_multi_GP / gr_clust_..  elbos.R:18-55
+  TK_OBJ_MARG = 2,   // logL_GP / gr_GP (K + S inverted)   likelihoods.R:73-86
+  TK_OBJ_MIX = 3     // update_mixture: K values of -logL_GP_mod per task
+};
+
+struct TaskData {          // resident dataset (device pointers)
+  const int64_t* offs;     // n_tasks + 1
+  const double* X;         // rows x D, row-major
+  const double* y;         // rows
+  const int32_t* gidx;     // rows: position in the union grid
+  int D;
+  int64_t n_tasks;
+  int nmax;                // largest task
+};
+
+struct HyperPost {         // hyper-posterior on the U grid (K = 1 for Magma)
+  int K;
+  int U;
+  const double* mean;      // K x U
+  const double* cov;       // K x U x U (symmetric, so storage order is irrelevant)
+  const double* tau;       // n_tasks x K row-major (NULL = weight 1)
+};
+
+struct TaskObjArgs {
+  TaskData db;
+  HyperPost hpst;
+  DevKern kd;
+  const double* hp;          // HP table, or NULL when lb != NULL
+  int64_t hp_stride;         // doubles between tasks (0 = shared)
+  const LbfgsbState* lb;     // device optimiser states: HPs are lb[t].x
+  const int32_t* active;     // task ids to evaluate (NULL = all), n_active entries
+  int mode;
+  int want_grad;
+  int logdet_chol;           // 0: LU of the explicit inverse (reference), 1: Cholesky diagonal
+  double pen;
+  double* f;                 // n_tasks (TK_OBJ_MIX: n_tasks x K)
+  double* g;                 // n_tasks x n_hp
+  int32_t* retries;          // n_tasks (may be NULL)
+  int ld;                    // shared-memory leading dimension (odd, >= nmax)
+};
+
+struct TaskInvArgs {       // E step / list_kern_to_inv
+  TaskData db;
+  DevKern kd;
+  const double* hp;
+  int64_t hp_stride;
+  double pen;
+  int K;                     // clusters (weights tau), 1 for Magma
+  const double* tau;         // n_tasks x K or NULL
+  int U;
+  double* part_inv;          // gridDim.x x K x U x U partial precision sums (NULL = skip)
+  double* part_w;            // gridDim.x x K x U    partial weighted sums
+  double* inv_out;           // optional: all inverses, block t at inv_offs[t], column-major
+  const int64_t* inv_offs;
+  int32_t* retries;
+  int ld;
+};

@@ -1,0 +1,288 @@
+"""numpy-level handle on the C-ABI library: one `Context` = one GPU, one resident dataset.
+
+Thin marshalling only; every number comes from libmagma_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import check, f64, ptr
+
+
+class Context:
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        check(L.lib().mb_create(C.byref(self._h), int(device)))
+        self.device = device
+        self.n_tasks = 0
+        self.U = 0
+        self.offs = None
+        self._ar_cb = None
+
+    def close(self):
+        if self._h:
+            L.lib().mb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(L.lib().mb_launch_count(self._h))
+
+    def set_allreduce(self, fn, rank, world):
+        """fn(dev_ptr:int, count:int) -> None performs an in-place sum all-reduce."""
+        def _cb(user, dev_ptr, count):
+            try:
+                fn(int(dev_ptr), int(count))
+                return 0
+            except Exception:  # pragma: no cover
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._ar_cb = L.ALLREDUCE_FN(_cb)
+        check(L.lib().mb_set_allreduce(self._h, self._ar_cb, None, int(rank), int(world)))
+
+    # ---- the five native builders (R matrices are column-major) ---------------------------
+    def _legacy(self, name, m1, m2, par=None):
+        m1 = np.asfortranarray(np.atleast_2d(np.asarray(m1, dtype=np.float64).T).T)
+        m2 = np.asfortranarray(np.atleast_2d(np.asarray(m2, dtype=np.float64).T).T)
+        if name in ("mb_cpp_dist", "mb_cpp_prod") and m1.shape[1] != m2.shape[1]:
+            raise RuntimeError("Incompatible number of dimensions")
+        out = np.zeros((m1.shape[0], m2.shape[0]), order="F")
+        args = [self._h, m1.ctypes.data_as(L._dp), m1.shape[0], m2.ctypes.data_as(L._dp),
+                m2.shape[0], m1.shape[1]]
+        if par is not None:
+            args.append(float(par))
+        args.append(out.ctypes.data_as(L._dp))
+        check(getattr(L.lib(), name)(*args))
+        return out
+
+    def cpp_dist(self, m1, m2):
+        return self._legacy("mb_cpp_dist", m1, m2)
+
+    def cpp_prod(self, m1, m2):
+        return self._legacy("mb_cpp_prod", m1, m2)
+
+    def cpp_perio(self, m1, m2, period):
+        return self._legacy("mb_cpp_perio", m1, m2, period)
+
+    def cpp_perio_deriv(self, m1, m2, period):
+        return self._legacy("mb_cpp_perio_deriv", m1, m2, period)
+
+    def cpp_noise(self, m1, m2, noise):
+        return self._legacy("mb_cpp_noise", m1, m2, noise)
+
+    # ---- kern_to_cov / inv -------------------------------------------------------------
+    def kern_to_cov(self, k, hp, x1, x2=None, deriv=-1):
+        x1 = f64(np.atleast_2d(np.asarray(x1, dtype=np.float64).T).T)
+        n1, d = x1.shape
+        if x2 is None:
+            x2p, n2 = None, n1
+        else:
+            x2 = f64(np.atleast_2d(np.asarray(x2, dtype=np.float64).T).T)
+            x2p, n2 = ptr(x2), x2.shape[0]
+        out = np.zeros((n1, n2), order="F")
+        hp = f64(hp)
+        check(L.lib().mb_kern_to_cov(self._h, C.byref(k), ptr(hp), ptr(x1), n1, x2p, n2, d,
+                                     int(deriv), out.ctypes.data_as(L._dp)))
+        return out
+
+    def list_kern_to_mat(self, k, offs, X, hp, shared=False, deriv=-1, inverse=False,
+                         pen_diag=1e-10):
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        X = f64(np.atleast_2d(np.asarray(X, dtype=np.float64).T).T)
+        hp = f64(hp)
+        m = len(offs) - 1
+        sizes = np.diff(offs)
+        out_offs = np.zeros(m, dtype=np.int64)
+        out_offs[1:] = np.cumsum(sizes[:-1] ** 2)
+        out = np.zeros(int(np.sum(sizes ** 2)))
+        retries = np.zeros(m, dtype=np.int32)
+        check(L.lib().mb_list_kern_to_mat(self._h, C.byref(k), m, ptr(offs), X.shape[1], ptr(X),
+                                          ptr(hp), 1 if shared else 0, int(deriv),
+                                          1 if inverse else 0, float(pen_diag), ptr(out_offs),
+                                          ptr(out), ptr(retries)))
+        mats = [out[out_offs[t]: out_offs[t] + sizes[t] ** 2].reshape(sizes[t], sizes[t], order="F")
+                for t in range(m)]
+        return mats, retries
+
+    def chol_inv_jitter(self, mat, pen_diag):
+        mat = np.asfortranarray(mat, dtype=np.float64)
+        n = mat.shape[0]
+        inv = np.zeros((n, n), order="F")
+        nr = C.c_int32(0)
+        jt = C.c_double(0)
+        check(L.lib().mb_chol_inv_jitter(self._h, mat.ctypes.data_as(L._dp), n, n, float(pen_diag),
+                                         inv.ctypes.data_as(L._dp), C.byref(nr), C.byref(jt)))
+        return inv, nr.value, jt.value
+
+    # ---- dataset ---------------------------------------------------------------------------
+    def upload_dataset(self, offs, X, y, grid_index, grid_X):
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        X = f64(np.atleast_2d(np.asarray(X, dtype=np.float64).T).T)
+        y = f64(y)
+        gi = np.ascontiguousarray(grid_index, dtype=np.int32)
+        gX = f64(np.atleast_2d(np.asarray(grid_X, dtype=np.float64).T).T)
+        check(L.lib().mb_upload_dataset(self._h, len(offs) - 1, ptr(offs), X.shape[1], ptr(X), ptr(y),
+                                        ptr(gi), gX.shape[0], ptr(gX)))
+        self.n_tasks = len(offs) - 1
+        self.U = gX.shape[0]
+        self.offs = offs
+        self.D = X.shape[1]
+
+    # ---- Magma -------------------------------------------------------------------------------
+    def e_step(self, k0, hp_0, ki, hp_i, m_0, pen_diag=1e-10, shared=False):
+        hp_0, hp_i, m_0 = f64(hp_0), f64(hp_i), f64(m_0)
+        pm = np.zeros(self.U)
+        pc = np.zeros((self.U, self.U))
+        info = np.zeros(3, dtype=np.int32)
+        check(L.lib().mb_e_step(self._h, C.byref(k0), ptr(hp_0), C.byref(ki), ptr(hp_i),
+                                1 if shared else 0, ptr(m_0), float(pen_diag), ptr(pm), ptr(pc),
+                                ptr(info)))
+        return pm, pc, info
+
+    def logL_GP_mod_tasks(self, ki, hp_i, post_mean, post_cov, pen_diag=1e-10, shared=False,
+                          grad=True):
+        hp_i, pm, pc = f64(hp_i), f64(post_mean), f64(post_cov)
+        f = np.zeros(self.n_tasks)
+        g = np.zeros((self.n_tasks, ki.n_hp)) if grad else None
+        r = np.zeros(self.n_tasks, dtype=np.int32)
+        check(L.lib().mb_logL_GP_mod_tasks(self._h, C.byref(ki), ptr(hp_i), 1 if shared else 0,
+                                           ptr(pm), ptr(pc), float(pen_diag), ptr(f), ptr(g), ptr(r)))
+        return f, g, r
+
+    def logL_GP_mod(self, k, hp, x, y, mean, post_cov, pen_diag=1e-10, grad=True):
+        x = f64(np.atleast_2d(np.asarray(x, dtype=np.float64).T).T)
+        n, d = x.shape
+        hp, y, mean, pc = f64(hp), f64(y), f64(np.broadcast_to(mean, (n,))), f64(post_cov)
+        f = C.c_double(0)
+        g = np.zeros(k.n_hp) if grad else None
+        check(L.lib().mb_logL_GP_mod(self._h, C.byref(k), ptr(hp), ptr(x), n, d, ptr(y), ptr(mean),
+                                     ptr(pc), float(pen_diag), C.byref(f), ptr(g)))
+        return f.value, g
+
+    def m_step(self, k0, hp_0, ki, hp_i, m_0, post_mean, post_cov, shared_hp=False,
+               pen_diag=1e-10):
+        hp_0 = f64(hp_0).copy()
+        hp_i = f64(hp_i).copy()
+        stats = np.zeros(4, dtype=np.int64)
+        check(L.lib().mb_m_step(self._h, C.byref(k0), ptr(hp_0), C.byref(ki), ptr(hp_i),
+                                1 if shared_hp else 0, ptr(f64(m_0)), ptr(f64(post_mean)),
+                                ptr(f64(post_cov)), float(pen_diag), ptr(stats)))
+        return hp_0, hp_i, stats
+
+    def logL_monitoring(self, k0, hp_0, ki, hp_i, m_0, post_mean, post_cov, pen_diag=1e-10,
+                        shared=False):
+        out = C.c_double(0)
+        check(L.lib().mb_logL_monitoring(self._h, C.byref(k0), ptr(f64(hp_0)), C.byref(ki),
+                                         ptr(f64(hp_i)), 1 if shared else 0, ptr(f64(m_0)),
+                                         ptr(f64(post_mean)), ptr(f64(post_cov)), float(pen_diag),
+                                         C.byref(out)))
+        return out.value
+
+    def em_step(self, k0, hp_0, ki, hp_i, m_0, shared_hp=False, pen_diag=1e-10, want_post=False):
+        """In-place on hp_0 / hp_i (contiguous float64 arrays).  Returns (logL, stats[, pm, pc])."""
+        assert hp_0.dtype == np.float64 and hp_i.dtype == np.float64
+        assert hp_0.flags.c_contiguous and hp_i.flags.c_contiguous
+        ll = C.c_double(0)
+        stats = np.zeros(4, dtype=np.int64)
+        pm = np.zeros(self.U) if want_post else None
+        pc = np.zeros((self.U, self.U)) if want_post else None
+        check(L.lib().mb_em_step(self._h, C.byref(k0), ptr(hp_0), C.byref(ki), ptr(hp_i),
+                                 1 if shared_hp else 0, ptr(f64(m_0)), float(pen_diag), C.byref(ll),
+                                 ptr(pm), ptr(pc), ptr(stats)))
+        if want_post:
+            return ll.value, stats, pm, pc
+        return ll.value, stats
+
+    def train_magma(self, k0, hp_0, ki, hp_i, m_0, shared_hp=False, pen_diag=1e-10,
+                    n_iter_max=25, cv_threshold=1e-3):
+        hp_0 = f64(hp_0).copy()
+        hp_i = f64(hp_i).copy()
+        seq = np.zeros(n_iter_max)
+        n_iter = C.c_int32(0)
+        conv = C.c_int32(0)
+        pm = np.zeros(self.U)
+        pc = np.zeros((self.U, self.U))
+        check(L.lib().mb_train_magma(self._h, C.byref(k0), ptr(hp_0), C.byref(ki), ptr(hp_i),
+                                     1 if shared_hp else 0, ptr(f64(m_0)), float(pen_diag),
+                                     int(n_iter_max), float(cv_threshold), ptr(seq), C.byref(n_iter),
+                                     C.byref(conv), ptr(pm), ptr(pc)))
+        return {"hp_0": hp_0, "hp_i": hp_i, "seq_loglikelihood": seq[: n_iter.value].copy(),
+                "converged": bool(conv.value), "post_mean": pm, "post_cov": pc}
+
+    # ---- device-resident state / timing (measurement support) -----------------------------
+    def set_state(self, k0, hp_0, ki, hp_i, m_0):
+        check(L.lib().mb_set_state(self._h, C.byref(k0), ptr(f64(hp_0)), C.byref(ki), ptr(f64(hp_i)),
+                                   ptr(f64(m_0))))
+
+    def em_step_resident(self, k0, ki, shared_hp=False, pen_diag=1e-10, restart=True):
+        ll = C.c_double(0)
+        stats = np.zeros(4, dtype=np.int64)
+        check(L.lib().mb_em_step_resident(self._h, C.byref(k0), C.byref(ki), 1 if shared_hp else 0,
+                                          float(pen_diag), 1 if restart else 0, C.byref(ll), ptr(stats)))
+        return ll.value, stats
+
+    def get_state(self, k0, ki):
+        hp_0 = np.zeros(k0.n_hp)
+        hp_i = np.zeros((self.n_tasks, ki.n_hp))
+        check(L.lib().mb_get_state(self._h, C.byref(k0), ptr(hp_0), C.byref(ki), ptr(hp_i)))
+        return hp_0, hp_i
+
+    def timer_start(self):
+        check(L.lib().mb_timer(self._h, 0))
+
+    def timer_stop_ms(self):
+        check(L.lib().mb_timer(self._h, 1))
+        ms = C.c_double(0)
+        check(L.lib().mb_timer_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def profile(self, enable):
+        check(L.lib().mb_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        out = np.zeros(3)
+        check(L.lib().mb_profile_read(self._h, ptr(out)))
+        return {"ms": out[0], "launches": int(out[1]), "evals": int(out[2])}
+
+    def flush_l2(self, nbytes=256 << 20):
+        check(L.lib().mb_flush_l2(self._h, int(nbytes)))
+
+    def hyperposterior(self, k0, hp_0, ki, hp_i, grid_X, grid_index, m_0, pen_diag=1e-10,
+                       shared=False):
+        gX = f64(np.atleast_2d(np.asarray(grid_X, dtype=np.float64).T).T)
+        gi = np.ascontiguousarray(grid_index, dtype=np.int32)
+        u = gX.shape[0]
+        pm = np.zeros(u)
+        pc = np.zeros((u, u))
+        check(L.lib().mb_hyperposterior(self._h, C.byref(k0), ptr(f64(hp_0)), C.byref(ki),
+                                        ptr(f64(hp_i)), 1 if shared else 0, u, ptr(gX), ptr(gi),
+                                        ptr(f64(np.broadcast_to(m_0, (u,)))), float(pen_diag),
+                                        ptr(pm), ptr(pc)))
+        return pm, pc
+
+    def pred_magma(self, k, hp, x_obs, y_obs, x_pred, mean_obs, mean_pred, cov_obs, cov_pred,
+                   cov_crossed, pen_diag=1e-10, full_cov=True):
+        xo = f64(np.atleast_2d(np.asarray(x_obs, dtype=np.float64).T).T)
+        xp = f64(np.atleast_2d(np.asarray(x_pred, dtype=np.float64).T).T)
+        no, d = xo.shape
+        npred = xp.shape[0]
+        mean = np.zeros(npred)
+        var = np.zeros(npred)
+        cov = np.zeros((npred, npred), order="F") if full_cov else None
+        so = np.asfortranarray(cov_obs, dtype=np.float64)
+        sp = np.asfortranarray(cov_pred, dtype=np.float64)
+        sc = np.asfortranarray(cov_crossed, dtype=np.float64)
+        check(L.lib().mb_pred_magma(self._h, C.byref(k), ptr(f64(hp)), ptr(xo), no, ptr(f64(y_obs)),
+                                    ptr(xp), npred, d, ptr(f64(mean_obs)), ptr(f64(mean_pred)),
+                                    so.ctypes.data_as(L._dp), sp.ctypes.data_as(L._dp),
+                                    sc.ctypes.data_as(L._dp), float(pen_diag), ptr(mean), ptr(var),
+                                    cov.ctypes.data_as(L._dp) if full_cov else None))
+        return mean, var, cov
