@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- train_magma EM steps/s at BASELINE config 2 (M = 10 000 tasks x N = 64 points,
+SE kernel, shared_hp = FALSE, U = 201), measured through the C-ABI library.
+
+A step = ONE EM iteration (e_step + m_step + logL_monitoring, /root/reference/R/training.R:905-1030)
+started from the pristine initial hyper-parameters, so every timed step does identical work.
+
+  value   : device-resident inputs (dataset + HP tables already in HBM), CUDA events on the
+            library's stream, max over ranks.
+  e2e     : the same step through mb_upload_dataset + mb_em_step with HOST buffers (pinned):
+            host->device copy of the table and HP arrays and device->host read of the new
+            HPs / log-likelihood inside the timed region.
+  roofline: dominant kernel k_task_objective, algorithmic flops = objective evaluations x
+            5.67 N^3, divided by its summed event time; peak = cuBLAS DGEMM
+            8192^3 measured in the same run (MEASURED_PEAKS.json has no FP64 figure).
+  cpu_baseline / --impl reference: the oracle (CPU restatement of the reference's algorithm,
+            all host cores) on a bounded task sample, scaled linearly in M.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M_TASKS, N_POINTS = 10000, 64
+DATA_SEED, HP0_SEED, HPI_SEED = 2024, 6, 106
+METRIC = "train_magma EM steps/sec at M=10k,N=64"
+FLOPS_PER_EVAL = 5.0 + 2.0 / 3.0  # x N^3: chol+inverse N^3, LU log-det 2/3 N^3, S A and A (S A) 4 N^3
+
+
+def make_inputs(m_tasks=M_TASKS):
+    from magmaclustr_b200.dataprep import Prepared
+    from magmaclustr_b200.simulate import simu_db, ini_hp
+    df, _ = simu_db(M=M_TASKS, N=N_POINTS, seed=DATA_SEED)
+    prep = Prepared(df.ID.values, df.Input.values, df.Output.values)
+    hp0 = ini_hp("SE", ["0"], True, False, HP0_SEED).drop(columns="ID").iloc[0].to_numpy(dtype=np.float64)
+    # ini_hp_i without an ID column is broadcast to every task (training.R:831-833)
+    hpi = ini_hp("SE", prep.ids, True, True, HPI_SEED).drop(columns="ID").to_numpy(dtype=np.float64)
+    return df, prep, np.ascontiguousarray(hp0), np.ascontiguousarray(hpi)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dgemm_peak_tflops():
+    import torch
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def oracle_sample_step(df, m_sample, procs):
+    """One EM step of the oracle on the first m_sample tasks; returns (seconds, evals)."""
+    from oracle import magma as OM
+    from oracle import parallel as OP
+    from magmaclustr_b200.simulate import ini_hp
+    ids = sorted(df.ID.unique(), key=lambda s: s.encode())[:m_sample]
+    sub = df[df.ID.isin(ids)]
+    db = OM.Dataset(sub.ID.values, sub.Input.values, sub.Output.values)
+    h0 = ini_hp("SE", ["0"], True, False, HP0_SEED).drop(columns="ID").iloc[0].to_dict()
+    hi_row = ini_hp("SE", ["x"], True, True, HPI_SEED).drop(columns="ID").iloc[0].to_dict()
+    hi = {i: dict(hi_row) for i in db.ids}
+    t = time.perf_counter()
+    _, _, ll, evals = OP.em_step(db, 0.0, "SE", "SE", h0, hi, 1e-10, procs)
+    return time.perf_counter() - t, evals, ll
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU algorithm (oracle port; R is not installable in this
+    image) on all host cores, bounded sample per step, scaled linearly in M."""
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    m_sample = args.cpu_sample
+    df, _, _, _ = make_inputs()
+    secs = []
+    for s in range(args.warmup + args.steps):
+        dt, evals, ll = oracle_sample_step(df, m_sample, cores)
+        if s >= args.warmup:
+            secs.append(dt)
+    per_step_full = float(np.mean(secs)) * (M_TASKS / m_sample)
+    value = 1.0 / per_step_full
+    sample = ("first %d of %d tasks per step (one EM step = e_step + m_step + logL_monitoring), "
+              "time scaled linearly in M (DESCRIPTION:23-24)" % (m_sample, M_TASKS))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "EM steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": per_step_full * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2: train_magma EM step, M=10000 tasks x N=64, SE, shared_hp=FALSE, U=201"},
+            "cpu_baseline": {"value": value, "unit": "EM steps/s", "cores": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "EM steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fit", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    from magmaclustr_b200 import _lib as L
+    from magmaclustr_b200.engine import Context
+    from magmaclustr_b200.parallel import shard_tasks, make_allreduce
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    df, prep, hp0, hpi = make_inputs()
+    k0, ki = L.parse_kernel("SE", False), L.parse_kernel("SE", True)
+    ctx = Context(local_rank)
+    lo, hi_ = shard_tasks(prep.offs, rank, world)
+    offs = (prep.offs[lo:hi_ + 1] - prep.offs[lo]).astype(np.int64)
+    r0, r1 = int(prep.offs[lo]), int(prep.offs[hi_])
+    # pinned host copies of the step's inputs (e2e path)
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy(), t
+    X_h, _k1 = pinned(prep.X[r0:r1])
+    y_h, _k2 = pinned(prep.y[r0:r1])
+    gi_h, _k3 = pinned(prep.grid_index[r0:r1])
+    gX_h, _k4 = pinned(prep.grid_X)
+    hpi_loc = np.ascontiguousarray(hpi[lo:hi_])
+    if world > 1:
+        ctx.set_allreduce(make_allreduce(dist), rank, world)
+    ctx.upload_dataset(offs, X_h, y_h, gi_h, gX_h)
+    m0 = np.zeros(ctx.U)
+    ctx.set_state(k0, hp0, ki, hpi_loc, m0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident steps ------------------------------------------------------------
+    for _ in range(args.warmup):
+        ctx.em_step_resident(k0, ki, restart=True)
+    ctx.profile(True)
+    ctx.profile_read()
+    sampler = ClockSampler(local_rank)
+    launches0 = ctx.launches
+    if rank == 0:
+        sampler.start()
+    ms = []
+    stats = None
+    logL = None
+    for _ in range(args.steps):
+        ctx.flush_l2()                      # 256 MiB write between timed iterations
+        barrier()
+        ctx.timer_start()
+        logL, stats = ctx.em_step_resident(k0, ki, restart=True)
+        ms.append(ctx.timer_stop_ms())
+        barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launches - launches0
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    total_ms = float(np.sum(ms))
+    evals_local = prof["evals"]
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = args.steps / (total_ms * 1e-3)
+
+    # ---- end-to-end steps: host buffers in, host buffers out -------------------------------
+    e2e_ms = []
+    h0_h, hi_h = hp0.copy(), hpi_loc.copy()
+    for s in range(args.warmup + args.steps):
+        h0_h[:] = hp0
+        hi_h[:] = hpi_loc
+        ctx.flush_l2()
+        barrier()
+        t0 = time.perf_counter()
+        ctx.upload_dataset(offs, X_h, y_h, gi_h, gX_h)
+        ll_e2e, _ = ctx.em_step(k0, h0_h, ki, hi_h, m0)
+        dt = (time.perf_counter() - t0) * 1e3
+        barrier()
+        if s >= args.warmup:
+            e2e_ms.append(dt)
+    e2e_total = float(np.sum(e2e_ms))
+    if world > 1:
+        t = torch.tensor([e2e_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_total = float(t.item())
+    h2d = int(offs.nbytes + X_h.nbytes + y_h.nbytes + gi_h.nbytes + gX_h.nbytes + hi_h.nbytes + m0.nbytes)
+    d2h = int(hi_h.nbytes + 8)
+
+    # ---- full fit (context for the step metric; outside the timed regions) --------------------
+    fit = None
+    if not args.no_fit:
+        t0 = time.perf_counter()
+        res = ctx.train_magma(k0, hp0, ki, hpi_loc, m0)
+        fit = {"em_steps": int(len(res["seq_loglikelihood"])), "converged": bool(res["converged"]),
+               "seconds": time.perf_counter() - t0, "final_logL": float(res["seq_loglikelihood"][-1])}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak = dgemm_peak_tflops()
+    achieved = evals_local * FLOPS_PER_EVAL * N_POINTS ** 3 / (prof["ms"] * 1e-3) / 1e12 if prof["ms"] > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": "EM steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2: train_magma EM step (e_step + m_step + logL_monitoring), "
+                               "M=10000 tasks x N=64, SE kernel, shared_hp=FALSE, U=201, seeds data=2024 "
+                               "hp_0=6 hp_i=106 (hp_i broadcast to all tasks)",
+                   "step": "first EM iteration from the initial hyper-parameters, repeated",
+                   "l2": "256 MiB flush between timed iterations",
+                   "tasks_per_rank": int(hi_ - lo), "task_evals_per_step": int(stats[2]),
+                   "lockstep_rounds": int(stats[1]), "hp0_evals": int(stats[0]), "logL": logL},
+        "clocks": clocks,
+        "e2e": {"value": args.steps / (e2e_total * 1e-3), "unit": "EM steps/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "k_task_objective", "achieved": achieved, "peak": peak,
+                     "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (no FP64 figure in MEASURED_PEAKS.json)",
+                     "kernel_ms_per_step": prof["ms"] / args.steps,
+                     "kernel_share_of_step": prof["ms"] / float(np.sum(ms))},
+    }
+    if fit:
+        line["fit"] = fit
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count()
+        dt, evals, _ = oracle_sample_step(df, args.cpu_sample, cores)
+        line["cpu_baseline"] = {
+            "value": 1.0 / (dt * M_TASKS / args.cpu_sample), "unit": "EM steps/s", "cores": cores,
+            "kind": "port",
+            "sample": "one EM step on the first %d of %d tasks (%.1f s), scaled linearly in M"
+                      % (args.cpu_sample, M_TASKS, dt)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -137,6 +137,11 @@ int mb_m_step(mb_context*, const mb_kernel* kern_0, double* hp_0, const mb_kerne
               double* hp_i, int shared_hp, const double* m_0, const double* post_mean,
               const double* post_cov, double pen_diag, int64_t* stats);
 
+/* Per-task outcome of the last per-task M step: optim's `convergence` code (0 ok, 1 maxit,
+ * 52 abnormal line search, 99 non-finite objective -- R raises "L-BFGS-B needs finite values of
+ * 'fn'" there) and the number of objective evaluations.  Either pointer may be NULL. */
+int mb_last_task_status(mb_context*, int32_t* convergence, int32_t* n_eval);
+
 /* logL_monitoring (likelihoods.R:253-312). */
 int mb_logL_monitoring(mb_context*, const mb_kernel* kern_0, const double* hp_0,
                        const mb_kernel* kern_i, const double* hp_i, int hp_i_shared,

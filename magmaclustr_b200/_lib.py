@@ -56,6 +56,7 @@ _SIGS = {
     "mb_logL_GP_mod_tasks": [_vp, _kp, _dp, C.c_int, _dp, _dp, C.c_double, _dp, _dp, _ip],
     "mb_logL_GP_mod": [_vp, _kp, _dp, _dp, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, _dp, _dp],
     "mb_m_step": [_vp, _kp, _dp, _kp, _dp, C.c_int, _dp, _dp, _dp, C.c_double, _lp],
+    "mb_last_task_status": [_vp, _ip, _ip],
     "mb_logL_monitoring": [_vp, _kp, _dp, _kp, _dp, C.c_int, _dp, _dp, _dp, C.c_double, _dp],
     "mb_em_step": [_vp, _kp, _dp, _kp, _dp, C.c_int, _dp, C.c_double, _dp, _dp, _dp, _lp],
     "mb_train_magma": [_vp, _kp, _dp, _kp, _dp, C.c_int, _dp, C.c_double, C.c_int, C.c_double, _dp,

@@ -752,7 +752,7 @@ static int optimise(mb_context* c, std::vector<SingleProblem>& singles, bool tas
     MB_TRY(d2h(hn.data(), c->nfgv.p, M * 4, c->st));
     CU(cudaStreamSynchronize(c->st));
     int64_t tot = 0, bad = 0;
-    for (int64_t t = 0; t < M; ++t) { tot += hn[t]; if (hf[t] != 0) bad++; }
+    for (int64_t t = 0; t < M; ++t) { tot += hn[t]; if (hf[t] == 99) bad++; }
     if (stats) { stats[1] = rounds; stats[2] = tot; stats[3] = bad; }
     c->prof_evals += tot;
   }
@@ -963,6 +963,15 @@ extern "C" int mb_m_step(mb_context* c, const mb_kernel* kern_0, double* hp_0, c
   MB_TRY(dev_m_step(c, kern_0, hp_0, kern_i, c->hp_k.as<double>(), shared_hp, c->m0.as<double>(),
                     c->pm.as<double>(), c->pc.as<double>(), pen_diag, stats));
   MB_TRY(d2h(hp_i, c->hp_k.p, (size_t)c->db.n_tasks * P * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+extern "C" int mb_last_task_status(mb_context* c, int32_t* convergence, int32_t* n_eval) {
+  MB_TRY(need_db(c, false));
+  if (!c->fails.p || !c->nfgv.p) MB_FAIL(-1, "no per-task M step has run yet");
+  if (convergence) MB_TRY(d2h(convergence, c->fails.p, c->db.n_tasks * 4, c->st));
+  if (n_eval) MB_TRY(d2h(n_eval, c->nfgv.p, c->db.n_tasks * 4, c->st));
   CU(cudaStreamSynchronize(c->st));
   return 0;
 }

@@ -177,6 +177,12 @@ class Context:
                                 ptr(f64(post_cov)), float(pen_diag), ptr(stats)))
         return hp_0, hp_i, stats
 
+    def last_task_status(self):
+        conv = np.zeros(self.n_tasks, dtype=np.int32)
+        nev = np.zeros(self.n_tasks, dtype=np.int32)
+        check(L.lib().mb_last_task_status(self._h, ptr(conv), ptr(nev)))
+        return conv, nev
+
     def logL_monitoring(self, k0, hp_0, ki, hp_i, m_0, post_mean, post_cov, pen_diag=1e-10,
                         shared=False):
         out = C.c_double(0)

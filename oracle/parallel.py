@@ -1,0 +1,62 @@
+"""All-host-cores driver of the oracle's EM step (TEST INFRASTRUCTURE / CPU baseline only).
+
+The reference runs its per-task loops sequentially in one R thread
+(/root/reference/R/em-magma.R:200-230, R/likelihoods.R:271-298).  For the `cpu_baseline`
+and `--impl reference` legs of bench.py the same restated arithmetic (oracle/magma.py) is
+spread over a fork pool, one task per work item, so the CPU figure uses every host core.
+"""
+import math
+import multiprocessing as mp
+import os
+
+import numpy as np
+
+from . import magma as M
+
+_G = {}
+
+
+def _task_opt(i):
+    db, hp_i, kern_i, pm, pc, pen = (_G[k] for k in ("db", "hp_i", "kern_i", "pm", "pc", "pen"))
+    Xi, yi, mi, Si = M._task_views(db, pm, pc, i)
+    new, res = M._optim(hp_i[i],
+                        lambda h: M.logL_GP_mod(h, Xi, yi, mi, kern_i, Si, pen),
+                        lambda h: M.gr_GP_mod(h, Xi, yi, mi, kern_i, Si, pen))
+    return i, new, res["counts"]
+
+
+def _task_ll(i):
+    db, hp_i, kern_i, pm, pc, pen = (_G[k] for k in ("db", "new_hp_i", "kern_i", "pm", "pc", "pen"))
+    Xi, yi, mi, Si = M._task_views(db, pm, pc, i)
+    return M.logL_GP_mod(hp_i[i], Xi, yi, mi, kern_i, Si, pen)
+
+
+def em_step(db, m_0, kern_0, kern_i, hp_0, hp_i, pen_diag=1e-10, procs=None):
+    """One iteration of train_magma's loop body (training.R:905-1030), shared_hp = FALSE.
+    Returns (new_hp_0, new_hp_i, logL, n_task_evals)."""
+    procs = procs or os.cpu_count()
+    U = db.grid_X.shape[0]
+    m0 = M._mean_vec(m_0, U)
+    pm, pc = M.e_step(db, m0, kern_0, kern_i, hp_0, hp_i, pen_diag)
+    _G.update(db=db, hp_i=hp_i, kern_i=kern_i, pm=pm, pc=pc, pen=pen_diag)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        fut = pool.map_async(_task_opt, db.ids, chunksize=max(1, len(db.ids) // (4 * procs)))
+        new_hp_0, _ = M._optim(
+            hp_0,
+            lambda h: M.logL_GP_mod(h, db.grid_X, pm, m0, kern_0, pc, pen_diag),
+            lambda h: M.gr_GP_mod(h, db.grid_X, pm, m0, kern_0, pc, pen_diag))
+        out = fut.get()
+    new_hp_i = {i: h for i, h, _ in out}
+    evals = sum(c for _, _, c in out)
+    _G.update(new_hp_i=new_hp_i)
+    with ctx.Pool(procs) as pool:
+        lls = pool.map(_task_ll, db.ids, chunksize=max(1, len(db.ids) // (4 * procs)))
+    from scipy.linalg import lapack
+    ll_0 = M.logL_GP_mod(new_hp_0, db.grid_X, pm, m0, kern_0, pc, pen_diag)
+    c, info = lapack.dpotrf(np.asfortranarray(pc), lower=0, clean=1)
+    det = float(np.sum(np.log(np.diag(c)))) if info == 0 else math.nan
+    s = 0.0
+    for v in lls:
+        s += v
+    return new_hp_0, new_hp_i, -ll_0 - s + det, evals
