@@ -23,9 +23,11 @@ def r_signif(x, digits=6):
     e10 = (digits - 1 - np.floor(np.log10(ax))).astype(np.int64)
     pos = e10 > 0
     res = np.empty_like(ax)
+    extra = np.power(10.0, np.maximum(e10 - 308, 0).astype(np.float64))   # max10e split
+    e10 = np.minimum(e10, 308)
     p = np.power(10.0, np.where(pos, e10, 0).astype(np.float64))
     q = np.power(10.0, np.where(pos, 0, -e10).astype(np.float64))
-    res[pos] = np.rint(ax[pos] * p[pos]) / p[pos]
+    res[pos] = np.rint((ax[pos] * p[pos]) * extra[pos]) / p[pos] / extra[pos]
     res[~pos] = np.rint(ax[~pos] / q[~pos]) * q[~pos]
     out[ok] = np.sign(x[ok]) * res
     return out

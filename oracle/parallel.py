@@ -16,6 +16,15 @@ from . import magma as M
 _G = {}
 
 
+def _limit_blas_threads():
+    """One BLAS thread per worker: the pool already uses every core (no oversubscription)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        _G["_tp"] = threadpool_limits(1)
+    except Exception:  # pragma: no cover
+        os.environ["OPENBLAS_NUM_THREADS"] = "1"
+
+
 def _task_opt(i):
     db, hp_i, kern_i, pm, pc, pen = (_G[k] for k in ("db", "hp_i", "kern_i", "pm", "pc", "pen"))
     Xi, yi, mi, Si = M._task_views(db, pm, pc, i)
@@ -40,7 +49,8 @@ def em_step(db, m_0, kern_0, kern_i, hp_0, hp_i, pen_diag=1e-10, procs=None):
     pm, pc = M.e_step(db, m0, kern_0, kern_i, hp_0, hp_i, pen_diag)
     _G.update(db=db, hp_i=hp_i, kern_i=kern_i, pm=pm, pc=pc, pen=pen_diag)
     ctx = mp.get_context("fork")
-    with ctx.Pool(procs) as pool:
+    _limit_blas_threads()
+    with ctx.Pool(procs, initializer=_limit_blas_threads) as pool:
         fut = pool.map_async(_task_opt, db.ids, chunksize=max(1, len(db.ids) // (4 * procs)))
         new_hp_0, _ = M._optim(
             hp_0,
@@ -50,7 +60,7 @@ def em_step(db, m_0, kern_0, kern_i, hp_0, hp_i, pen_diag=1e-10, procs=None):
     new_hp_i = {i: h for i, h, _ in out}
     evals = sum(c for _, _, c in out)
     _G.update(new_hp_i=new_hp_i)
-    with ctx.Pool(procs) as pool:
+    with ctx.Pool(procs, initializer=_limit_blas_threads) as pool:
         lls = pool.map(_task_ll, db.ids, chunksize=max(1, len(db.ids) // (4 * procs)))
     from scipy.linalg import lapack
     ll_0 = M.logL_GP_mod(new_hp_0, db.grid_X, pm, m0, kern_0, pc, pen_diag)

@@ -11,6 +11,8 @@ Follows:
 """
 import math
 
+import numpy as np
+
 
 def r_signif(x, digits=6):
     """R's fprec(): round to `digits` significant digits."""
@@ -28,12 +30,15 @@ def r_signif(x, digits=6):
         x = -x
     l10 = math.log10(x)
     e10 = int(dig - 1 - math.floor(l10))
+    p10 = 1.0
+    if e10 > 308:                       # max10e: split the power so it stays finite
+        p10 = 10.0 ** (e10 - 308)
+        e10 = 308
     if e10 > 0:
-        p10 = 10.0 ** e10
-        return sgn * (float(round(x * p10)) / p10) if abs(x * p10) < 2 ** 52 \
-            else sgn * x
-    p10 = 10.0 ** (-e10)
-    return sgn * (float(round(x / p10)) * p10)
+        pow10 = 10.0 ** e10
+        return sgn * (float(np.rint((x * pow10) * p10)) / pow10) / p10
+    pow10 = 10.0 ** (-e10)
+    return sgn * (float(np.rint(x / pow10)) * pow10)
 
 
 def r_as_character(x):
