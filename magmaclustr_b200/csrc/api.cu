@@ -19,15 +19,38 @@ cudaError_t launch_task_inverse(TaskInvArgs a, int n_ctas, cudaStream_t st);
 cudaError_t launch_task_cov(TaskData db, DevKern kd, const double* hp, int64_t hp_stride,
                             int deriv, double* out, const int64_t* out_offs, cudaStream_t st);
 int task_max_ctas_per_sm(int nmax, int D);
+cudaError_t launch_task_objective2(TaskObjArgs a, int n_launch, cudaStream_t st);
+cudaError_t launch_task_inverse2(TaskInvArgs a, int n_ctas, cudaStream_t st);
+int task2_max_ctas_per_sm(int nmax, int D);
+
+// kernel generation switch: v2 = DMMA-tiled (default); MB_TASK_KERNEL=v1 selects the first,
+// scalar shared-memory version (kept as an independent cross-check)
+static bool use_v2() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MB_TASK_KERNEL"); v = (e && e[0] == 'v' && e[1] == '1') ? 0 : 1; }
+  return v == 1;
+}
+static cudaError_t launch_task_objective_any(TaskObjArgs a, int n_launch, cudaStream_t st) {
+  if (use_v2() && a.mode != TK_OBJ_MARG) return launch_task_objective2(a, n_launch, st);
+  return launch_task_objective(a, n_launch, st);
+}
+static cudaError_t launch_task_inverse_any(TaskInvArgs a, int n_ctas, cudaStream_t st) {
+  return use_v2() ? launch_task_inverse2(a, n_ctas, st) : launch_task_inverse(a, n_ctas, st);
+}
+static int task_ctas_per_sm_any(int nmax, int D) {
+  return use_v2() ? task2_max_ctas_per_sm(nmax, D) : task_max_ctas_per_sm(nmax, D);
+}
 cudaError_t launch_dense_cov(const DevKern& kd, const double* hp_host, const double* x1, int n1,
                              const double* x2, int n2, int D, int deriv, int with_noise,
                              double* out, int64_t rs, int64_t cs, cudaStream_t st);
 cudaError_t launch_legacy_builder(int which, const double* m1, int n1, const double* m2, int n2,
                                   int d, double par, double* out, cudaStream_t st);
-cudaError_t launch_dense_cholinv(const double* src, int ld_src, double* A, double* B, int n,
-                                 double pen, int* info, double* out, cudaStream_t st);
-cudaError_t launch_dense_chol_logdiag(const double* src, double* W, int n, int* info, double* out,
-                                      cudaStream_t st);
+cudaError_t launch_dense_cholinv(const double* src, int ld_src, double* A, double* B, double* Xd,
+                                 double* inv, int n, double pen, int* info, double* out,
+                                 cudaStream_t st);
+cudaError_t launch_dense_chol_logdiag(const double* src, double* W, double* Xd, int n, int* info,
+                                      double* out, cudaStream_t st);
+size_t dense_xd_doubles(int n);
 cudaError_t launch_dense_lu_logdet(const double* src, double* W, int n, int* done, double* out,
                                    cudaStream_t st);
 cudaError_t launch_gemm(int m, int n, int k, const double* A, int64_t ars, int64_t acs,
@@ -89,7 +112,7 @@ struct DBuf {
 };
 
 struct DenseWs {   // workspace of one dense n x n problem
-  DBuf Kmat, A, B, T, S, vecs, part, res, info, done;
+  DBuf Kmat, A, B, T, S, Ap, Bp, Xd, vecs, part, res, info, done;
   int n = 0;
   double* r() { return vecs.as<double>(); }
   double* al() { return vecs.as<double>() + n; }
@@ -98,13 +121,16 @@ struct DenseWs {   // workspace of one dense n x n problem
     n = nn;
     size_t m = (size_t)nn * nn * sizeof(double);
     if (Kmat.ensure(m) || A.ensure(m) || B.ensure(m) || T.ensure(m) || S.ensure(m)) return -3;
+    const size_t npad = (size_t)((nn + 7) / 8) * 8;
+    if (Ap.ensure(npad * npad * sizeof(double)) || Bp.ensure(npad * npad * sizeof(double)) ||
+        Xd.ensure(dense_xd_doubles(nn) * sizeof(double))) return -3;
     if (vecs.ensure(4 * (size_t)nn * sizeof(double))) return -3;
     if (part.ensure((size_t)dense_obj_nparts(nn) * (1 + MB_MAX_HP) * sizeof(double))) return -3;
     if (res.ensure(32 * sizeof(double)) || info.ensure(8 * sizeof(int))) return -3;
     if (done.ensure((size_t)nn * sizeof(int))) return -3;
     return 0;
   }
-  void release() { Kmat.release(); A.release(); B.release(); T.release(); S.release(); vecs.release();
+  void release() { Kmat.release(); A.release(); B.release(); T.release(); S.release(); Ap.release(); Bp.release(); Xd.release(); vecs.release();
                    part.release(); res.release(); info.release(); done.release(); }
 };
 
@@ -150,7 +176,7 @@ struct mb_context {
 // launch of the dominant kernel, optionally bracketed by events (mb_profile)
 static int launch_obj(mb_context* c, const TaskObjArgs& a, int n_launch, cudaStream_t st,
                       bool profiled = false) {
-  if (!c->prof_on || !profiled) { LAUNCH(c, launch_task_objective(a, n_launch, st)); return 0; }
+  if (!c->prof_on || !profiled) { LAUNCH(c, launch_task_objective_any(a, n_launch, st)); return 0; }
   if (c->prof_used == c->prof_ev.size()) {
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
@@ -159,7 +185,7 @@ static int launch_obj(mb_context* c, const TaskObjArgs& a, int n_launch, cudaStr
   }
   auto& ev = c->prof_ev[c->prof_used++];
   CU(cudaEventRecord(ev.first, st));
-  LAUNCH(c, launch_task_objective(a, n_launch, st));
+  LAUNCH(c, launch_task_objective_any(a, n_launch, st));
   CU(cudaEventRecord(ev.second, st));
   return 0;
 }
@@ -205,8 +231,10 @@ extern "C" int mb_create(mb_context** out, int device) {
   CU(cudaMallocHost((void**)&c->h_pin_i, 1024 * sizeof(int)));
   CU(cudaEventCreate(&c->ev_t0));
   CU(cudaEventCreate(&c->ev_t1));
-  const char* env = getenv("MB_LOGDET_CHOL");
-  c->logdet_chol = (env && env[0] == '1') ? 1 : 0;
+  // log|det(inv)|: read off the Cholesky diagonal by default; MB_LOGDET=lu reproduces the
+  // reference's determinant() (LU of the explicit inverse, likelihoods.R:37-41) -- see DESIGN.md
+  const char* env = getenv("MB_LOGDET");
+  c->logdet_chol = (env && env[0] == 'l' && env[1] == 'u') ? 0 : 1;
   *out = c;
   return 0;
 }
@@ -367,8 +395,8 @@ extern "C" int mb_kern_to_cov(mb_context* c, const mb_kernel* k, const double* h
 // src (n x n, upper read) -> ws.A = inverse.  Synchronises `s`; returns >0 on numerical failure.
 static int dev_cholinv(mb_context* c, DenseWs& ws, const double* src, int n, double pen,
                        cudaStream_t s, int* retries, double* jitter, double* sumlogdiag) {
-  LAUNCH(c, launch_dense_cholinv(src, n, ws.A.as<double>(), ws.B.as<double>(), n, pen,
-                                 ws.info.as<int>(), ws.res.as<double>() + 16, s));
+  LAUNCH(c, launch_dense_cholinv(src, n, ws.Ap.as<double>(), ws.Bp.as<double>(), ws.Xd.as<double>(),
+                                 ws.A.as<double>(), n, pen, ws.info.as<int>(), ws.res.as<double>() + 16, s));
   MB_TRY(d2h(c->h_pin_i, ws.info.p, sizeof(int), s));
   MB_TRY(d2h(c->h_pin + 200, ws.res.as<double>() + 16, 2 * sizeof(double), s));
   CU(cudaStreamSynchronize(s));
@@ -508,9 +536,9 @@ extern "C" int mb_list_kern_to_mat(mb_context* c, const mb_kernel* k, int64_t n_
     a.db = db; a.kd = kd; a.hp = b_hp.as<double>(); a.hp_stride = hp_shared ? 0 : k->n_hp;
     a.pen = pen_diag; a.K = 1; a.inv_out = b_out.as<double>(); a.inv_offs = b_oo.as<int64_t>();
     a.retries = b_ret.as<int32_t>();
-    int g = c->sm_count * task_max_ctas_per_sm(nmax, d);
+    int g = c->sm_count * task_ctas_per_sm_any(nmax, d);
     if (g > n_tasks) g = (int)n_tasks;
-    e = launch_task_inverse(a, g, c->st);
+    e = launch_task_inverse_any(a, g, c->st);
   }
   c->launches++;
   if (e == cudaSuccess) e = cudaMemcpyAsync(out, b_out.p, total * 8, cudaMemcpyDeviceToHost, c->st);
@@ -542,8 +570,9 @@ static int dense_obj_enqueue(mb_context* c, DenseWs& ws, const DevKern& kd, cons
                              const double* S, double pen, int want_grad, cudaStream_t s,
                              double* hres, int* hinfo) {
   LAUNCH(c, launch_dense_cov(kd, hp_host, X, n, X, n, D, -1, 1, ws.Kmat.as<double>(), n, 1, s));
-  LAUNCH(c, launch_dense_cholinv(ws.Kmat.as<double>(), n, ws.A.as<double>(), ws.B.as<double>(), n,
-                                 pen, ws.info.as<int>(), ws.res.as<double>() + 16, s));
+  LAUNCH(c, launch_dense_cholinv(ws.Kmat.as<double>(), n, ws.Ap.as<double>(), ws.Bp.as<double>(),
+                                 ws.Xd.as<double>(), ws.A.as<double>(), n, pen, ws.info.as<int>(),
+                                 ws.res.as<double>() + 16, s));
   const double* logdet;
   if (c->logdet_chol) {
     logdet = ws.res.as<double>() + 17;
@@ -596,7 +625,7 @@ static int dev_e_step(mb_context* c, int K, const mb_kernel* kern_k, const doubl
     CU(cudaMemcpyAsync(c->inv0.as<double>() + k * UU, c->ws1.A.p, UU * 8, cudaMemcpyDeviceToDevice, c->st2));
   }
   // task inverses + deterministic partial sums
-  int G = c->sm_count * task_max_ctas_per_sm(c->db.nmax, c->db.D);
+  int G = c->sm_count * task_ctas_per_sm_any(c->db.nmax, c->db.D);
   if (G > c->db.n_tasks) G = (int)c->db.n_tasks;
   const size_t cap = (size_t)2 << 30;
   while (G > 1 && (size_t)G * K * UU * 8 > cap) G = (G + 1) / 2;
@@ -611,7 +640,7 @@ static int dev_e_step(mb_context* c, int K, const mb_kernel* kern_k, const doubl
   a.kd = kdi; a.hp = hp_i_dev; a.hp_stride = hp_stride; a.pen = pen; a.K = K; a.tau = tau_dev; a.U = U;
   a.part_inv = c->part_inv.as<double>(); a.part_w = c->part_w.as<double>();
   a.retries = c->retries.as<int32_t>();
-  LAUNCH(c, launch_task_inverse(a, G, c->st));
+  LAUNCH(c, launch_task_inverse_any(a, G, c->st));
   CU(cudaStreamSynchronize(c->st2));
   // post_inv_k = inv_k (+) sum_i tau_ik inv_i ; weighted_k = inv_k m_k (+) sum_i tau_ik inv_i y_i
   if (c->world > 1) {
@@ -935,8 +964,8 @@ static int dev_logL_monitoring(mb_context* c, const mb_kernel* kern_0, const dou
   LAUNCH(c, launch_sum_sequential(a.f, c->db.n_tasks, 1, c->sums.as<double>(), c->st));
   MB_TRY(ctx_allreduce(c, c->sums.p, 1, c->st));
   // det term: chol(post_cov) without jitter (likelihoods.R:303-307)
-  LAUNCH(c, launch_dense_chol_logdiag(pc_dev, c->ws1.A.as<double>(), c->U, c->ws1.info.as<int>(),
-                                      c->sums.as<double>() + 8, c->st));
+  LAUNCH(c, launch_dense_chol_logdiag(pc_dev, c->ws1.Ap.as<double>(), c->ws1.Xd.as<double>(), c->U,
+                                      c->ws1.info.as<int>(), c->sums.as<double>() + 8, c->st));
   MB_TRY(d2h(c->h_pin, c->sums.p, 16 * 8, c->st));
   MB_TRY(d2h(c->h_pin_i, c->ws1.info.p, sizeof(int), c->st));
   CU(cudaStreamSynchronize(c->st));

@@ -54,24 +54,46 @@ __device__ __forceinline__ PairSums pair_sums(const double* xa, const double* xb
   return s;
 }
 
+// Exponentials of the HPs that every matrix element needs, computed once per thread:
+// SE / RQ: (exp(v), exp(-l)[, -]); PERIO: (exp(v), exp(-l), pi / exp(period)); LIN: (exp(slope),
+// exp(offset)); noise: exp(noise).  They are the very sub-expressions of kernels.R, so hoisting
+// them does not change any rounding.
+__device__ __forceinline__ void prep_hp(const DevKern& kd, const double* hp, double* hpe) {
+  for (int t = 0; t < kd.n_terms; ++t) {
+    const double* h = hp + kd.hp_off[t];
+    double* e = hpe + kd.hp_off[t];
+    const int type = kd.types[t];
+    if (type == MB_KERN_LIN) { e[0] = exp(h[0]); e[1] = exp(h[1]); }
+    else {
+      e[0] = exp(h[0]);
+      e[1] = exp(-h[1]);
+      if (type == MB_KERN_PERIO) e[2] = MB_PI / exp(h[2]);
+      if (type == MB_KERN_RQ) e[2] = h[2];
+    }
+  }
+  if (kd.has_noise) hpe[kd.n_hp - 1] = exp(hp[kd.n_hp - 1]);
+}
+
 // One base kernel and, when WITH_DERIV, its derivatives w.r.t. its own HPs
 // (/root/reference/R/kernels.R:164-398).  dv has mb_term_nhp(type) entries.
 template <bool WITH_DERIV>
-__device__ __forceinline__ double base_kernel(int type, const double* hp, const PairSums& s,
-                                              const double* xa, const double* xb, int D,
-                                              double* dv) {
+__device__ __forceinline__ double base_kernel(int type, const double* hp, const double* e,
+                                              const PairSums& s, const double* xa,
+                                              const double* xb, int D, double* dv) {
   if (type == MB_KERN_SE) {
     // kernels.R:182-189: top = exp(-l) * 0.5 * d2 ; K = exp(v - top)
-    double top = exp(-hp[1]) * 0.5 * s.d2;
+    double top = e[1] * 0.5 * s.d2;
     double k = exp(hp[0] - top);
     if (WITH_DERIV) {
       dv[0] = k;
-      dv[1] = exp(hp[0]) * top * exp(-top);
+      // the reference evaluates exp(v) * top * exp(-top); k * top is the same number up to
+      // one rounding and saves two exponentials per matrix element
+      dv[1] = k * top;
     }
     return k;
   } else if (type == MB_KERN_PERIO) {
     // code.cpp:31-76 + kernels.R:243-263
-    double w = MB_PI / exp(hp[2]);
+    double w = e[2];
     double perio = 0.0, sderiv = 0.0;
     for (int c = 0; c < D; ++c) {
       double ang = w * fabs(xa[c] - xb[c]);
@@ -80,32 +102,32 @@ __device__ __forceinline__ double base_kernel(int type, const double* hp, const 
       perio += sn * sn;
       if (WITH_DERIV) sderiv += 2 * sn * cs * ang;
     }
-    double el = exp(-hp[1]);
-    double k = exp(hp[0]) * exp(-2 * el * perio);
+    double el = e[1];
+    double k = e[0] * exp(-2 * el * perio);
     if (WITH_DERIV) {
       dv[0] = k;
-      dv[1] = exp(hp[0]) * 2 * perio * el * exp(-2 * perio * el);
+      dv[1] = e[0] * 2 * perio * el * exp(-2 * perio * el);
       dv[2] = k * 2 * el * sderiv;
     }
     return k;
   } else if (type == MB_KERN_RQ) {
     // kernels.R:312-333 (rq_scale raw)
-    double el = exp(-hp[1]);
+    double el = e[1];
     double a = hp[2];
     double term = 1 + s.d2 * el / (2 * a);
-    double k = exp(hp[0]) * pow(term, -a);
+    double k = e[0] * pow(term, -a);
     if (WITH_DERIV) {
       dv[0] = k;
-      dv[1] = exp(hp[0]) * s.d2 * 0.5 * el * pow(term, -a - 1);
+      dv[1] = e[0] * s.d2 * 0.5 * el * pow(term, -a - 1);
       dv[2] = k * (s.d2 * el / (2 * a * term) - log(term));
     }
     return k;
   } else {
     // kernels.R:385-391: exp(slope) * prod + exp(offset)
-    double k = exp(hp[0]) * s.xy + exp(hp[1]);
+    double k = e[0] * s.xy + e[1];
     if (WITH_DERIV) {
-      dv[0] = exp(hp[0]) * s.xy;
-      dv[1] = exp(hp[1] * 1.0);
+      dv[0] = e[0] * s.xy;
+      dv[1] = e[1];
     }
     return k;
   }
@@ -116,18 +138,18 @@ __device__ __forceinline__ double base_kernel(int type, const double* hp, const 
 // HP of a product factor is d(k_j) * prod_{i != j} k_i (left-to-right), of a summand d(k_j)
 // alone; the noise term adds exp(noise) on coincident pairs (:440-447,:481-487).
 template <bool WITH_DERIV>
-__device__ __forceinline__ double cov_eval(const DevKern& kd, const double* hp, const double* xa,
-                                           const double* xb, int D, bool with_noise,
-                                           double* dval) {
+__device__ __forceinline__ double cov_eval(const DevKern& kd, const double* hp, const double* hpe,
+                                           const double* xa, const double* xb, int D,
+                                           bool with_noise, double* dval) {
   PairSums s = pair_sums(xa, xb, D);
   double val;
   if (kd.n_terms == 1) {
-    val = base_kernel<WITH_DERIV>(kd.types[0], hp, s, xa, xb, D, dval);
+    val = base_kernel<WITH_DERIV>(kd.types[0], hp, hpe, s, xa, xb, D, dval);
   } else {
     double kv[MB_MAX_TERMS];
     double dv[MB_MAX_HP];
     for (int t = 0; t < kd.n_terms; ++t)
-      kv[t] = base_kernel<WITH_DERIV>(kd.types[t], hp + kd.hp_off[t], s, xa, xb, D,
+      kv[t] = base_kernel<WITH_DERIV>(kd.types[t], hp + kd.hp_off[t], hpe + kd.hp_off[t], s, xa, xb, D,
                                       dv + kd.hp_off[t]);
     val = 0.0;
     for (int t = 0; t < kd.n_prod; ++t) val = (t == 0) ? (0.0 + kv[0]) : val * kv[t];
@@ -150,7 +172,7 @@ __device__ __forceinline__ double cov_eval(const DevKern& kd, const double* hp, 
     }
   }
   if (kd.has_noise) {
-    double nz = (s.l1 < 0.000001) ? exp(hp[kd.n_hp - 1]) : 0.0;
+    double nz = (s.l1 < 0.000001) ? hpe[kd.n_hp - 1] : 0.0;
     if (with_noise) val += nz;
     if (WITH_DERIV) dval[kd.n_hp - 1] = nz;
   }

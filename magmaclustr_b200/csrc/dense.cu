@@ -9,6 +9,9 @@
 // chol(post_cov) of logL_monitoring (R/likelihoods.R:303-307) and the matrix algebra of
 // pred_magma (R/prediction.R:1146-1189).
 #include "linalg.cuh"
+#include "tiles.cuh"
+
+#define NWD 16 /* warps of the single-CTA union-grid kernels */
 
 struct HpVal { double v[MB_MAX_HP]; };
 
@@ -17,14 +20,16 @@ __global__ void k_dense_cov(DevKern kd, HpVal hp, const double* x1, int n1, cons
                             int n2, int D, int deriv, int with_noise, double* out, int64_t rs,
                             int64_t cs) {
   const int64_t tot = (int64_t)n1 * n2;
+  double hpe[MB_MAX_HP];
+  prep_hp(kd, hp.v, hpe);
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < tot;
        e += (int64_t)gridDim.x * blockDim.x) {
     int i = (int)(e / n2), j = (int)(e % n2);
     double dv[MB_MAX_HP];
     double v;
-    if (deriv < 0) v = cov_eval<false>(kd, hp.v, x1 + (size_t)i * D, x2 + (size_t)j * D, D,
+    if (deriv < 0) v = cov_eval<false>(kd, hp.v, hpe, x1 + (size_t)i * D, x2 + (size_t)j * D, D,
                                        with_noise != 0, nullptr);
-    else { cov_eval<true>(kd, hp.v, x1 + (size_t)i * D, x2 + (size_t)j * D, D, with_noise != 0, dv);
+    else { cov_eval<true>(kd, hp.v, hpe, x1 + (size_t)i * D, x2 + (size_t)j * D, D, with_noise != 0, dv);
            v = dv[deriv]; }
     out[i * rs + j * cs] = v;
   }
@@ -52,31 +57,48 @@ __global__ void k_legacy_builder(int which, const double* m1, int n1, const doub
   }
 }
 
-// chol_inv_jitter of one matrix by a single CTA.  src: n x n (upper triangle read), A: result
-// (full symmetric inverse), B: scratch.  info[0] = retries (-1: gave up), out[0] = total
-// jitter, out[1] = sum log diag(R) of the successful factorisation.
-__global__ void __launch_bounds__(1024) k_dense_cholinv(const double* src, int ld_src,
-                                                        double* A, double* B, int n, double pen,
-                                                        int max_retry, int* info, double* out) {
+// Padded copy of the upper triangle of src (+ cumulative jitter) into A (np x np, identity on
+// the padding), kernel-to-matrices.R:672-678.
+__device__ inline void dense_load_padded(const double* src, int ld_src, double* A, int n, int np,
+                                         double pen, int retries) {
+  for (int e = threadIdx.x; e < np * np; e += blockDim.x) {
+    int i = e / np, j = e - i * np;
+    double v = 0.0;
+    if (i < n && j < n) {
+      if (j >= i) {
+        v = src[(size_t)i * ld_src + j];
+        if (i == j && retries >= 0) {
+          double q = pen;
+          for (int r = 0; r <= retries; ++r) { v += q; q = 10 * q; }
+        }
+      }
+    } else if (i == j) {
+      v = 1.0;
+    }
+    A[e] = v;
+  }
+  __syncthreads();
+}
+
+// chol_inv_jitter of one matrix by a single CTA (32 warps) with the tile algorithms of
+// tiles.cuh on L2-resident buffers.  src: n x n (upper triangle read); A, B: np x np scratch
+// (np = n rounded up to 8); Xd: (np / 8) * XD_STRIDE doubles; inv: n x n result (full, exactly
+// symmetric).  info[0] = retries (-1: gave up), out[0] = total jitter, out[1] = sum log diag(R).
+__global__ void __launch_bounds__(512) k_dense_cholinv(const double* src, int ld_src, double* A,
+                                                        double* B, double* Xd, double* inv, int n,
+                                                        double pen, int max_retry, int* info,
+                                                        double* out) {
   __shared__ double red[32];
+  __shared__ int flag;
+  const int np = ((n + 7) / 8) * 8, n8 = np / 8;
   int retries = 0;
   double total = 0.0;
   for (;;) {
     double p = pen;
     total = 0.0;
     for (int r = 0; r <= retries; ++r) { total += p; p = 10 * p; }
-    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-      int i = e / n, j = e % n;
-      if (j < i) continue;
-      double v = src[(size_t)i * ld_src + j];
-      if (i == j) {
-        double q = pen;
-        for (int r = 0; r <= retries; ++r) { v += q; q = 10 * q; }
-      }
-      A[(size_t)i * n + j] = v;
-    }
-    __syncthreads();
-    if (blk_chol_upper(A, n, n) == 0) break;
+    dense_load_padded(src, ld_src, A, n, np, pen, retries);
+    if (chol_tiles<NWD>(A, Xd, n8, np, &flag) == 0) break;
     __syncthreads();
     if (++retries > max_retry) {
       if (threadIdx.x == 0) { info[0] = -1; out[0] = total; out[1] = NAN; }
@@ -84,23 +106,28 @@ __global__ void __launch_bounds__(1024) k_dense_cholinv(const double* src, int l
     }
   }
   double v[1] = {0.0};
-  for (int j = threadIdx.x; j < n; j += blockDim.x) v[0] += log(A[(size_t)j * n + j]);
+  for (int j = threadIdx.x; j < n; j += blockDim.x) v[0] += log(A[(size_t)j * np + j]);
   blk_reduce_sum<1>(v, red);
   if (threadIdx.x == 0) { info[0] = retries; out[0] = total; out[1] = v[0]; }
-  blk_tri_inv_upper(A, B, n, n);
-  blk_lauum_upper(B, A, n, n);
+  trtri_tiles<NWD>(A, Xd, B, n8, np);
+  lauum_tiles<NWD>(B, A, n8, np);
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    int i = e / n, j = e - i * n;
+    inv[e] = A[(size_t)i * np + j];
+  }
 }
 
 // sum log diag chol(src) with NO jitter (likelihoods.R:303-307); info[0] = 0 or failing pivot.
-__global__ void __launch_bounds__(1024) k_dense_chol_logdiag(const double* src, double* W, int n,
-                                                             int* info, double* out) {
+__global__ void __launch_bounds__(512) k_dense_chol_logdiag(const double* src, double* W, double* Xd,
+                                                             int n, int* info, double* out) {
   __shared__ double red[32];
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) W[e] = src[e];
-  __syncthreads();
-  int r = blk_chol_upper(W, n, n);
+  __shared__ int flag;
+  const int np = ((n + 7) / 8) * 8, n8 = np / 8;
+  dense_load_padded(src, n, W, n, np, 0.0, -1);
+  int r = chol_tiles<NWD>(W, Xd, n8, np, &flag);
   if (r != 0) { if (threadIdx.x == 0) { info[0] = r; out[0] = NAN; } return; }
   double v[1] = {0.0};
-  for (int j = threadIdx.x; j < n; j += blockDim.x) v[0] += log(W[(size_t)j * n + j]);
+  for (int j = threadIdx.x; j < n; j += blockDim.x) v[0] += log(W[(size_t)j * np + j]);
   blk_reduce_sum<1>(v, red);
   if (threadIdx.x == 0) { info[0] = 0; out[0] = v[0]; }
 }
@@ -186,7 +213,8 @@ __global__ void __launch_bounds__(256) k_dense_obj_partials(
   __shared__ double red[4 * 32];
   const int P = kd.n_hp;
   double tr = 0.0;
-  double gacc[MB_MAX_HP];
+  double gacc[MB_MAX_HP], hpe[MB_MAX_HP];
+  prep_hp(kd, hp.v, hpe);
 #pragma unroll
   for (int p = 0; p < MB_MAX_HP; ++p) gacc[p] = 0.0;
   const int64_t tot = (int64_t)n * n;
@@ -199,7 +227,7 @@ __global__ void __launch_bounds__(256) k_dense_obj_partials(
       double w = al[i] * al[j] - a;
       if (T) w += T[e];
       double dv[MB_MAX_HP];
-      cov_eval<true>(kd, hp.v, x + (size_t)i * D, x + (size_t)j * D, D, true, dv);
+      cov_eval<true>(kd, hp.v, hpe, x + (size_t)i * D, x + (size_t)j * D, D, true, dv);
       for (int p = 0; p < P; ++p) gacc[p] += w * dv[p];
     }
   }
@@ -306,7 +334,9 @@ __global__ void k_pred_var(DevKern kd, HpVal hp, const double* xp, int np, int D
                            double noise, double* out) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= np) return;
-  double kjj = cov_eval<false>(kd, hp.v, xp + (size_t)j * D, xp + (size_t)j * D, D, false, nullptr);
+  double hpe[MB_MAX_HP];
+  prep_hp(kd, hp.v, hpe);
+  double kjj = cov_eval<false>(kd, hp.v, hpe, xp + (size_t)j * D, xp + (size_t)j * D, D, false, nullptr);
   double s = 0.0;
   for (int i = 0; i < no; ++i) s += C[i + (size_t)j * no] * GC[(size_t)i * np + j];
   out[j] = ((kjj + sdiag[j]) - s) + noise;
@@ -337,17 +367,20 @@ cudaError_t launch_legacy_builder(int which, const double* m1, int n1, const dou
   return cudaGetLastError();
 }
 
-cudaError_t launch_dense_cholinv(const double* src, int ld_src, double* A, double* B, int n,
-                                 double pen, int* info, double* out, cudaStream_t st) {
-  k_dense_cholinv<<<1, 1024, 0, st>>>(src, ld_src, A, B, n, pen, 40, info, out);
+cudaError_t launch_dense_cholinv(const double* src, int ld_src, double* A, double* B, double* Xd,
+                                 double* inv, int n, double pen, int* info, double* out,
+                                 cudaStream_t st) {
+  k_dense_cholinv<<<1, 512, 0, st>>>(src, ld_src, A, B, Xd, inv, n, pen, 40, info, out);
   return cudaGetLastError();
 }
 
-cudaError_t launch_dense_chol_logdiag(const double* src, double* W, int n, int* info, double* out,
-                                      cudaStream_t st) {
-  k_dense_chol_logdiag<<<1, 1024, 0, st>>>(src, W, n, info, out);
+cudaError_t launch_dense_chol_logdiag(const double* src, double* W, double* Xd, int n, int* info,
+                                      double* out, cudaStream_t st) {
+  k_dense_chol_logdiag<<<1, 512, 0, st>>>(src, W, Xd, n, info, out);
   return cudaGetLastError();
 }
+
+size_t dense_xd_doubles(int n) { return (size_t)((n + 7) / 8) * XD_STRIDE; }
 
 cudaError_t launch_dense_lu_logdet(const double* src, double* W, int n, int* done, double* out,
                                    cudaStream_t st) {

@@ -46,10 +46,12 @@ __device__ inline TaskSmem carve(double* base, int nmax, int ld, int D) {
 __device__ inline void build_cov_upper(double* A, int n, int ld, const double* xs, int D,
                                        const DevKern& kd, const double* hp, const double* Sadd,
                                        double pen, int retries) {
+  double hpe[MB_MAX_HP];
+  prep_hp(kd, hp, hpe);
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
     int i = e / n, j = e % n;
     if (j < i) continue;
-    double v = cov_eval<false>(kd, hp, xs + i * D, xs + j * D, D, true, nullptr);
+    double v = cov_eval<false>(kd, hp, hpe, xs + i * D, xs + j * D, D, true, nullptr);
     if (Sadd) v += Sadd[i * ld + j];
     if (i == j) {
       double p = pen;
@@ -216,7 +218,8 @@ __global__ void __launch_bounds__(256) k_task_objective(TaskObjArgs a) {
     blk_gemm_nn(s.B, s.C, s.A, n, ld);  // B = S A
     blk_gemm_nn(s.C, s.A, s.B, n, ld);  // C = A S A
   }
-  double gacc[MB_MAX_HP];
+  double gacc[MB_MAX_HP], hpe[MB_MAX_HP];
+  prep_hp(a.kd, hp, hpe);
 #pragma unroll
   for (int p = 0; p < MB_MAX_HP; ++p) gacc[p] = 0.0;
   for (int e = tid; e < n * n; e += nt) {
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(256) k_task_objective(TaskObjArgs a) {
       w += w2;
     }
     double dv[MB_MAX_HP];
-    cov_eval<true>(a.kd, hp, s.xs + i * D, s.xs + j * D, D, true, dv);
+    cov_eval<true>(a.kd, hp, hpe, s.xs + i * D, s.xs + j * D, D, true, dv);
     for (int p = 0; p < P; ++p) gacc[p] += w * dv[p];
   }
   // reduce P sums (in chunks of 4 to bound the scratch)
@@ -304,14 +307,16 @@ __global__ void k_task_cov(TaskData db, DevKern kd, const double* hp, int64_t hp
   const int D = db.D;
   double hpl[MB_MAX_HP];
   for (int p = 0; p < kd.n_hp; ++p) hpl[p] = hp[t * hp_stride + p];
+  double hpe[MB_MAX_HP];
+  prep_hp(kd, hpl, hpe);
   const double* x = db.X + row0 * D;
   double* o = out + out_offs[t];
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
     int i = e % n, j = e / n;  // column-major output, consecutive threads -> consecutive rows
     double dv[MB_MAX_HP];
     double v;
-    if (deriv < 0) v = cov_eval<false>(kd, hpl, x + i * D, x + j * D, D, true, nullptr);
-    else { cov_eval<true>(kd, hpl, x + i * D, x + j * D, D, true, dv); v = dv[deriv]; }
+    if (deriv < 0) v = cov_eval<false>(kd, hpl, hpe, x + i * D, x + j * D, D, true, nullptr);
+    else { cov_eval<true>(kd, hpl, hpe, x + i * D, x + j * D, D, true, dv); v = dv[deriv]; }
     o[e] = v;
   }
 }

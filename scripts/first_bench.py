@@ -11,8 +11,8 @@ N = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 t = time.time(); df, _ = simu_db(M=M, N=N, seed=2024); print("simu", time.time() - t)
 t = time.time(); prep = Prepared(df.ID.values, df.Input.values, df.Output.values); print("prep", time.time() - t, "U", len(prep.grid_keys))
 k0 = L.parse_kernel("SE", False); ki = L.parse_kernel("SE", True)
-hp0 = ini_hp("SE", ["0"], True, False, 1).drop(columns="ID").iloc[0].to_numpy()
-hpi = ini_hp("SE", prep.ids, False, True, 2).drop(columns="ID").to_numpy()
+hp0 = ini_hp("SE", ["0"], True, False, 6).drop(columns="ID").iloc[0].to_numpy()
+hpi = ini_hp("SE", prep.ids, True, True, 106).drop(columns="ID").to_numpy()
 ctx = Context(0)
 t = time.time(); ctx.upload_dataset(prep.offs, prep.X, prep.y, prep.grid_index, prep.grid_X); print("upload", time.time() - t)
 m0 = np.zeros(ctx.U)
