@@ -35,3 +35,19 @@ def upload(ctx, case):
 def relerr(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def ulp_perturb(x, rng, k=1.0):
+    """Multiply every entry by (1 +/- k * 2^-52): the smallest change an input can undergo.
+    Quantities whose oracle value moves by d under this perturbation cannot be reproduced by ANY
+    other correct implementation to better than ~d."""
+    x = np.asarray(x, dtype=np.float64)
+    return x * (1.0 + k * 2.0 ** -52 * rng.choice([-1.0, 1.0], size=x.shape))
+
+
+def oracle_sensitivity(fn, args_perturbed_list, base):
+    """max over perturbed evaluations of the relative deviation (w.r.t. max |base|) of fn."""
+    worst = 0.0
+    for a in args_perturbed_list:
+        worst = max(worst, relerr(fn(*a), base))
+    return worst
