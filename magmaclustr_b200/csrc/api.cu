@@ -1266,3 +1266,305 @@ extern "C" int mb_pred_magma(mb_context* c, const mb_kernel* k, const double* hp
   CU(cudaStreamSynchronize(s));
   return 0;
 }
+
+// ================================================================================================
+// MagmaClust: ve_step / update_mixture / vm_step / elbo_monitoring_VEM
+// ================================================================================================
+
+// R's round(x, digits) for digits > 0 (nmath/fround.c, R >= 4.0.0): the closer of the two
+// neighbouring decimals, ties to the even one.  vem-magmaclust.R:392 rounds tau to 5 decimals.
+static double r_round(double x, int dig) {
+  if (!std::isfinite(x)) return x;
+  double sgn = 1.0;
+  if (x < 0) { sgn = -1.0; x = -x; }
+  long double p10 = 1.0L;
+  for (int i = 0; i < dig; ++i) p10 *= 10.0L;
+  long double x10 = p10 * (long double)x;
+  long double i10 = floorl(x10);
+  double xd = (double)(i10 / p10), xu = (double)(ceill(x10) / p10);
+  double du = xu - x, dd = x - xd;
+  bool even = fmodl(i10, 2.0L) == 0.0L;
+  return sgn * ((dd < du || (dd == du && even)) ? xd : xu);
+}
+
+// R's mean(): long double sum, then one correction pass (summary.c rsum / mean)
+static double r_mean(const double* v, int n) {
+  long double s = 0.0L;
+  for (int i = 0; i < n; ++i) s += v[i];
+  s /= n;
+  long double t = 0.0L;
+  for (int i = 0; i < n; ++i) t += (v[i] - s);
+  return (double)(s + t / n);
+}
+
+// upload K hyper-posteriors (mean K x U, cov K x U x U) and tau (n_tasks x K)
+static int put_hyperpost(mb_context* c, int K, const double* post_mean, const double* post_cov,
+                         const double* tau) {
+  const size_t UU = (size_t)c->U * c->U;
+  MB_TRY(ensure_em_buffers(c, K));
+  MB_TRY(h2d(c->pm.p, post_mean, (size_t)K * c->U * 8, c->st));
+  MB_TRY(h2d(c->pc.p, post_cov, K * UU * 8, c->st));
+  if (tau) {
+    MB_TRY(c->tau.ensure((size_t)c->db.n_tasks * K * 8));
+    MB_TRY(h2d(c->tau.p, tau, (size_t)c->db.n_tasks * K * 8, c->st));
+  }
+  return 0;
+}
+
+// update_mixture on device state -> host tau_out (n_tasks x K)
+static int dev_update_mixture(mb_context* c, int K, const DevKern& kdi, const double* hp_i_dev,
+                              int64_t stride, const double* pm_dev, const double* pc_dev,
+                              const double* prop, double pen, double* tau_out) {
+  const int64_t M = c->db.n_tasks;
+  MB_TRY(c->f_t.ensure((size_t)M * K * 8));
+  TaskObjArgs a = make_obj_args(c, kdi, hp_i_dev, stride, TK_OBJ_MIX, 0, pen, K, pm_dev, pc_dev, nullptr,
+                                c->f_t.as<double>(), c->g_t.as<double>());
+  MB_TRY(launch_obj(c, a, (int)M, c->st));
+  std::vector<double> f((size_t)M * K);
+  MB_TRY(d2h(f.data(), c->f_t.p, f.size() * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  // vem-magmaclust.R:383-392: exp(L - max L) * pi, normalised per task, round(5)
+  for (int64_t t = 0; t < M; ++t) {
+    double mx = -INFINITY;
+    for (int k = 0; k < K; ++k) mx = fmax(mx, -f[t * K + k]);
+    double w[MB_MAX_CLUSTERS], sum = 0.0;
+    for (int k = 0; k < K; ++k) { w[k] = prop[k] * exp(-f[t * K + k] - mx); sum += w[k]; }
+    for (int k = 0; k < K; ++k) tau_out[t * K + k] = r_round(w[k] / sum, 5);
+  }
+  return 0;
+}
+
+extern "C" int mb_update_mixture(mb_context* c, int n_clusters, const mb_kernel* kern_i, const double* hp_i,
+                                 int hp_i_shared, const double* post_mean, const double* post_cov,
+                                 const double* prop_mixture, double pen_diag, double* tau_out) {
+  MB_TRY(need_db(c, true));
+  if (!kern_i || !hp_i || !post_mean || !post_cov || !prop_mixture || !tau_out) MB_FAIL(-1, "null argument");
+  if (n_clusters < 1 || n_clusters > MB_MAX_CLUSTERS) MB_FAIL(-1, "bad cluster count");
+  int64_t stride;
+  MB_TRY(put_hp_i(c, kern_i, hp_i, hp_i_shared, &stride));
+  MB_TRY(put_hyperpost(c, n_clusters, post_mean, post_cov, nullptr));
+  return dev_update_mixture(c, n_clusters, make_devkern(kern_i), c->hp_i.as<double>(), stride, c->pm.as<double>(),
+                            c->pc.as<double>(), prop_mixture, pen_diag, tau_out);
+}
+
+extern "C" int mb_ve_step(mb_context* c, int n_clusters, const mb_kernel* kern_k, const double* hp_k,
+                          const mb_kernel* kern_i, const double* hp_i, int hp_i_shared, const double* m_k,
+                          const double* tau, const double* prop_mixture, int update, double pen_diag,
+                          double* post_mean, double* post_cov, double* tau_out) {
+  MB_TRY(need_db(c, true));
+  if (!kern_k || !hp_k || !kern_i || !hp_i || !m_k || !tau || !post_mean || !post_cov) MB_FAIL(-1, "null argument");
+  const int K = n_clusters;
+  if (K < 1 || K > MB_MAX_CLUSTERS) MB_FAIL(-1, "bad cluster count");
+  if (update && (!prop_mixture || !tau_out)) MB_FAIL(-1, "update_mixture needs prop_mixture and tau_out");
+  const size_t UU = (size_t)c->U * c->U;
+  MB_TRY(ensure_em_buffers(c, K));
+  int64_t stride;
+  MB_TRY(put_hp_i(c, kern_i, hp_i, hp_i_shared, &stride));
+  MB_TRY(c->tau.ensure((size_t)c->db.n_tasks * K * 8));
+  MB_TRY(h2d(c->tau.p, tau, (size_t)c->db.n_tasks * K * 8, c->st));
+  MB_TRY(h2d(c->m0.p, m_k, (size_t)K * c->U * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  DevKern kdi = make_devkern(kern_i);
+  MB_TRY(dev_e_step(c, K, kern_k, hp_k, kdi, c->hp_i.as<double>(), stride, c->m0.as<double>(), c->tau.as<double>(),
+                    c->d_gridX.as<double>(), c->U, nullptr, pen_diag, c->pm.as<double>(), c->pc.as<double>(), nullptr));
+  MB_TRY(d2h(post_mean, c->pm.p, (size_t)K * c->U * 8, c->st));
+  MB_TRY(d2h(post_cov, c->pc.p, K * UU * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  if (tau_out) {
+    if (update) {
+      MB_TRY(dev_update_mixture(c, K, kdi, c->hp_i.as<double>(), stride, c->pm.as<double>(), c->pc.as<double>(),
+                                prop_mixture, pen_diag, tau_out));
+    } else {
+      memcpy(tau_out, tau, (size_t)c->db.n_tasks * K * 8);   // vem-magmaclust.R:130-131
+    }
+  }
+  return 0;
+}
+
+extern "C" int mb_elbo_clust_tasks(mb_context* c, int n_clusters, const mb_kernel* kern_i, const double* hp_i,
+                                   int hp_i_shared, const double* post_mean, const double* post_cov,
+                                   const double* tau, double pen_diag, double* f, double* g) {
+  MB_TRY(need_db(c, true));
+  if (!kern_i || !hp_i || !post_mean || !post_cov || !tau || !f) MB_FAIL(-1, "null argument");
+  if (n_clusters < 1 || n_clusters > MB_MAX_CLUSTERS) MB_FAIL(-1, "bad cluster count");
+  int64_t stride;
+  MB_TRY(put_hp_i(c, kern_i, hp_i, hp_i_shared, &stride));
+  MB_TRY(put_hyperpost(c, n_clusters, post_mean, post_cov, tau));
+  DevKern kd = make_devkern(kern_i);
+  TaskObjArgs a = make_obj_args(c, kd, c->hp_i.as<double>(), stride, TK_OBJ_ELBO, g != nullptr, pen_diag, n_clusters,
+                                c->pm.as<double>(), c->pc.as<double>(), c->tau.as<double>(), c->f_t.as<double>(),
+                                c->g_t.as<double>());
+  MB_TRY(launch_obj(c, a, (int)c->db.n_tasks, c->st));
+  MB_TRY(d2h(f, c->f_t.p, c->db.n_tasks * 8, c->st));
+  if (g) MB_TRY(d2h(g, c->g_t.p, (size_t)c->db.n_tasks * kd.n_hp * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+// elbo_GP_mod_shared_hp_k + gr_GP_mod_shared_hp_k (elbos.R:78-100, gradients-elbos.R:94-150):
+// sum over clusters of logL_GP_mod with ONE hyper-parameter vector.
+static int shared_k_eval(mb_context* c, int K, const DevKern& kdk, const double* hp, const double* mk_dev,
+                         double pen, int want_grad, double* f, double* g) {
+  const size_t UU = (size_t)c->U * c->U;
+  double* hres = c->h_pin + 32;
+  int* hinfo = c->h_pin_i + 8;
+  double ll = 0.0, cor = 0.0;
+  (void)cor;
+  *f = 0.0;
+  for (int p = 0; p < kdk.n_hp; ++p) g[p] = 0.0;
+  for (int k = 0; k < K; ++k) {
+    MB_TRY(dense_obj_enqueue(c, c->ws0, kdk, hp, c->d_gridX.as<double>(), c->U, c->db.D,
+                             c->pm.as<double>() + (size_t)k * c->U, mk_dev + (size_t)k * c->U,
+                             c->pc.as<double>() + k * UU, pen, want_grad, c->st2, hres, hinfo));
+    CU(cudaStreamSynchronize(c->st2));
+    if (hinfo[0] < 0) { *f = NAN; return 0; }
+    ll += hres[0];
+    if (want_grad) for (int p = 0; p < kdk.n_hp; ++p) g[p] += hres[1 + p];
+  }
+  *f = ll;
+  return 0;
+}
+
+extern "C" int mb_vm_step(mb_context* c, int n_clusters, const mb_kernel* kern_k, double* hp_k,
+                          const mb_kernel* kern_i, double* hp_i, int shared_hp_k, int shared_hp_i, double* m_k,
+                          const double* post_mean, const double* post_cov, const double* tau, double pen_diag,
+                          double* prop_mixture, int64_t* stats) {
+  MB_TRY(need_db(c, true));
+  if (!kern_k || !hp_k || !kern_i || !hp_i || !m_k || !post_mean || !post_cov || !tau || !prop_mixture)
+    MB_FAIL(-1, "null argument");
+  const int K = n_clusters, U = c->U;
+  if (K < 1 || K > MB_MAX_CLUSTERS) MB_FAIL(-1, "bad cluster count");
+  const int64_t M = c->db.n_tasks;
+  DevKern kdk = make_devkern(kern_k), kdi = make_devkern(kern_i);
+  const int Pi = kdi.n_hp, Pk = kdk.n_hp;
+  if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+  MB_TRY(put_hyperpost(c, K, post_mean, post_cov, tau));
+  // m_k <- mean of the hyper-posterior mean, replicated (vem-magmaclust.R:229-232)
+  for (int k = 0; k < K; ++k) {
+    double mu = r_mean(post_mean + (size_t)k * U, U);
+    for (int u = 0; u < U; ++u) m_k[(size_t)k * U + u] = mu;
+  }
+  MB_TRY(h2d(c->m0.p, m_k, (size_t)K * U * 8, c->st));
+  // pi_k = colMeans(tau) (:265-266)
+  for (int k = 0; k < K; ++k) {
+    long double s = 0.0L;
+    for (int64_t t = 0; t < M; ++t) s += tau[t * K + k];
+    prop_mixture[k] = (double)(s / M);
+  }
+  MB_TRY(c->hp_k.ensure((size_t)M * Pi * 8));
+  MB_TRY(h2d(c->hp_k.p, hp_i, (size_t)M * Pi * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  double* hp_i_dev = c->hp_k.as<double>();
+  TaskObjArgs a = make_obj_args(c, kdi, hp_i_dev, Pi, TK_OBJ_ELBO, 1, pen_diag, K, c->pm.as<double>(),
+                                c->pc.as<double>(), c->tau.as<double>(), c->f_t.as<double>(), c->g_t.as<double>());
+  // cluster processes: K independent problems, or one shared problem handled after the tasks
+  std::vector<SingleProblem> singles;
+  if (!shared_hp_k) {
+    singles.resize(K);
+    for (int k = 0; k < K; ++k) {
+      SingleProblem& sp = singles[k];
+      sp.kd = kdk; sp.X = c->d_gridX.as<double>(); sp.n = U; sp.D = c->db.D;
+      sp.y = c->pm.as<double>() + (size_t)k * U; sp.mean = c->m0.as<double>() + (size_t)k * U;
+      sp.S = c->pc.as<double>() + (size_t)k * U * U;
+      lb_init(&sp.s, Pk, hp_k + (size_t)k * Pk, 1e13, 0.0, 25);
+    }
+  }
+  if (!shared_hp_i) {
+    MB_TRY(optimise(c, singles, true, a, hp_i_dev, Pi, pen_diag, stats));
+    MB_TRY(d2h(hp_i, hp_i_dev, (size_t)M * Pi * 8, c->st));
+    CU(cudaStreamSynchronize(c->st));
+  } else {
+    MB_TRY(optimise(c, singles, false, a, hp_i_dev, Pi, pen_diag, stats));
+    LbfgsbState s;
+    lb_init(&s, Pi, hp_i, 1e13, 0.0, 25);       // block of the first task (:236-238)
+    int evals = 0;
+    while (s.active) {
+      double f, g[MB_MAX_HP];
+      MB_TRY(shared_obj_eval(c, a, s.x, Pi, 1, &f, g));
+      lb_advance(&s, f, g);
+      evals++;
+    }
+    for (int64_t t = 0; t < M; ++t)
+      for (int p = 0; p < Pi; ++p) hp_i[t * Pi + p] = s.x[p];
+    if (stats) { stats[1] = evals; stats[2] = (int64_t)evals * M; stats[3] = (s.fail == 99); }
+  }
+  if (!shared_hp_k) {
+    int ev = 0;
+    for (int k = 0; k < K; ++k) {
+      for (int p = 0; p < Pk; ++p) hp_k[(size_t)k * Pk + p] = singles[k].s.x[p];
+      ev += singles[k].evals;
+    }
+    if (stats) stats[0] = ev;
+  } else {
+    LbfgsbState s;
+    lb_init(&s, Pk, hp_k, 1e13, 0.0, 25);       // block of the first cluster (:270-272)
+    int evals = 0;
+    while (s.active) {
+      double f, g[MB_MAX_HP];
+      MB_TRY(shared_k_eval(c, K, kdk, s.x, c->m0.as<double>(), pen_diag, 1, &f, g));
+      lb_advance(&s, f, g);
+      evals++;
+    }
+    for (int k = 0; k < K; ++k)
+      for (int p = 0; p < Pk; ++p) hp_k[(size_t)k * Pk + p] = s.x[p];
+    if (stats) stats[0] = evals;
+  }
+  return 0;
+}
+
+extern "C" int mb_elbo_monitoring(mb_context* c, int n_clusters, const mb_kernel* kern_k, const double* hp_k,
+                                  const mb_kernel* kern_i, const double* hp_i, int hp_i_shared, const double* m_k,
+                                  const double* post_mean, const double* post_cov, const double* tau,
+                                  const double* prop_mixture, double pen_diag, double* elbo) {
+  MB_TRY(need_db(c, true));
+  if (!kern_k || !hp_k || !kern_i || !hp_i || !m_k || !post_mean || !post_cov || !tau || !prop_mixture || !elbo)
+    MB_FAIL(-1, "null argument");
+  const int K = n_clusters, U = c->U;
+  if (K < 1 || K > MB_MAX_CLUSTERS) MB_FAIL(-1, "bad cluster count");
+  const int64_t M = c->db.n_tasks;
+  const size_t UU = (size_t)U * U;
+  DevKern kdk = make_devkern(kern_k), kdi = make_devkern(kern_i);
+  int64_t stride;
+  MB_TRY(put_hp_i(c, kern_i, hp_i, hp_i_shared, &stride));
+  MB_TRY(put_hyperpost(c, K, post_mean, post_cov, tau));
+  MB_TRY(c->ws1.ensure(U));
+  MB_TRY(h2d(c->m0.p, m_k, (size_t)K * U * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  // task sum (elbos.R:221-235)
+  TaskObjArgs a = make_obj_args(c, kdi, c->hp_i.as<double>(), stride, TK_OBJ_ELBO, 0, pen_diag, K, c->pm.as<double>(),
+                                c->pc.as<double>(), c->tau.as<double>(), c->f_t.as<double>(), c->g_t.as<double>());
+  MB_TRY(launch_obj(c, a, (int)M, c->st));
+  MB_TRY(c->sums.ensure(64 * 8));
+  LAUNCH(c, launch_sum_sequential(a.f, M, 1, c->sums.as<double>(), c->st));
+  MB_TRY(ctx_allreduce(c, c->sums.p, 1, c->st));
+  MB_TRY(d2h(c->h_pin, c->sums.p, 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  const double sum_ll_i = c->h_pin[0];
+  // cluster terms (elbos.R:209-219, 237-268)
+  double sum_ll_k = 0.0, sum_corr = 0.0;
+  double* hres = c->h_pin + 32;
+  int* hinfo = c->h_pin_i + 8;
+  for (int k = 0; k < K; ++k) {
+    MB_TRY(dense_obj_enqueue(c, c->ws0, kdk, hp_k + (size_t)k * kdk.n_hp, c->d_gridX.as<double>(), U, c->db.D,
+                             c->pm.as<double>() + (size_t)k * U, c->m0.as<double>() + (size_t)k * U,
+                             c->pc.as<double>() + k * UU, pen_diag, 0, c->st2, hres, hinfo));
+    CU(cudaStreamSynchronize(c->st2));
+    sum_ll_k += (hinfo[0] < 0) ? NAN : hres[0];
+    LAUNCH(c, launch_dense_chol_logdiag(c->pc.as<double>() + k * UU, c->ws1.Ap.as<double>(), c->ws1.Xd.as<double>(), U,
+                                        c->ws1.info.as<int>(), c->sums.as<double>() + 8, c->st));
+    MB_TRY(d2h(c->h_pin + 8, c->sums.as<double>() + 8, 8, c->st));
+    MB_TRY(d2h(c->h_pin_i, c->ws1.info.p, sizeof(int), c->st));
+    CU(cudaStreamSynchronize(c->st));
+    if (c->h_pin_i[0] != 0) MB_FAIL(1, "chol(cov_k) failed in elbo_monitoring_VEM (no jitter is applied there)");
+    double sum_tau = 0.0;
+    const double pi_k = prop_mixture[k];
+    for (int64_t t = 0; t < M; ++t) {
+      double tk = tau[t * K + k];
+      double lf = (tk == 0.0 || pi_k == 0.0) ? 0.0 : log(pi_k / tk);
+      sum_tau = sum_tau + tk * lf;
+    }
+    sum_corr += sum_tau + c->h_pin[8];
+  }
+  *elbo = -sum_ll_k - sum_ll_i + sum_corr;
+  return 0;
+}

@@ -292,3 +292,81 @@ class Context:
                                     sc.ctypes.data_as(L._dp), float(pen_diag), ptr(mean), ptr(var),
                                     cov.ctypes.data_as(L._dp) if full_cov else None))
         return mean, var, cov
+
+    # ---- MagmaClust ------------------------------------------------------------------------
+    def ve_step(self, K, kk, hp_k, ki, hp_i, m_k, tau, prop_mixture=None, update=False, pen_diag=1e-10,
+                shared=False):
+        pm = np.zeros((K, self.U))
+        pc = np.zeros((K, self.U, self.U))
+        tau = f64(tau)
+        tau_out = np.zeros_like(tau)
+        prop = f64(prop_mixture) if prop_mixture is not None else None
+        check(L.lib().mb_ve_step(self._h, int(K), C.byref(kk), ptr(f64(hp_k)), C.byref(ki), ptr(f64(hp_i)),
+                                 1 if shared else 0, ptr(f64(m_k)), ptr(tau), ptr(prop), 1 if update else 0,
+                                 float(pen_diag), ptr(pm), ptr(pc), ptr(tau_out)))
+        return pm, pc, tau_out
+
+    def update_mixture(self, K, ki, hp_i, post_mean, post_cov, prop_mixture, pen_diag=1e-10, shared=False):
+        tau = np.zeros((self.n_tasks, K))
+        check(L.lib().mb_update_mixture(self._h, int(K), C.byref(ki), ptr(f64(hp_i)), 1 if shared else 0,
+                                        ptr(f64(post_mean)), ptr(f64(post_cov)), ptr(f64(prop_mixture)),
+                                        float(pen_diag), ptr(tau)))
+        return tau
+
+    def elbo_clust_tasks(self, K, ki, hp_i, post_mean, post_cov, tau, pen_diag=1e-10, shared=False, grad=True):
+        f = np.zeros(self.n_tasks)
+        g = np.zeros((self.n_tasks, ki.n_hp)) if grad else None
+        check(L.lib().mb_elbo_clust_tasks(self._h, int(K), C.byref(ki), ptr(f64(hp_i)), 1 if shared else 0,
+                                          ptr(f64(post_mean)), ptr(f64(post_cov)), ptr(f64(tau)), float(pen_diag),
+                                          ptr(f), ptr(g)))
+        return f, g
+
+    def vm_step(self, K, kk, hp_k, ki, hp_i, m_k, post_mean, post_cov, tau, shared_hp_k=True, shared_hp_i=True,
+                pen_diag=1e-10):
+        hp_k, hp_i, m_k = f64(hp_k).copy(), f64(hp_i).copy(), f64(m_k).copy()
+        prop = np.zeros(K)
+        stats = np.zeros(4, dtype=np.int64)
+        check(L.lib().mb_vm_step(self._h, int(K), C.byref(kk), ptr(hp_k), C.byref(ki), ptr(hp_i),
+                                 1 if shared_hp_k else 0, 1 if shared_hp_i else 0, ptr(m_k), ptr(f64(post_mean)),
+                                 ptr(f64(post_cov)), ptr(f64(tau)), float(pen_diag), ptr(prop), ptr(stats)))
+        return m_k, hp_k, hp_i, prop, stats
+
+    def elbo_monitoring(self, K, kk, hp_k, ki, hp_i, m_k, post_mean, post_cov, tau, prop_mixture, pen_diag=1e-10,
+                        shared=False):
+        out = C.c_double(0)
+        check(L.lib().mb_elbo_monitoring(self._h, int(K), C.byref(kk), ptr(f64(hp_k)), C.byref(ki), ptr(f64(hp_i)),
+                                         1 if shared else 0, ptr(f64(m_k)), ptr(f64(post_mean)), ptr(f64(post_cov)),
+                                         ptr(f64(tau)), ptr(f64(prop_mixture)), float(pen_diag), C.byref(out)))
+        return out.value
+
+    def train_magmaclust(self, K, kk, hp_k, ki, hp_i, ini_mixture, shared_hp_k=True, shared_hp_i=True,
+                         pen_diag=1e-10, n_iter_max=25, cv_threshold=1e-3, m_k=None):
+        """VEM loop of train_magmaclust (training.R:1622-1758); every step runs in the library."""
+        hp_k, hp_i = f64(hp_k).copy(), f64(hp_i).copy()
+        m_k = np.zeros((K, self.U)) if m_k is None else f64(m_k).copy()
+        mixture = f64(ini_mixture).copy()
+        prop = np.array([float(np.sum(mixture[:, k].astype(np.longdouble)) / mixture.shape[0]) for k in range(K)])
+        elbo, seq, cv = -np.inf, [], False
+        pm = pc = None
+        for it in range(1, n_iter_max + 1):
+            pm, pc, post_mix = self.ve_step(K, kk, hp_k, ki, hp_i, m_k, mixture, prop, update=(it > 1),
+                                            pen_diag=pen_diag)
+            new_m_k, new_hp_k, new_hp_i, new_prop, _ = self.vm_step(K, kk, hp_k, ki, hp_i, m_k, pm, pc, post_mix,
+                                                                    shared_hp_k, shared_hp_i, pen_diag)
+            if np.isnan(new_hp_k).any() or np.isnan(new_hp_i).any():
+                break
+            new_elbo = self.elbo_monitoring(K, kk, new_hp_k, ki, new_hp_i, new_m_k, pm, pc, post_mix, new_prop,
+                                            pen_diag)
+            diff = new_elbo - elbo
+            if np.isnan(diff):
+                diff = -np.inf
+            m_k, hp_k, hp_i, mixture, prop, elbo = new_m_k, new_hp_k, new_hp_i, post_mix, new_prop, new_elbo
+            seq.append(elbo)
+            eps = diff / abs(elbo)
+            if np.isnan(eps):
+                eps = 1.0
+            if abs(eps) < cv_threshold:
+                cv = True
+                break
+        return {"hp_k": hp_k, "hp_i": hp_i, "m_k": m_k, "mixture": mixture, "prop_mixture": prop,
+                "post_mean": pm, "post_cov": pc, "seq_elbo": np.array(seq), "converged": cv}
