@@ -10,8 +10,8 @@ started from the pristine initial hyper-parameters, so every timed step does ide
   e2e     : the same step through mb_upload_dataset + mb_em_step with HOST buffers (pinned):
             host->device copy of the table and HP arrays and device->host read of the new
             HPs / log-likelihood inside the timed region.
-  roofline: dominant kernel k_task_objective, algorithmic flops = objective evaluations x
-            5.67 N^3, divided by its summed event time; peak = cuBLAS DGEMM
+  roofline: dominant kernel k_task_objective3, algorithmic flops = objective evaluations x
+            5 N^3, divided by its summed event time; peak = cuBLAS DGEMM
             8192^3 measured in the same run (MEASURED_PEAKS.json has no FP64 figure).
   cpu_baseline / --impl reference: the oracle (CPU restatement of the reference's algorithm,
             all host cores) on a bounded task sample, scaled linearly in M.
@@ -31,8 +31,11 @@ sys.path.insert(0, ROOT)
 
 M_TASKS, N_POINTS = 10000, 64
 DATA_SEED, HP0_SEED, HPI_SEED = 2024, 6, 106
+# dram__bytes_read.sum + dram__bytes_write.sum of one full-grid launch of the dominant kernel (10 000
+# evaluations), from the ncu --set full capture summarised in profiles/ (None until captured)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 13577472
 METRIC = "train_magma EM steps/sec at M=10k,N=64"
-FLOPS_PER_EVAL = 5.0 + 2.0 / 3.0  # x N^3: chol+inverse N^3, LU log-det 2/3 N^3, S A and A (S A) 4 N^3
+FLOPS_PER_EVAL = 5.0  # x N^3: chol+inverse N^3, S A and A (S A) 4 N^3; log-det read off the Cholesky diagonal
 
 
 def make_inputs(m_tasks=M_TASKS):
@@ -137,7 +140,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count()
-    m_sample = args.cpu_sample
+    m_sample = args.cpu_sample or 1024      # ~5 s of CPU work per step on 16 cores
     df, _, _, _ = make_inputs()
     secs = []
     for s in range(args.warmup + args.steps):
@@ -166,7 +169,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=256)
+    ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fit", action="store_true")
     args = ap.parse_args()
@@ -296,8 +299,9 @@ def main():
         "e2e": {"value": args.steps / (e2e_total * 1e-3), "unit": "EM steps/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "k_task_objective", "achieved": achieved, "peak": peak,
-                     "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+        "roofline": {"bound": "tensor", "kernel": "k_task_objective3<SE,8,D1>", "achieved": achieved, "peak": peak,
+                     "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
+                     "algorithmic_flops_per_eval": FLOPS_PER_EVAL * N_POINTS ** 3,
                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (no FP64 figure in MEASURED_PEAKS.json)",
                      "kernel_ms_per_step": prof["ms"] / args.steps,
                      "kernel_share_of_step": prof["ms"] / float(np.sum(ms))},
@@ -306,12 +310,13 @@ def main():
         line["fit"] = fit
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count()
-        dt, evals, _ = oracle_sample_step(df, args.cpu_sample, cores)
+        m_sample = args.cpu_sample or 3072  # 10-30 s of CPU work on the box's host cores
+        dt, evals, _ = oracle_sample_step(df, m_sample, cores)
         line["cpu_baseline"] = {
-            "value": 1.0 / (dt * M_TASKS / args.cpu_sample), "unit": "EM steps/s", "cores": cores,
+            "value": 1.0 / (dt * M_TASKS / m_sample), "unit": "EM steps/s", "cores": cores,
             "kind": "port",
-            "sample": "one EM step on the first %d of %d tasks (%.1f s), scaled linearly in M"
-                      % (args.cpu_sample, M_TASKS, dt)}
+            "sample": "one EM step of the oracle (numpy/LAPACK restatement of the reference, one process per core) "
+                      "on the first %d of %d tasks (%.1f s), scaled linearly in M" % (m_sample, M_TASKS, dt)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -23,22 +23,34 @@ cudaError_t launch_task_objective2(TaskObjArgs a, int n_launch, cudaStream_t st)
 cudaError_t launch_task_inverse2(TaskInvArgs a, int n_ctas, cudaStream_t st);
 int task2_max_ctas_per_sm(int nmax, int D);
 
-// kernel generation switch: v2 = DMMA-tiled (default); MB_TASK_KERNEL=v1 selects the first,
-// scalar shared-memory version (kept as an independent cross-check)
-static bool use_v2() {
+cudaError_t launch_task_objective3(TaskObjArgs a, int n_launch, cudaStream_t st);
+cudaError_t launch_task_inverse3(TaskInvArgs a, int n_ctas, cudaStream_t st);
+int task3_max_ctas_per_sm(int nmax, int D);
+
+// kernel generation switch: v3 (default) = 4-warp CTAs on packed swizzled tiles, DMMA; MB_TASK_KERNEL=v2
+// selects the 8-warp DMMA version, v1 the first scalar shared-memory version (both kept as
+// independent cross-checks of v3)
+static int task_kernel_version() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MB_TASK_KERNEL"); v = (e && e[0] == 'v' && e[1] == '1') ? 0 : 1; }
-  return v == 1;
+  if (v < 0) {
+    const char* e = getenv("MB_TASK_KERNEL");
+    v = 3;
+    if (e && e[0] == 'v' && (e[1] == '1' || e[1] == '2')) v = e[1] - '0';
+  }
+  return v;
 }
 static cudaError_t launch_task_objective_any(TaskObjArgs a, int n_launch, cudaStream_t st) {
-  if (use_v2() && a.mode != TK_OBJ_MARG) return launch_task_objective2(a, n_launch, st);
-  return launch_task_objective(a, n_launch, st);
+  const int v = task_kernel_version();
+  if (a.mode == TK_OBJ_MARG || v == 1) return launch_task_objective(a, n_launch, st);
+  return v == 2 ? launch_task_objective2(a, n_launch, st) : launch_task_objective3(a, n_launch, st);
 }
 static cudaError_t launch_task_inverse_any(TaskInvArgs a, int n_ctas, cudaStream_t st) {
-  return use_v2() ? launch_task_inverse2(a, n_ctas, st) : launch_task_inverse(a, n_ctas, st);
+  const int v = task_kernel_version();
+  return v == 1 ? launch_task_inverse(a, n_ctas, st) : (v == 2 ? launch_task_inverse2(a, n_ctas, st) : launch_task_inverse3(a, n_ctas, st));
 }
 static int task_ctas_per_sm_any(int nmax, int D) {
-  return use_v2() ? task2_max_ctas_per_sm(nmax, D) : task_max_ctas_per_sm(nmax, D);
+  const int v = task_kernel_version();
+  return v == 1 ? task_max_ctas_per_sm(nmax, D) : (v == 2 ? task2_max_ctas_per_sm(nmax, D) : task3_max_ctas_per_sm(nmax, D));
 }
 cudaError_t launch_dense_cov(const DevKern& kd, const double* hp_host, const double* x1, int n1,
                              const double* x2, int n2, int D, int deriv, int with_noise,
@@ -51,6 +63,21 @@ cudaError_t launch_dense_cholinv(const double* src, int ld_src, double* A, doubl
 cudaError_t launch_dense_chol_logdiag(const double* src, double* W, double* Xd, int n, int* info,
                                       double* out, cudaStream_t st);
 size_t dense_xd_doubles(int n);
+bool dense_sm_fits(int n);
+cudaError_t launch_dense_cholinv_sm(const double* src, int ld_src, double* inv, int n, double pen, int mode,
+                                    int* info, double* out, cudaStream_t st);
+cudaError_t launch_gemm_dmma(int m, int n, int k, const double* A, int64_t ars, int64_t acs, const double* B,
+                             int64_t brs, int64_t bcs, double* C, int64_t ldc, double alpha, const double* Cin,
+                             double beta, cudaStream_t st);
+cudaError_t launch_resid_gemv(int n, const double* A, const double* y, const double* mean, double* r, double* al,
+                              cudaStream_t st);
+// chol_inv_jitter of a device matrix: shared-memory-resident kernel when it fits (U <= 224), else the
+// L2-resident one.  MB_DENSE_KERNEL=v2 forces the latter (cross-check).
+static bool dense_use_sm(int n) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MB_DENSE_KERNEL"); v = (e && e[0] == 'v' && e[1] == '2') ? 0 : 1; }
+  return v == 1 && dense_sm_fits(n);
+}
 cudaError_t launch_dense_lu_logdet(const double* src, double* W, int n, int* done, double* out,
                                    cudaStream_t st);
 cudaError_t launch_gemm(int m, int n, int k, const double* A, int64_t ars, int64_t acs,
@@ -395,8 +422,11 @@ extern "C" int mb_kern_to_cov(mb_context* c, const mb_kernel* k, const double* h
 // src (n x n, upper read) -> ws.A = inverse.  Synchronises `s`; returns >0 on numerical failure.
 static int dev_cholinv(mb_context* c, DenseWs& ws, const double* src, int n, double pen,
                        cudaStream_t s, int* retries, double* jitter, double* sumlogdiag) {
-  LAUNCH(c, launch_dense_cholinv(src, n, ws.Ap.as<double>(), ws.Bp.as<double>(), ws.Xd.as<double>(),
-                                 ws.A.as<double>(), n, pen, ws.info.as<int>(), ws.res.as<double>() + 16, s));
+  if (dense_use_sm(n))
+    LAUNCH(c, launch_dense_cholinv_sm(src, n, ws.A.as<double>(), n, pen, 0, ws.info.as<int>(), ws.res.as<double>() + 16, s));
+  else
+    LAUNCH(c, launch_dense_cholinv(src, n, ws.Ap.as<double>(), ws.Bp.as<double>(), ws.Xd.as<double>(),
+                                   ws.A.as<double>(), n, pen, ws.info.as<int>(), ws.res.as<double>() + 16, s));
   MB_TRY(d2h(c->h_pin_i, ws.info.p, sizeof(int), s));
   MB_TRY(d2h(c->h_pin + 200, ws.res.as<double>() + 16, 2 * sizeof(double), s));
   CU(cudaStreamSynchronize(s));
@@ -570,9 +600,13 @@ static int dense_obj_enqueue(mb_context* c, DenseWs& ws, const DevKern& kd, cons
                              const double* S, double pen, int want_grad, cudaStream_t s,
                              double* hres, int* hinfo) {
   LAUNCH(c, launch_dense_cov(kd, hp_host, X, n, X, n, D, -1, 1, ws.Kmat.as<double>(), n, 1, s));
-  LAUNCH(c, launch_dense_cholinv(ws.Kmat.as<double>(), n, ws.Ap.as<double>(), ws.Bp.as<double>(),
-                                 ws.Xd.as<double>(), ws.A.as<double>(), n, pen, ws.info.as<int>(),
-                                 ws.res.as<double>() + 16, s));
+  if (dense_use_sm(n))
+    LAUNCH(c, launch_dense_cholinv_sm(ws.Kmat.as<double>(), n, ws.A.as<double>(), n, pen, 0, ws.info.as<int>(),
+                                      ws.res.as<double>() + 16, s));
+  else
+    LAUNCH(c, launch_dense_cholinv(ws.Kmat.as<double>(), n, ws.Ap.as<double>(), ws.Bp.as<double>(),
+                                   ws.Xd.as<double>(), ws.A.as<double>(), n, pen, ws.info.as<int>(),
+                                   ws.res.as<double>() + 16, s));
   const double* logdet;
   if (c->logdet_chol) {
     logdet = ws.res.as<double>() + 17;
@@ -581,12 +615,11 @@ static int dense_obj_enqueue(mb_context* c, DenseWs& ws, const DevKern& kd, cons
                                      ws.res.as<double>() + 18, s));
     logdet = ws.res.as<double>() + 18;
   }
-  LAUNCH(c, launch_axpby(n, 1.0, y, -1.0, mean, ws.r(), s));
-  LAUNCH(c, launch_gemv(n, n, ws.A.as<double>(), n, ws.r(), nullptr, ws.al(), s));
+  LAUNCH(c, launch_resid_gemv(n, ws.A.as<double>(), y, mean, ws.r(), ws.al(), s));
   const double* T = nullptr;
   if (want_grad && S) {
-    LAUNCH(c, launch_gemm(n, n, n, S, n, 1, ws.A.as<double>(), n, 1, ws.B.as<double>(), n, 1.0, nullptr, 0.0, s));
-    LAUNCH(c, launch_gemm(n, n, n, ws.A.as<double>(), n, 1, ws.B.as<double>(), n, 1, ws.T.as<double>(), n, 1.0, nullptr, 0.0, s));
+    LAUNCH(c, launch_gemm_dmma(n, n, n, S, n, 1, ws.A.as<double>(), n, 1, ws.B.as<double>(), n, 1.0, nullptr, 0.0, s));
+    LAUNCH(c, launch_gemm_dmma(n, n, n, ws.A.as<double>(), n, 1, ws.B.as<double>(), n, 1, ws.T.as<double>(), n, 1.0, nullptr, 0.0, s));
     T = ws.T.as<double>();
   }
   LAUNCH(c, launch_dense_obj(kd, hp_host, X, n, D, ws.A.as<double>(), S, T, ws.al(), ws.r(), logdet,
@@ -678,6 +711,13 @@ static int dev_e_step(mb_context* c, int K, const mb_kernel* kern_k, const doubl
   for (int32_t v : hr) { if (v < 0) MB_FAIL(1, "chol_inv_jitter: no positive-definite jitter found for a task"); if (v > max_rt) max_rt = v; }
   if (info3) { info3[0] = max_r0; info3[1] = max_rp; info3[2] = max_rt; }
   return 0;
+}
+
+// sum log diag chol(src) without jitter (likelihoods.R:303-307, elbos.R:259-264)
+static cudaError_t launch_chol_logdiag_any(mb_context* c, DenseWs& ws, const double* src, int n, int* info,
+                                           double* out, cudaStream_t s) {
+  if (dense_use_sm(n)) return launch_dense_cholinv_sm(src, n, nullptr, n, 0.0, 1, info, out, s);
+  return launch_dense_chol_logdiag(src, ws.Ap.as<double>(), ws.Xd.as<double>(), n, info, out, s);
 }
 
 static TaskObjArgs make_obj_args(mb_context* c, const DevKern& kd, const double* hp_dev, int64_t stride,
@@ -964,8 +1004,7 @@ static int dev_logL_monitoring(mb_context* c, const mb_kernel* kern_0, const dou
   LAUNCH(c, launch_sum_sequential(a.f, c->db.n_tasks, 1, c->sums.as<double>(), c->st));
   MB_TRY(ctx_allreduce(c, c->sums.p, 1, c->st));
   // det term: chol(post_cov) without jitter (likelihoods.R:303-307)
-  LAUNCH(c, launch_dense_chol_logdiag(pc_dev, c->ws1.Ap.as<double>(), c->ws1.Xd.as<double>(), c->U,
-                                      c->ws1.info.as<int>(), c->sums.as<double>() + 8, c->st));
+  LAUNCH(c, launch_chol_logdiag_any(c, c->ws1, pc_dev, c->U, c->ws1.info.as<int>(), c->sums.as<double>() + 8, c->st));
   MB_TRY(d2h(c->h_pin, c->sums.p, 16 * 8, c->st));
   MB_TRY(d2h(c->h_pin_i, c->ws1.info.p, sizeof(int), c->st));
   CU(cudaStreamSynchronize(c->st));
@@ -1246,14 +1285,14 @@ extern "C" int mb_pred_magma(mb_context* c, const mb_kernel* k, const double* hp
   // mean = mu_pred + C' Gamma^{-1} (y - mu_obs)  (prediction.R:1184-1186)
   LAUNCH(c, launch_axpby(no, 1.0, dyo, -1.0, dmo, dmo, s));
   LAUNCH(c, launch_gemv(no, no, Ginv, no, dmo, nullptr, dvec, s));
-  LAUNCH(c, launch_gemm(np, 1, no, dC, no, 1, dvec, 1, 1, dmean, 1, 1.0, dmp, 1.0, s));
-  LAUNCH(c, launch_gemm(no, np, no, Ginv, no, 1, dC, 1, no, dGC, np, 1.0, nullptr, 0.0, s));
+  LAUNCH(c, launch_gemm_dmma(np, 1, no, dC, no, 1, dvec, 1, 1, dmean, 1, 1.0, dmp, 1.0, s));
+  LAUNCH(c, launch_gemm_dmma(no, np, no, Ginv, no, 1, dC, 1, no, dGC, np, 1.0, nullptr, 0.0, s));
   const double noise = kd.has_noise ? exp(hp[kd.n_hp - 1]) : 0.0;
   if (full) {
     // cov = K(pred) + S_pred - C' Gamma^{-1} C  (prediction.R:1189)
     LAUNCH(c, launch_dense_cov(kd, hp, dXp, np, dXp, np, d, -1, 0, dKp, np, 1, s));
     LAUNCH(c, launch_axpby((int64_t)np * np, 1.0, dKp, 1.0, dSp, dKp, s));
-    LAUNCH(c, launch_gemm(np, np, no, dC, no, 1, dGC, np, 1, dKp, np, -1.0, dKp, 1.0, s));
+    LAUNCH(c, launch_gemm_dmma(np, np, no, dC, no, 1, dGC, np, 1, dKp, np, -1.0, dKp, 1.0, s));
     LAUNCH(c, launch_diag(np, dKp, np, noise, dvar, s));
     MB_TRY(d2h(pred_cov, dKp, (size_t)np * np * 8, s));
   } else {
@@ -1550,8 +1589,8 @@ extern "C" int mb_elbo_monitoring(mb_context* c, int n_clusters, const mb_kernel
                              c->pc.as<double>() + k * UU, pen_diag, 0, c->st2, hres, hinfo));
     CU(cudaStreamSynchronize(c->st2));
     sum_ll_k += (hinfo[0] < 0) ? NAN : hres[0];
-    LAUNCH(c, launch_dense_chol_logdiag(c->pc.as<double>() + k * UU, c->ws1.Ap.as<double>(), c->ws1.Xd.as<double>(), U,
-                                        c->ws1.info.as<int>(), c->sums.as<double>() + 8, c->st));
+    LAUNCH(c, launch_chol_logdiag_any(c, c->ws1, c->pc.as<double>() + k * UU, U, c->ws1.info.as<int>(),
+                                      c->sums.as<double>() + 8, c->st));
     MB_TRY(d2h(c->h_pin + 8, c->sums.as<double>() + 8, 8, c->st));
     MB_TRY(d2h(c->h_pin_i, c->ws1.info.p, sizeof(int), c->st));
     CU(cudaStreamSynchronize(c->st));

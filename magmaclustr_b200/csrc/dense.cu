@@ -279,21 +279,28 @@ __global__ void k_reduce_partials(int64_t count, int nparts, const double* base,
   }
 }
 
-// out[0] = sum_i v[i] in index order by one thread (the reference's sapply(...) %>% sum()).
-__global__ void k_sum_sequential(const double* v, int64_t n, int64_t stride, double* out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double s = 0.0;
-  for (int64_t i = 0; i < n; ++i) s += v[i * stride];
-  out[0] = s;
+// out[b] = sum_i v[b + i*stride] for block b: the reference's sapply(...) %>% sum() / rowSums().
+// R accumulates in long double; here every thread keeps a Neumaier-compensated partial over a strided
+// subset and thread 0 combines the 256 (sum, compensation) pairs in index order, which gives the
+// correctly rounded sum up to one ulp, independent of the launch geometry (deterministic).
+__device__ __forceinline__ void neumaier_add(double& s, double& c, double x) {
+  const double t = s + x;
+  c += (fabs(s) >= fabs(x)) ? (s - t) + x : (x - t) + s;
+  s = t;
 }
-
-// column sums of a row-major M x P table in row order (sapply(...) %>% rowSums()).
-__global__ void k_colsum_sequential(const double* v, int64_t n, int P, double* out) {
-  int p = threadIdx.x;
-  if (blockIdx.x != 0 || p >= P) return;
-  double s = 0.0;
-  for (int64_t i = 0; i < n; ++i) s += v[i * P + p];
-  out[p] = s;
+__global__ void __launch_bounds__(256) k_sum_compensated(const double* v, int64_t n, int64_t stride, double* out) {
+  __shared__ double sh[256], sc[256];
+  v += blockIdx.x;
+  double s = 0.0, c = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 256) neumaier_add(s, c, v[i * stride]);
+  sh[threadIdx.x] = s;
+  sc[threadIdx.x] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double S = 0.0, C = 0.0, plain = 0.0;
+    for (int w = 0; w < 256; ++w) { neumaier_add(S, C, sh[w]); C += sc[w]; plain += sh[w]; }
+    out[blockIdx.x] = isfinite(plain) ? S + C : plain;   // Inf / NaN propagate like a plain sum
+  }
 }
 
 __global__ void k_axpby(int64_t n, double a, const double* x, double b, const double* y,
@@ -404,6 +411,9 @@ cudaError_t launch_gemv(int m, int n, const double* A, int64_t ld, const double*
 
 int dense_obj_nparts(int n) { return grid_for((int64_t)n * n, 256, 148 * 2); }
 
+cudaError_t launch_dense_obj_final3(int n, int P, int nparts, const double* part, const double* r, const double* al,
+                                    const double* logdet, int from_chol, int add_trace, double* res, cudaStream_t st);
+
 cudaError_t launch_dense_obj(const DevKern& kd, const double* hp_host, const double* x, int n,
                              int D, const double* A, const double* S, const double* T,
                              const double* al, const double* r, const double* logdet,
@@ -413,9 +423,9 @@ cudaError_t launch_dense_obj(const DevKern& kd, const double* hp_host, const dou
   for (int p = 0; p < MB_MAX_HP; ++p) h.v[p] = p < kd.n_hp ? hp_host[p] : 0.0;
   int nparts = dense_obj_nparts(n);
   k_dense_obj_partials<<<nparts, 256, 0, st>>>(kd, h, x, n, D, A, S, T, al, want_grad, part);
-  k_dense_obj_final<<<1, 32, 0, st>>>(n, want_grad ? kd.n_hp : 0, nparts, part, r, al, logdet,
-                                      from_chol, S != nullptr, res);
-  return cudaGetLastError();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return launch_dense_obj_final3(n, want_grad ? kd.n_hp : 0, nparts, part, r, al, logdet, from_chol, S != nullptr, res, st);
 }
 
 cudaError_t launch_reduce_partials(int64_t count, int nparts, const double* base,
@@ -428,13 +438,13 @@ cudaError_t launch_reduce_partials(int64_t count, int nparts, const double* base
 
 cudaError_t launch_sum_sequential(const double* v, int64_t n, int64_t stride, double* out,
                                   cudaStream_t st) {
-  k_sum_sequential<<<1, 32, 0, st>>>(v, n, stride, out);
+  k_sum_compensated<<<1, 256, 0, st>>>(v, n, stride, out);
   return cudaGetLastError();
 }
 
 cudaError_t launch_colsum_sequential(const double* v, int64_t n, int P, double* out,
                                      cudaStream_t st) {
-  k_colsum_sequential<<<1, 32, 0, st>>>(v, n, P, out);
+  k_sum_compensated<<<P, 256, 0, st>>>(v, n, P, out);
   return cudaGetLastError();
 }
 
