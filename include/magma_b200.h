@@ -180,6 +180,25 @@ int mb_pred_magma(mb_context*, const mb_kernel* k, const double* hp, const doubl
                   const double* cov_pred, const double* cov_crossed, double pen_diag,
                   double* pred_mean, double* pred_var, double* pred_cov);
 
+/* hyperposterior_clust (prediction.R:1691-1747): ve_step without the mixture update on a caller-given grid.
+ * hp_k: K x n_hp(kern_k); m_k: K x n_grid; tau: n_tasks x K (row-major). post_mean: K x n_grid;
+ * post_cov: K blocks of n_grid x n_grid. */
+int mb_hyperposterior_clust(mb_context*, int n_clusters, const mb_kernel* kern_k, const double* hp_k,
+                            const mb_kernel* kern_i, const double* hp_i, int hp_i_shared, int32_t n_grid,
+                            const double* grid_X, const int32_t* grid_index, const double* m_k,
+                            const double* tau, double pen_diag, double* post_mean, double* post_cov);
+
+/* pred_magmaclust (prediction.R:2298-2413) for one new task with mixture probabilities proba (K): the
+ * arguments of mb_pred_magma with a leading cluster dimension (mean_obs: K x n_obs, cov_obs: K blocks of
+ * n_obs x n_obs column-major, ...).  pred_mean / pred_var: K x n_pred (the `pred` list), pred_cov: K blocks or
+ * NULL; mix_mean / mix_var: n_pred (`mixture_pred`). */
+int mb_pred_magmaclust(mb_context*, int n_clusters, const mb_kernel* k, const double* hp, const double* x_obs,
+                       int n_obs, const double* y_obs, const double* x_pred, int n_pred, int d,
+                       const double* mean_obs, const double* mean_pred, const double* cov_obs,
+                       const double* cov_pred, const double* cov_crossed, const double* proba,
+                       double pen_diag, double* pred_mean, double* pred_var, double* pred_cov,
+                       double* mix_mean, double* mix_var);
+
 /* ---- MagmaClust ------------------------------------------------------------------------ */
 /* ve_step (vem-magmaclust.R:32-150): K hyper-posteriors weighted by tau (n_tasks x K,
  * row-major).  hp_k: K x n_hp(kern_k); m_k: K x U.  post_mean: K x U; post_cov: K blocks

@@ -65,6 +65,10 @@ _SIGS = {
                           _dp, _dp],
     "mb_pred_magma": [_vp, _kp, _dp, _dp, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, _dp, _dp, _dp,
                       _dp, C.c_double, _dp, _dp, _dp],
+    "mb_hyperposterior_clust": [_vp, C.c_int, _kp, _dp, _kp, _dp, C.c_int, C.c_int32, _dp, _ip, _dp, _dp,
+                                C.c_double, _dp, _dp],
+    "mb_pred_magmaclust": [_vp, C.c_int, _kp, _dp, _dp, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, _dp, _dp, _dp,
+                           _dp, _dp, C.c_double, _dp, _dp, _dp, _dp, _dp],
     "mb_ve_step": [_vp, C.c_int, _kp, _dp, _kp, _dp, C.c_int, _dp, _dp, _dp, C.c_int, C.c_double,
                    _dp, _dp, _dp],
     "mb_update_mixture": [_vp, C.c_int, _kp, _dp, C.c_int, _dp, _dp, _dp, C.c_double, _dp],

@@ -1,6 +1,9 @@
 // api.cu -- context, device workspaces and the extern "C" entry points of include/magma_b200.h.
-// Host code here only orchestrates: every number is produced by the kernels of tasks.cu,
-// dense.cu and lbfgsb_dev.cu.  There is no CPU fallback: without a CUDA device every call fails.
+// Host code here only orchestrates: the matrices, likelihoods and gradients are produced by the kernels of
+// tasks*.cu, dense*.cu and lbfgsb_dev.cu; what runs on the host is O(M K) scalar glue in the reference's own
+// order (softmax + round(5) of K numbers per task, colMeans, the mixture combination of K prediction
+// vectors) and the L-BFGS-B state machines of the single mean / cluster problems.
+// There is no CPU fallback: without a CUDA device every call fails.
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -861,40 +864,62 @@ extern "C" int mb_e_step(mb_context* c, const mb_kernel* kern_0, const double* h
   return 0;
 }
 
+// hyperposterior / hyperposterior_clust core: (V)E step on a caller-given grid (data U grid_inputs)
+static int hyperposterior_any(mb_context* c, int K, const mb_kernel* kern_k, const double* hp_k,
+                              const mb_kernel* kern_i, const double* hp_i, int hp_i_shared, int32_t n_grid,
+                              const double* grid_X, const int32_t* grid_index, const double* m_k,
+                              const double* tau, double pen_diag, double* post_mean, double* post_cov) {
+  MB_TRY(check_ctx(c));
+  if (!c->have_db) MB_FAIL(-1, "no dataset uploaded");
+  if (c->db.nmax > TK_MAXN) MB_FAIL(-4, "a task has more than 96 points: the large-task path is not built yet");
+  if (!kern_k || !hp_k || !kern_i || !hp_i || !grid_X || !grid_index || n_grid < 1 || !m_k || !post_mean || !post_cov)
+    MB_FAIL(-1, "bad argument");
+  if (K < 1 || K > MB_MAX_CLUSTERS || (K > 1 && !tau)) MB_FAIL(-1, "bad cluster count / missing mixture");
+  for (int64_t r = 0; r < c->n_rows; ++r)
+    if (grid_index[r] < 0 || grid_index[r] >= n_grid) MB_FAIL(-1, "grid_index out of range");
+  const size_t UU = (size_t)n_grid * n_grid;
+  DBuf gX, gi, pm, pc, m0, dtau;
+  int rc = 0;
+  if (gX.ensure((size_t)n_grid * c->db.D * 8) || gi.ensure(c->n_rows * 4) || pm.ensure((size_t)K * n_grid * 8) ||
+      pc.ensure(K * UU * 8) || m0.ensure((size_t)K * n_grid * 8) ||
+      (tau && dtau.ensure((size_t)c->db.n_tasks * K * 8))) rc = -3;
+  if (!rc) {
+    cudaMemcpyAsync(gX.p, grid_X, (size_t)n_grid * c->db.D * 8, cudaMemcpyHostToDevice, c->st);
+    cudaMemcpyAsync(gi.p, grid_index, c->n_rows * 4, cudaMemcpyHostToDevice, c->st);
+    cudaMemcpyAsync(m0.p, m_k, (size_t)K * n_grid * 8, cudaMemcpyHostToDevice, c->st);
+    if (tau) cudaMemcpyAsync(dtau.p, tau, (size_t)c->db.n_tasks * K * 8, cudaMemcpyHostToDevice, c->st);
+    int64_t stride;
+    rc = put_hp_i(c, kern_i, hp_i, hp_i_shared, &stride);
+    if (!rc) rc = (cudaStreamSynchronize(c->st) == cudaSuccess) ? 0 : -2;
+    if (!rc) rc = dev_e_step(c, K, kern_k, hp_k, make_devkern(kern_i), c->hp_i.as<double>(), stride,
+                             m0.as<double>(), tau ? dtau.as<double>() : nullptr, gX.as<double>(), n_grid,
+                             gi.as<int32_t>(), pen_diag, pm.as<double>(), pc.as<double>(), nullptr);
+    if (!rc) {
+      cudaMemcpyAsync(post_mean, pm.p, (size_t)K * n_grid * 8, cudaMemcpyDeviceToHost, c->st);
+      cudaMemcpyAsync(post_cov, pc.p, K * UU * 8, cudaMemcpyDeviceToHost, c->st);
+      if (cudaStreamSynchronize(c->st) != cudaSuccess) { mb_set_error(__FILE__, __LINE__, "copy back failed"); rc = -2; }
+    }
+  }
+  gX.release(); gi.release(); pm.release(); pc.release(); m0.release(); dtau.release();
+  return rc;
+}
+
 extern "C" int mb_hyperposterior(mb_context* c, const mb_kernel* kern_0, const double* hp_0,
                                  const mb_kernel* kern_i, const double* hp_i, int hp_i_shared,
                                  int32_t n_grid, const double* grid_X, const int32_t* grid_index,
                                  const double* m_0, double pen_diag, double* post_mean,
                                  double* post_cov) {
-  MB_TRY(check_ctx(c));
-  if (!c->have_db) MB_FAIL(-1, "no dataset uploaded");
-  if (c->db.nmax > TK_MAXN) MB_FAIL(-4, "a task has more than 96 points: the large-task path is not built yet");
-  if (!grid_X || !grid_index || n_grid < 1 || !m_0 || !post_mean || !post_cov) MB_FAIL(-1, "bad argument");
-  for (int64_t r = 0; r < c->n_rows; ++r)
-    if (grid_index[r] < 0 || grid_index[r] >= n_grid) MB_FAIL(-1, "grid_index out of range");
-  const size_t UU = (size_t)n_grid * n_grid;
-  DBuf gX, gi, pm, pc, m0;
-  int rc = 0;
-  if (gX.ensure((size_t)n_grid * c->db.D * 8) || gi.ensure(c->n_rows * 4) || pm.ensure((size_t)n_grid * 8) ||
-      pc.ensure(UU * 8) || m0.ensure((size_t)n_grid * 8)) rc = -3;
-  if (!rc) {
-    cudaMemcpyAsync(gX.p, grid_X, (size_t)n_grid * c->db.D * 8, cudaMemcpyHostToDevice, c->st);
-    cudaMemcpyAsync(gi.p, grid_index, c->n_rows * 4, cudaMemcpyHostToDevice, c->st);
-    cudaMemcpyAsync(m0.p, m_0, (size_t)n_grid * 8, cudaMemcpyHostToDevice, c->st);
-    int64_t stride;
-    rc = put_hp_i(c, kern_i, hp_i, hp_i_shared, &stride);
-    if (!rc) rc = (cudaStreamSynchronize(c->st) == cudaSuccess) ? 0 : -2;
-    if (!rc) rc = dev_e_step(c, 1, kern_0, hp_0, make_devkern(kern_i), c->hp_i.as<double>(), stride,
-                             m0.as<double>(), nullptr, gX.as<double>(), n_grid, gi.as<int32_t>(), pen_diag,
-                             pm.as<double>(), pc.as<double>(), nullptr);
-    if (!rc) {
-      cudaMemcpyAsync(post_mean, pm.p, (size_t)n_grid * 8, cudaMemcpyDeviceToHost, c->st);
-      cudaMemcpyAsync(post_cov, pc.p, UU * 8, cudaMemcpyDeviceToHost, c->st);
-      if (cudaStreamSynchronize(c->st) != cudaSuccess) { mb_set_error(__FILE__, __LINE__, "copy back failed"); rc = -2; }
-    }
-  }
-  gX.release(); gi.release(); pm.release(); pc.release(); m0.release();
-  return rc;
+  return hyperposterior_any(c, 1, kern_0, hp_0, kern_i, hp_i, hp_i_shared, n_grid, grid_X, grid_index, m_0,
+                            nullptr, pen_diag, post_mean, post_cov);
+}
+
+extern "C" int mb_hyperposterior_clust(mb_context* c, int n_clusters, const mb_kernel* kern_k, const double* hp_k,
+                                       const mb_kernel* kern_i, const double* hp_i, int hp_i_shared,
+                                       int32_t n_grid, const double* grid_X, const int32_t* grid_index,
+                                       const double* m_k, const double* tau, double pen_diag,
+                                       double* post_mean, double* post_cov) {
+  return hyperposterior_any(c, n_clusters, kern_k, hp_k, kern_i, hp_i, hp_i_shared, n_grid, grid_X, grid_index,
+                            m_k, tau, pen_diag, post_mean, post_cov);
 }
 
 extern "C" int mb_logL_GP_mod_tasks(mb_context* c, const mb_kernel* kern_i, const double* hp_i,
@@ -1303,6 +1328,38 @@ extern "C" int mb_pred_magma(mb_context* c, const mb_kernel* k, const double* hp
   MB_TRY(d2h(pred_mean, dmean, (size_t)np * 8, s));
   MB_TRY(d2h(pred_var, dvar, (size_t)np * 8, s));
   CU(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// pred_magmaclust (prediction.R:2298-2413) for one new task: the GP conditional of mb_pred_magma per cluster
+// with that cluster's hyper-posterior blocks, then the mixture mean / variance.  The final combination of
+// K short vectors (prediction.R:2380,2396-2404) is host arithmetic in the reference's order.
+extern "C" int mb_pred_magmaclust(mb_context* c, int n_clusters, const mb_kernel* k, const double* hp,
+                                  const double* x_obs, int n_obs, const double* y_obs, const double* x_pred,
+                                  int n_pred, int d, const double* mean_obs, const double* mean_pred,
+                                  const double* cov_obs, const double* cov_pred, const double* cov_crossed,
+                                  const double* proba, double pen_diag, double* pred_mean, double* pred_var,
+                                  double* pred_cov, double* mix_mean, double* mix_var) {
+  if (n_clusters < 1 || n_clusters > MB_MAX_CLUSTERS) MB_FAIL(-1, "bad cluster count");
+  if (!proba || !mix_mean || !mix_var || !pred_mean || !pred_var) MB_FAIL(-1, "null argument");
+  const size_t no = n_obs, np = n_pred;
+  for (int q = 0; q < n_clusters; ++q)
+    MB_TRY(mb_pred_magma(c, k, hp, x_obs, n_obs, y_obs, x_pred, n_pred, d, mean_obs + q * no, mean_pred + q * np,
+                         cov_obs + q * no * no, cov_pred + q * np * np, cov_crossed + q * no * np, pen_diag,
+                         pred_mean + q * np, pred_var + q * np, pred_cov ? pred_cov + q * np * np : nullptr));
+  for (size_t j = 0; j < np; ++j) {
+    double m = 0.0;
+    for (int q = 0; q < n_clusters; ++q) m = m + proba[q] * pred_mean[q * np + j];
+    mix_mean[j] = m;
+  }
+  for (size_t j = 0; j < np; ++j) {
+    double v = 0.0;
+    for (int q = 0; q < n_clusters; ++q) {
+      const double dm = pred_mean[q * np + j] - mix_mean[j];
+      v = v + proba[q] * (pred_var[q * np + j] + dm * dm);
+    }
+    mix_var[j] = v;
+  }
   return 0;
 }
 

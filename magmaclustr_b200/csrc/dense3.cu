@@ -56,33 +56,25 @@ __device__ __forceinline__ void d3_update_tile(double* T1, int idx, int e, int k
   *reinterpret_cast<double2*>(Tij + L.o_c) = cv;
 }
 
-// blocked upper Cholesky in place, inverses of the diagonal tiles to Xd; 0 or failing pivot code
+// blocked upper Cholesky in place; every panel tile is a substitution solve with the factored diagonal
+// tile (no explicit inverse anywhere in the factorisation).  0 or failing pivot code.
 __device__ inline int d3_chol(const SmD& s, int n8, const Ln& L) {
   const int ntri = n8 * (n8 + 1) / 2;
   if (threadIdx.x == 0) *s.flag = 0;
   __syncthreads();
   if (L.warp == 0) {
     const int f = warp_factor_panel(s.T1, n8 < 4 ? n8 : 4, s.rinv, L.lane);
-    if (f) { if (L.lane == 0) *s.flag = f; }
-    else if (4 < n8 || n8 == 1) warp_diag_inverse(s.T1, s.rinv, s.Xd, L.lane);
+    if (f && L.lane == 0) *s.flag = f;
   }
   __syncthreads();
   if (*s.flag) return *s.flag;
   for (int k = 0; k + 1 < n8; ++k) {
     const int dk = d3_tri(k, n8);
-    double* Xkk = s.Xd + (size_t)k * 64;
-    const bool far = (k + 4 < n8);
-    if (far) {
-      for (int j = k + 4 + L.warp; j < n8; j += NWS) {
-        double* Tkj = s.T1 + (size_t)(dk + j - k) * 64;
-        double a0, a1, b0, b1, c0 = 0.0, c1 = 0.0;
-        cf(Xkk, L, a0, a1);
-        cf(Tkj, L, b0, b1);
-        dmma884(c0, c1, a0, b0);
-        dmma884(c0, c1, a1, b1);
-        __syncwarp();
-        *reinterpret_cast<double2*>(Tkj + L.o_c) = make_double2(c0, c1);
-      }
+    if (k + 4 < n8) {
+      // remaining panel tiles R_kj = R_kk^{-T} A_kj, four tiles per warp
+      for (int j = k + 4 + 4 * L.warp; j < n8; j += 4 * NWS)
+        warp_panel_solve(s.T1 + (size_t)dk * 64, s.rinv + 8 * k, s.T1 + (size_t)(dk + j - k) * 64,
+                         (n8 - j) < 4 ? (n8 - j) : 4, L.lane);
       __syncthreads();
     }
     const int m = n8 - k - 1, nla = m < 4 ? m : 4;
@@ -93,11 +85,8 @@ __device__ inline int d3_chol(const SmD& s, int n8, const Ln& L) {
         if (q < nla) d3_update_tile(s.T1, j0 + q, s.tab[j0 + q], k, dk, L);
       __syncwarp();
       const int f = warp_factor_panel(s.T1 + (size_t)j0 * 64, nla, s.rinv + 8 * (k + 1), L.lane);
-      if (f) { if (L.lane == 0) *s.flag = 8 * (k + 1) + f; }
-      else if (k + 5 < n8 || k + 2 == n8)
-        warp_diag_inverse(s.T1 + (size_t)j0 * 64, s.rinv + 8 * (k + 1), s.Xd + (size_t)(k + 1) * 64, L.lane);
+      if (f && L.lane == 0) *s.flag = 8 * (k + 1) + f;
     } else {
-      if (!far && L.warp == NWS - 1) warp_diag_inverse(s.T1 + (size_t)dk * 64, s.rinv + 8 * k, Xkk, L.lane);
       for (int idx = j0 + nla + L.warp - 1; idx < ntri; idx += NWS - 1) d3_update_tile(s.T1, idx, s.tab[idx], k, dk, L);
     }
     __syncthreads();
@@ -106,26 +95,16 @@ __device__ inline int d3_chol(const SmD& s, int n8, const Ln& L) {
   return 0;
 }
 
-// in place: off-diagonal tiles R_im <- -X_ii R_im, then rows bottom-up X_ij = sum_{i<m<=j} T1_im X_mj
-// (row i's results are held in registers until every read of the old row is done), finally the diagonal
-// tiles X_ii from Xd.
+// in place X = R^{-1}: diagonal tiles by substitution (Xd), then block rows bottom-up:
+//   W_ij = -sum_{i<m<=j} R_im X_mj  (DMMA, held in registers until every read of row i is done),
+//   X_ij = R_ii^{-1} W_ij           (back substitution with the diagonal tile, like dtrsm);
+// finally the diagonal tiles X_ii are copied in.
 __device__ inline void d3_trtri(const SmD& s, int n8, const Ln& L) {
-  const int ntri = n8 * (n8 + 1) / 2;
-  for (int idx = L.warp; idx < ntri; idx += NWS) {
-    const int e = s.tab[idx], i = e >> 8, j = e & 255;
-    if (i == j) continue;
-    double* Tim = s.T1 + (size_t)idx * 64;
-    double a0, a1, b0, b1, c0 = 0.0, c1 = 0.0;
-    rf(s.Xd + (size_t)i * 64, L, a0, a1);
-    cf(Tim, L, b0, b1);
-    dmma884(c0, c1, a0, -b0);
-    dmma884(c0, c1, a1, -b1);
-    __syncwarp();
-    *reinterpret_cast<double2*>(Tim + L.o_c) = make_double2(c0, c1);
-  }
+  for (int k = L.warp; k < n8; k += NWS)
+    warp_diag_inverse(s.T1 + (size_t)d3_tri(k, n8) * 64, s.rinv + 8 * k, s.Xd + (size_t)k * 64, L.lane);
   __syncthreads();
   for (int i = n8 - 2; i >= 0; --i) {
-    const double* Ti = s.T1 + (size_t)(d3_tri(i, n8) - i) * 64;   // tile (i, m) at Ti + m * 64
+    double* Ti = s.T1 + (size_t)(d3_tri(i, n8) - i) * 64;   // tile (i, m) at Ti + m * 64
     double res[2][2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -137,21 +116,20 @@ __device__ inline void d3_trtri(const SmD& s, int n8, const Ln& L) {
           double a0, a1, b0, b1, p0, p1, q0, q1;
           rf(Ti + (size_t)m * 64, L, a0, a1);
           rf(Ti + (size_t)(m + 1) * 64, L, p0, p1);
-          // X_mj: tile (m, j) of T1 for m < j, Xd_j for m == j
           cf(s.T1 + (size_t)(d3_tri(m, n8) + j - m) * 64, L, b0, b1);
           if (m + 1 < j) cf(s.T1 + (size_t)(d3_tri(m + 1, n8) + j - m - 1) * 64, L, q0, q1);
           else cf(s.Xd + (size_t)j * 64, L, q0, q1);
-          dmma884(c0, c1, a0, b0);
-          dmma884(e0, e1, p0, q0);
-          dmma884(c0, c1, a1, b1);
-          dmma884(e0, e1, p1, q1);
+          dmma884(c0, c1, -a0, b0);
+          dmma884(e0, e1, -p0, q0);
+          dmma884(c0, c1, -a1, b1);
+          dmma884(e0, e1, -p1, q1);
         }
         if (m <= j) {   // m == j
           double a0, a1, b0, b1;
           rf(Ti + (size_t)m * 64, L, a0, a1);
           cf(s.Xd + (size_t)j * 64, L, b0, b1);
-          dmma884(c0, c1, a0, b0);
-          dmma884(c0, c1, a1, b1);
+          dmma884(c0, c1, -a0, b0);
+          dmma884(c0, c1, -a1, b1);
         }
       }
       res[h][0] = c0 + e0;
@@ -161,8 +139,11 @@ __device__ inline void d3_trtri(const SmD& s, int n8, const Ln& L) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int j = i + 1 + L.warp + h * NWS;
-      if (j < n8) *reinterpret_cast<double2*>(const_cast<double*>(Ti) + (size_t)j * 64 + L.o_c) = make_double2(res[h][0], res[h][1]);
+      if (j < n8) *reinterpret_cast<double2*>(Ti + (size_t)j * 64 + L.o_c) = make_double2(res[h][0], res[h][1]);
     }
+    __syncthreads();
+    for (int j = i + 1 + 4 * L.warp; j < n8; j += 4 * NWS)
+      warp_row_backsolve(Ti + (size_t)i * 64, s.rinv + 8 * i, Ti + (size_t)j * 64, (n8 - j) < 4 ? (n8 - j) : 4, L.lane);
     __syncthreads();
   }
   for (int e = threadIdx.x; e < n8 * 64; e += DSM_THREADS) s.T1[(size_t)d3_tri(e >> 6, n8) * 64 + (e & 63)] = s.Xd[e];

@@ -80,3 +80,46 @@ __device__ __forceinline__ void warp_diag_inverse(const double* Rt, const double
   __syncwarp();
 }
 
+
+// Z = R_kk^{-T} A for up to four contiguous tiles (32 columns) by forward substitution, lane c owning column
+// c & 7 of tile c >> 3 -- the panel step of dpotrf as a true triangular solve (what dtrsm does), not a product
+// with an explicit inverse: on the ill-conditioned union-grid matrices (cond ~ 1e12) the latter loses
+// cond(R_kk) more digits.  Rkk: factored diagonal tile, rinv8: reciprocals of its diagonal.
+__device__ __forceinline__ void warp_panel_solve(const double* Rkk, const double* rinv8, double* P, int ntiles, int lane) {
+  const int cb = lane >> 3, cc = lane & 7;
+  if (cb < ntiles) {
+    double* T = P + (size_t)cb * 64;
+    double a[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a[r] = T[sw(r, cc)];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[j] *= rinv8[j];
+#pragma unroll
+      for (int i = j + 1; i < 8; ++i) a[i] -= Rkk[sw(j, i)] * a[j];
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) T[sw(r, cc)] = a[r];
+  }
+  __syncwarp();
+}
+
+// X = R_ii^{-1} W for up to four contiguous tiles by back substitution (same lane mapping)
+__device__ __forceinline__ void warp_row_backsolve(const double* Rii, const double* rinv8, double* P, int ntiles, int lane) {
+  const int cb = lane >> 3, cc = lane & 7;
+  if (cb < ntiles) {
+    double* T = P + (size_t)cb * 64;
+    double a[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a[r] = T[sw(r, cc)];
+#pragma unroll
+    for (int r = 7; r >= 0; --r) {
+      a[r] *= rinv8[r];
+#pragma unroll
+      for (int i = 0; i < r; ++i) a[i] -= Rii[sw(i, r)] * a[r];
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) T[sw(r, cc)] = a[r];
+  }
+  __syncwarp();
+}

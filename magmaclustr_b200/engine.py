@@ -339,6 +339,37 @@ class Context:
                                          ptr(f64(tau)), ptr(f64(prop_mixture)), float(pen_diag), C.byref(out)))
         return out.value
 
+    def hyperposterior_clust(self, K, kk, hp_k, ki, hp_i, grid_X, grid_index, m_k, tau, pen_diag=1e-10, shared=False):
+        gX = f64(np.atleast_2d(np.asarray(grid_X, dtype=np.float64).T).T)
+        gi = np.ascontiguousarray(grid_index, dtype=np.int32)
+        u = gX.shape[0]
+        pm = np.zeros((K, u))
+        pc = np.zeros((K, u, u))
+        mk = f64(np.broadcast_to(np.asarray(m_k, dtype=np.float64).reshape(K, -1), (K, u)))
+        check(L.lib().mb_hyperposterior_clust(self._h, int(K), C.byref(kk), ptr(f64(hp_k)), C.byref(ki), ptr(f64(hp_i)),
+                                              1 if shared else 0, u, ptr(gX), ptr(gi), ptr(mk), ptr(f64(tau)),
+                                              float(pen_diag), ptr(pm), ptr(pc)))
+        return pm, pc
+
+    def pred_magmaclust(self, K, k, hp, x_obs, y_obs, x_pred, mean_obs, mean_pred, cov_obs, cov_pred, cov_crossed,
+                        proba, pen_diag=1e-10, full_cov=True):
+        """Cluster-leading arrays: mean_obs (K, n_obs), cov_obs (K, n_obs, n_obs), cov_crossed (K, n_obs, n_pred)."""
+        xo = f64(np.atleast_2d(np.asarray(x_obs, dtype=np.float64).T).T)
+        xp = f64(np.atleast_2d(np.asarray(x_pred, dtype=np.float64).T).T)
+        no, d = xo.shape
+        npred = xp.shape[0]
+        colmajor = lambda a: f64(np.transpose(np.asarray(a, dtype=np.float64), (0, 2, 1)))   # each block column-major
+        mean = np.zeros((K, npred)); var = np.zeros((K, npred))
+        cov = np.zeros((K, npred, npred)) if full_cov else None
+        mm = np.zeros(npred); mv = np.zeros(npred)
+        check(L.lib().mb_pred_magmaclust(self._h, int(K), C.byref(k), ptr(f64(hp)), ptr(xo), no, ptr(f64(y_obs)), ptr(xp),
+                                         npred, d, ptr(f64(mean_obs)), ptr(f64(mean_pred)), ptr(colmajor(cov_obs)),
+                                         ptr(colmajor(cov_pred)), ptr(colmajor(cov_crossed)), ptr(f64(proba)),
+                                         float(pen_diag), ptr(mean), ptr(var), ptr(cov), ptr(mm), ptr(mv)))
+        if full_cov:
+            cov = np.transpose(cov, (0, 2, 1))
+        return mean, var, cov, mm, mv
+
     def train_magmaclust(self, K, kk, hp_k, ki, hp_i, ini_mixture, shared_hp_k=True, shared_hp_i=True,
                          pen_diag=1e-10, n_iter_max=25, cv_threshold=1e-3, m_k=None):
         """VEM loop of train_magmaclust (training.R:1622-1758); every step runs in the library."""

@@ -40,9 +40,11 @@ def cpp_perio(m1, m2, period):
     """code.cpp:31-52."""
     m1, m2 = _mat(m1), _mat(m2)
     out = np.zeros((m1.shape[0], m2.shape[0]))
-    w = math.pi / math.exp(period)
+    with np.errstate(all="ignore"):
+        w = float(np.float64(math.pi) / np.exp(np.float64(period)))   # IEEE like C++: pi / 0 = Inf
     for c in range(m1.shape[1]):
-        s = np.sin(w * np.abs(m1[:, c][:, None] - m2[:, c][None, :]))
+        with np.errstate(all="ignore"):
+            s = np.sin(w * np.abs(m1[:, c][:, None] - m2[:, c][None, :]))
         out += s * s
     return out
 
@@ -51,10 +53,12 @@ def cpp_perio_deriv(m1, m2, period):
     """code.cpp:56-76."""
     m1, m2 = _mat(m1), _mat(m2)
     out = np.zeros((m1.shape[0], m2.shape[0]))
-    w = math.pi / math.exp(period)
+    with np.errstate(all="ignore"):
+        w = float(np.float64(math.pi) / np.exp(np.float64(period)))
     for c in range(m1.shape[1]):
-        a = w * np.abs(m1[:, c][:, None] - m2[:, c][None, :])
-        out += 2 * np.sin(a) * np.cos(a) * a
+        with np.errstate(all="ignore"):
+            a = w * np.abs(m1[:, c][:, None] - m2[:, c][None, :])
+            out += 2 * np.sin(a) * np.cos(a) * a
     return out
 
 

@@ -267,3 +267,44 @@ def train_magmaclust(db, nb_cluster, ini_hp_k, ini_hp_i, kern_k, kern_i, ini_mix
             break
     return {"hp_k": hp_k, "hp_i": hp_i, "m_k": m_k, "mixture": mixture, "prop_mixture": prop, "mean_k": mean_k,
             "cov_k": cov_k, "seq_elbo": seq, "converged": cv}
+
+
+# ---- prediction -------------------------------------------------------------------------------------
+def hyperposterior_clust(db, hp_k, hp_i, kern_k, kern_i, m_k, mixture, grid_X, pen_diag=1e-10):
+    """prediction.R:1685-1764: the K weighted hyper-posteriors re-evaluated on data U grid (the
+    mixture is taken as given).  m_k: list of K scalars/vectors.  Returns keys, X, mean[K], cov[K]."""
+    if grid_X is None:
+        keys, Xg, index = db.grid_keys, db.grid_X, db.index
+    else:
+        keys, Xg, index = db.extend_grid(grid_X)
+    Kc, U = len(hp_k), Xg.shape[0]
+    row = {i: t for t, i in enumerate(db.ids)}
+    inv_k = [K.kern_to_inv(Xg, kern_k, hp_k[k], pen_diag) for k in range(Kc)]
+    inv_i = {i: K.kern_to_inv(db.tasks[i][1], kern_i, hp_i[i], pen_diag) for i in db.ids}
+    cov_k, mean_k = [], []
+    for k in range(Kc):
+        post_inv = inv_k[k].copy()
+        for i in db.ids:
+            idx = index[i]
+            post_inv[np.ix_(idx, idx)] += mixture[row[i], k] * inv_i[i]
+        cov_k.append(K.chol_inv_jitter(post_inv, pen_diag))
+    for k in range(Kc):
+        weighted = inv_k[k] @ M._mean_vec(m_k[k], U)
+        for i in db.ids:
+            weighted[index[i]] += mixture[row[i], k] * (inv_i[i] @ db.tasks[i][2])
+        mean_k.append(cov_k[k] @ weighted)
+    return {"keys": keys, "X": Xg, "mean": mean_k, "cov": cov_k}
+
+
+def pred_magmaclust(X_obs, y_obs, X_pred, kern, hp, hyperpost, proba, pen_diag=1e-10):
+    """prediction.R:2298-2413 for one new task whose mixture probabilities are `proba` (K)."""
+    preds = [M.pred_magma(X_obs, y_obs, X_pred, kern, hp,
+                          {"keys": hyperpost["keys"], "mean": hyperpost["mean"][k], "cov": hyperpost["cov"][k]}, pen_diag)
+             for k in range(len(proba))]
+    mixture_mean = 0
+    for k, p in enumerate(preds):
+        mixture_mean = mixture_mean + proba[k] * p["Mean"]
+    mixture_var = 0
+    for k, p in enumerate(preds):
+        mixture_var = mixture_var + proba[k] * (p["Var"] + (p["Mean"] - mixture_mean) ** 2)
+    return {"pred": preds, "Mean": mixture_mean, "Var": mixture_var, "keys": preds[0]["keys"], "X": preds[0]["X"]}

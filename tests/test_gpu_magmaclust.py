@@ -116,3 +116,43 @@ def test_train_magmaclust_small(ctx):
     np.testing.assert_allclose(res["seq_elbo"], ores["seq_elbo"], rtol=2e-3)
     assert np.array_equal(np.argmax(res["mixture"], axis=1), np.argmax(ores["mixture"], axis=1))
     assert np.all(np.diff(res["seq_elbo"]) > -1e-6 * np.abs(res["seq_elbo"][1:]))
+
+
+def test_hyperposterior_clust_and_pred_magmaclust(ctx):
+    """hyperposterior_clust on data U grid (prediction.R:1685-1764), then pred_magmaclust for a new task
+    (prediction.R:2298-2413): per-cluster conditionals and the mixture mean / variance."""
+    from magmaclustr_b200.dataprep import reference_keys, r_signif
+    case, mix, hp_k, o_hp_k = _setup(ctx, shared_i=True)
+    prep, odb = case["prep"], case["odb"]
+    rng = np.random.default_rng(5)
+    Xp = np.round(np.linspace(-1, 1, 9), 2)[:, None]
+    i0 = prep.ids[0]
+    Xo, yo = odb.tasks[i0][1][:4], odb.tasks[i0][2][:4]
+    ohyp = OC.hyperposterior_clust(odb, o_hp_k, case["o_hpi"], "SE", "SE", [0.0] * KC, mix, np.vstack([Xo, Xp]))
+    prep.set_grid(np.vstack([Xo, Xp]))
+    assert [k.decode() for k in prep.grid_keys] == ohyp["keys"]
+    pm, pc = ctx.hyperposterior_clust(KC, case["k0"], hp_k, case["ki"], case["hpi"], prep.grid_X, prep.grid_index,
+                                      np.zeros((KC, 1)), mix)
+    for k in range(KC):
+        assert relerr(pm[k], ohyp["mean"][k]) < 1e-4 and relerr(pc[k], ohyp["cov"][k]) < 1e-4
+    proba = np.array([0.2, 0.5, 0.3])[:KC]
+    proba = proba / proba.sum()
+    hp_new = case["o_hpi"][i0]
+    opred = OC.pred_magmaclust(Xo, yo, Xp, "SE", hp_new, ohyp, proba)
+    Xo_r, Xp_r = r_signif(Xo), r_signif(Xp)
+    ko, kp = reference_keys(Xo_r), reference_keys(Xp_r)
+    oo, op = np.argsort(ko, kind="stable"), np.argsort(kp, kind="stable")
+    io, ip = prep.index_of(ko[oo]), prep.index_of(kp[op])
+    Hm, Hc = np.array(ohyp["mean"]), np.array(ohyp["cov"])
+    mean, var, cov, mm, mv = ctx.pred_magmaclust(
+        KC, case["ki"], np.array([hp_new[n] for n in case["names_i"]]), Xo_r[oo], yo[oo], Xp_r[op],
+        Hm[:, io], Hm[:, ip], np.array([Hc[k][np.ix_(io, io)] for k in range(KC)]),
+        np.array([Hc[k][np.ix_(ip, ip)] for k in range(KC)]), np.array([Hc[k][np.ix_(io, ip)] for k in range(KC)]), proba)
+    for k in range(KC):
+        np.testing.assert_allclose(mean[k], opred["pred"][k]["Mean"], rtol=1e-8, atol=1e-9)
+        np.testing.assert_allclose(var[k], opred["pred"][k]["Var"], rtol=1e-7, atol=1e-10)
+        assert relerr(cov[k], opred["pred"][k]["cov"]) < 1e-7
+    np.testing.assert_allclose(mm, opred["Mean"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(mv, opred["Var"], rtol=1e-7, atol=1e-10)
+    assert np.all(mv >= 0)
+    prep.set_grid(None)
