@@ -140,7 +140,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count()
-    m_sample = args.cpu_sample or 1024      # ~5 s of CPU work per step on 16 cores
+    m_sample = args.cpu_sample or 2048      # a few seconds of CPU work per step
     df, _, _, _ = make_inputs()
     secs = []
     for s in range(args.warmup + args.steps):
@@ -310,7 +310,10 @@ def main():
         line["fit"] = fit
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count()
-        m_sample = args.cpu_sample or 3072  # 10-30 s of CPU work on the box's host cores
+        m_sample = args.cpu_sample
+        if not m_sample:                     # size the sample for ~15 s of CPU work on this box's cores
+            dt0, _, _ = oracle_sample_step(df, 512, cores)
+            m_sample = int(min(M_TASKS, max(512, 512 * 15.0 / max(dt0, 1e-3)))) // 256 * 256
         dt, evals, _ = oracle_sample_step(df, m_sample, cores)
         line["cpu_baseline"] = {
             "value": 1.0 / (dt * M_TASKS / m_sample), "unit": "EM steps/s", "cores": cores,

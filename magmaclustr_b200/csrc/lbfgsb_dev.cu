@@ -18,32 +18,44 @@ __global__ void k_lbfgsb_init(LbfgsbState* st, int64_t m, int n, const double* x
 }
 
 // Feed (f[t], g[t,:]) to every still-active problem; n_active[0] += problems still active.
-// The 2.3 KB state is copied to thread-local memory with 16-byte loads (whole sectors per thread),
-// advanced there (local memory is interleaved per thread, so the state machine's scattered accesses
-// coalesce) and written back.
-__global__ void __launch_bounds__(64) k_lbfgsb_advance(LbfgsbState* st, int64_t m, int n, const double* f,
+// One warp per 32 problems.  The 2192-byte states of the ACTIVE problems are staged through shared memory
+// with warp-cooperative, fully coalesced 16-byte copies (a padded stride of 275 doubles keeps the per-thread
+// accesses of the state machine bank-conflict free); inactive problems cost one 4-byte read.
+#define LB_STRIDE_D 275   /* doubles per staged state: 274 + 1 pad (odd => conflict-free half-warps) */
+__global__ void __launch_bounds__(32) k_lbfgsb_advance(LbfgsbState* st, int64_t m, int n, const double* f,
                                                       const double* g, int* n_active) {
-  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (t >= m) return;
-  if (!st[t].active) return;
-  static_assert(sizeof(LbfgsbState) % 16 == 0, "LbfgsbState must be a multiple of 16 bytes");
-  LbfgsbState loc;
-  {
-    const double2* src = reinterpret_cast<const double2*>(&st[t]);
-    double2* dst = reinterpret_cast<double2*>(&loc);
-#pragma unroll 4
-    for (int i = 0; i < (int)(sizeof(LbfgsbState) / 16); ++i) dst[i] = src[i];
+  extern __shared__ double lb_smem[];
+  static_assert(sizeof(LbfgsbState) == 274 * 8, "LbfgsbState layout changed: update LB_STRIDE_D");
+  const int lane = threadIdx.x;
+  const int64_t t0 = (int64_t)blockIdx.x * 32;
+  const int64_t t = t0 + lane;
+  const bool mine = t < m && st[t].active;
+  const unsigned act = __ballot_sync(0xffffffffu, mine);
+  if (act == 0) return;
+  for (int q = 0; q < 32; ++q) {
+    if (!((act >> q) & 1u)) continue;
+    const double* src = reinterpret_cast<const double*>(&st[t0 + q]);
+    double* dst = lb_smem + (size_t)q * LB_STRIDE_D;
+    for (int i = lane; i < 274; i += 32) dst[i] = src[i];
   }
-  double gl[LB_NP];
-  for (int p = 0; p < n; ++p) gl[p] = g[t * n + p];
-  lb_advance(&loc, f[t], gl);
-  {
-    double2* dst = reinterpret_cast<double2*>(&st[t]);
-    const double2* src = reinterpret_cast<const double2*>(&loc);
-#pragma unroll 4
-    for (int i = 0; i < (int)(sizeof(LbfgsbState) / 16); ++i) dst[i] = src[i];
+  __syncwarp();
+  int still = 0;
+  if (mine) {
+    LbfgsbState* s = reinterpret_cast<LbfgsbState*>(lb_smem + (size_t)lane * LB_STRIDE_D);
+    double gl[LB_NP];
+    for (int p = 0; p < n; ++p) gl[p] = g[t * n + p];
+    lb_advance(s, f[t], gl);
+    still = s->active;
   }
-  if (loc.active) atomicAdd(n_active, 1);
+  __syncwarp();
+  for (int q = 0; q < 32; ++q) {
+    if (!((act >> q) & 1u)) continue;
+    double* dst = reinterpret_cast<double*>(&st[t0 + q]);
+    const double* src = lb_smem + (size_t)q * LB_STRIDE_D;
+    for (int i = lane; i < 274; i += 32) dst[i] = src[i];
+  }
+  const unsigned alive = __ballot_sync(0xffffffffu, still != 0);
+  if (lane == 0 && alive) atomicAdd(n_active, __popc(alive));
 }
 
 // x -> HP table; fail codes and evaluation counts out.
@@ -66,7 +78,14 @@ cudaError_t launch_lbfgsb_init(LbfgsbState* st, int64_t m, int n, const double* 
 
 cudaError_t launch_lbfgsb_advance(LbfgsbState* st, int64_t m, int n, const double* f,
                                   const double* g, int* n_active, cudaStream_t s) {
-  k_lbfgsb_advance<<<(unsigned)((m + 63) / 64), 64, 0, s>>>(st, m, n, f, g, n_active);
+  const size_t smem = (size_t)32 * LB_STRIDE_D * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_lbfgsb_advance, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  k_lbfgsb_advance<<<(unsigned)((m + 31) / 32), 32, smem, s>>>(st, m, n, f, g, n_active);
   return cudaGetLastError();
 }
 
