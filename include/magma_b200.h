@@ -253,6 +253,16 @@ int mb_profile_read(mb_context*, double* out3);
 /* Write `bytes` of device memory (L2 flush between timed iterations). */
 int mb_flush_l2(mb_context*, int64_t bytes);
 
+/* C = op(A) op(B) on host column-major matrices: R's `%*%`, crossprod(), tcrossprod() -> BLAS dgemm in the
+ * reference (e.g. /root/reference/R/prediction.R:1165-1190, R/gradients-likelihoods.R:84-94).  transX != 0
+ * means op(X) = t(X).  A is (transa ? k x m : m x k) with leading dimension lda, etc. */
+int mb_matmul(mb_context*, int transa, int transb, int m, int n, int k, const double* A, int lda,
+              const double* B, int ldb, double* C, int ldc);
+/* Device-only timing of the large-matrix kernels (batched-Cholesky FP64 TFLOP/s of BASELINE.json's metric)
+ * on an n-point SE + noise covariance: what = 0 product (2 n^3 flops), 1 chol() (n^3 / 3), 2 chol2inv(chol())
+ * (n^3).  ms_out[0] = mean milliseconds per repetition, CUDA events on the library's stream. */
+int mb_bench_dense(mb_context*, int what, int n, int reps, double* ms_out);
+
 /* ---- optimiser, exposed for tests: optim(method="L-BFGS-B") on a built-in test function
  * (0 = Rosenbrock n=2), run by the same state machine the M step uses (host build). */
 int mb_lbfgsb_selftest(int which, double* x, int n, double factr, int maxit, double* fval,

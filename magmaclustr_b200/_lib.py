@@ -85,6 +85,8 @@ _SIGS = {
     "mb_profile": [_vp, C.c_int],
     "mb_profile_read": [_vp, _dp],
     "mb_flush_l2": [_vp, C.c_int64],
+    "mb_matmul": [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int],
+    "mb_bench_dense": [_vp, C.c_int, C.c_int, C.c_int, _dp],
     "mb_lbfgsb_selftest": [C.c_int, _dp, C.c_int, C.c_double, C.c_int, _dp, _ip, _ip],
 }
 

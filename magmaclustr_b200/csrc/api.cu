@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "lbfgsb.h"
 #include "tasks.cuh"
+#include "dense_big.cuh"
 
 // ---- launchers defined in the other translation units ------------------------------------
 cudaError_t launch_task_objective(TaskObjArgs a, int n_launch, cudaStream_t st);
@@ -75,12 +76,15 @@ cudaError_t launch_gemm_dmma(int m, int n, int k, const double* A, int64_t ars, 
 cudaError_t launch_resid_gemv(int n, const double* A, const double* y, const double* mean, double* r, double* al,
                               cudaStream_t st);
 // chol_inv_jitter of a device matrix: shared-memory-resident kernel when it fits (U <= 224), else the
-// L2-resident one.  MB_DENSE_KERNEL=v2 forces the latter (cross-check).
-static bool dense_use_sm(int n) {
+// multi-CTA blocked path of dense_big.cu.  MB_DENSE_KERNEL=v2 forces the single-CTA L2-resident kernel of
+// dense.cu (cross-check only: slow).
+static int dense_env() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MB_DENSE_KERNEL"); v = (e && e[0] == 'v' && e[1] == '2') ? 0 : 1; }
-  return v == 1 && dense_sm_fits(n);
+  if (v < 0) { const char* e = getenv("MB_DENSE_KERNEL"); v = (e && e[0] == 'v' && e[1] == '2') ? 0 : ((e && e[0] == 'b') ? 2 : 1); }
+  return v;
 }
+static bool dense_use_sm(int n) { return dense_env() == 1 && dense_sm_fits(n); }
+static bool dense_use_big(int n) { return dense_env() == 2 || (dense_env() == 1 && !dense_sm_fits(n)); }
 cudaError_t launch_dense_lu_logdet(const double* src, double* W, int n, int* done, double* out,
                                    cudaStream_t st);
 cudaError_t launch_gemm(int m, int n, int k, const double* A, int64_t ars, int64_t acs,
@@ -423,10 +427,29 @@ extern "C" int mb_kern_to_cov(mb_context* c, const mb_kernel* k, const double* h
 
 // ---- dense chol_inv_jitter on device data -------------------------------------------------------
 // src (n x n, upper read) -> ws.A = inverse.  Synchronises `s`; returns >0 on numerical failure.
+// one chol_inv_jitter (mode 0) / plain Cholesky log-diagonal (mode 1) on the multi-CTA path, host loop over
+// the jitter escalation (kernel-to-matrices.R:670-680).  Synchronises `s`.  info/out: as k_dense_cholinv_sm.
+static int big_cholinv_sync(mb_context* c, DenseWs& ws, const double* src, int n, double pen, int mode, double* inv,
+                            int* info, double* out, cudaStream_t s) {
+  const int64_t ldw = ((int64_t)n + 7) / 8 * 8;
+  int retries = 0;
+  for (;;) {
+    CU(launch_big_cholinv_attempt(src, n, ws.Ap.as<double>(), ws.Bp.as<double>(), ldw, inv, n, pen, retries, mode,
+                                  ws.info.as<int>() + 4, info, out, s, &c->launches));
+    if (mode == 1) return 0;
+    int* slot = c->h_pin_i + 512 + (s == c->st2 ? 1 : 0);
+    MB_TRY(d2h(slot, info, sizeof(int), s));
+    CU(cudaStreamSynchronize(s));
+    if (*slot >= 0 || ++retries > TK_MAX_RETRY) return 0;
+  }
+}
+
 static int dev_cholinv(mb_context* c, DenseWs& ws, const double* src, int n, double pen,
                        cudaStream_t s, int* retries, double* jitter, double* sumlogdiag) {
   if (dense_use_sm(n))
     LAUNCH(c, launch_dense_cholinv_sm(src, n, ws.A.as<double>(), n, pen, 0, ws.info.as<int>(), ws.res.as<double>() + 16, s));
+  else if (dense_use_big(n))
+    MB_TRY(big_cholinv_sync(c, ws, src, n, pen, 0, ws.A.as<double>(), ws.info.as<int>(), ws.res.as<double>() + 16, s));
   else
     LAUNCH(c, launch_dense_cholinv(src, n, ws.Ap.as<double>(), ws.Bp.as<double>(), ws.Xd.as<double>(),
                                    ws.A.as<double>(), n, pen, ws.info.as<int>(), ws.res.as<double>() + 16, s));
@@ -438,6 +461,16 @@ static int dev_cholinv(mb_context* c, DenseWs& ws, const double* src, int n, dou
   if (sumlogdiag) *sumlogdiag = c->h_pin[201];
   if (c->h_pin_i[0] < 0) MB_FAIL(1, "chol_inv_jitter: no positive-definite jitter found");
   return 0;
+}
+
+// C = alpha op(A) op(B) + beta Cin: the 128 x 128-tile DMMA kernel for large products, the 32 x 32 one otherwise
+static cudaError_t gemm_any(int m, int n, int k, const double* A, int64_t ars, int64_t acs, const double* B,
+                            int64_t brs, int64_t bcs, double* C, int64_t ldc, double alpha, const double* Cin,
+                            double beta, cudaStream_t st) {
+  const bool unit = (ars == 1 || acs == 1) && (brs == 1 || bcs == 1);
+  if (unit && (int64_t)m * n >= 192 * 192 && k >= 64)
+    return launch_big_gemm_plain(m, n, k, A, ars, acs, B, brs, bcs, C, ldc, alpha, Cin, beta, st);
+  return launch_gemm_dmma(m, n, k, A, ars, acs, B, brs, bcs, C, ldc, alpha, Cin, beta, st);
 }
 
 extern "C" int mb_chol_inv_jitter(mb_context* c, const double* mat, int n, int ld, double pen_diag,
@@ -606,6 +639,9 @@ static int dense_obj_enqueue(mb_context* c, DenseWs& ws, const DevKern& kd, cons
   if (dense_use_sm(n))
     LAUNCH(c, launch_dense_cholinv_sm(ws.Kmat.as<double>(), n, ws.A.as<double>(), n, pen, 0, ws.info.as<int>(),
                                       ws.res.as<double>() + 16, s));
+  else if (dense_use_big(n))
+    MB_TRY(big_cholinv_sync(c, ws, ws.Kmat.as<double>(), n, pen, 0, ws.A.as<double>(), ws.info.as<int>(),
+                            ws.res.as<double>() + 16, s));
   else
     LAUNCH(c, launch_dense_cholinv(ws.Kmat.as<double>(), n, ws.Ap.as<double>(), ws.Bp.as<double>(),
                                    ws.Xd.as<double>(), ws.A.as<double>(), n, pen, ws.info.as<int>(),
@@ -621,8 +657,8 @@ static int dense_obj_enqueue(mb_context* c, DenseWs& ws, const DevKern& kd, cons
   LAUNCH(c, launch_resid_gemv(n, ws.A.as<double>(), y, mean, ws.r(), ws.al(), s));
   const double* T = nullptr;
   if (want_grad && S) {
-    LAUNCH(c, launch_gemm_dmma(n, n, n, S, n, 1, ws.A.as<double>(), n, 1, ws.B.as<double>(), n, 1.0, nullptr, 0.0, s));
-    LAUNCH(c, launch_gemm_dmma(n, n, n, ws.A.as<double>(), n, 1, ws.B.as<double>(), n, 1, ws.T.as<double>(), n, 1.0, nullptr, 0.0, s));
+    LAUNCH(c, gemm_any(n, n, n, S, n, 1, ws.A.as<double>(), n, 1, ws.B.as<double>(), n, 1.0, nullptr, 0.0, s));
+    LAUNCH(c, gemm_any(n, n, n, ws.A.as<double>(), n, 1, ws.B.as<double>(), n, 1, ws.T.as<double>(), n, 1.0, nullptr, 0.0, s));
     T = ws.T.as<double>();
   }
   LAUNCH(c, launch_dense_obj(kd, hp_host, X, n, D, ws.A.as<double>(), S, T, ws.al(), ws.r(), logdet,
@@ -720,6 +756,11 @@ static int dev_e_step(mb_context* c, int K, const mb_kernel* kern_k, const doubl
 static cudaError_t launch_chol_logdiag_any(mb_context* c, DenseWs& ws, const double* src, int n, int* info,
                                            double* out, cudaStream_t s) {
   if (dense_use_sm(n)) return launch_dense_cholinv_sm(src, n, nullptr, n, 0.0, 1, info, out, s);
+  if (dense_use_big(n)) {
+    const int64_t ldw = ((int64_t)n + 7) / 8 * 8;
+    return launch_big_cholinv_attempt(src, n, ws.Ap.as<double>(), ws.Bp.as<double>(), ldw, nullptr, n, 0.0, 0, 1,
+                                      ws.info.as<int>() + 4, info, out, s, &c->launches);
+  }
   return launch_dense_chol_logdiag(src, ws.Ap.as<double>(), ws.Xd.as<double>(), n, info, out, s);
 }
 
@@ -1247,6 +1288,76 @@ extern "C" int mb_flush_l2(mb_context* c, int64_t bytes) {
   return 0;
 }
 
+// R's `%*%` / crossprod / tcrossprod on host column-major matrices (-> dgemm in the reference): C = op(A) op(B).
+// Computed as C' (row-major) = op(B)' op(A)' so that the device kernel's row-major output IS column-major C.
+extern "C" int mb_matmul(mb_context* c, int transa, int transb, int m, int n, int k, const double* A, int lda,
+                         const double* B, int ldb, double* C, int ldc) {
+  MB_TRY(check_ctx(c));
+  if (!A || !B || !C || m < 1 || n < 1 || k < 1 || ldc < m) MB_FAIL(-1, "bad argument");
+  const int a_rows = transa ? k : m, a_cols = transa ? m : k, b_rows = transb ? n : k, b_cols = transb ? k : n;
+  if (lda < a_rows || ldb < b_rows) MB_FAIL(-1, "bad leading dimension");
+  static thread_local DBuf dA, dB, dC;
+  MB_TRY(dA.ensure((size_t)lda * a_cols * 8));
+  MB_TRY(dB.ensure((size_t)ldb * b_cols * 8));
+  MB_TRY(dC.ensure((size_t)ldc * n * 8));
+  MB_TRY(h2d(dA.p, A, (size_t)lda * a_cols * 8, c->st));
+  MB_TRY(h2d(dB.p, B, (size_t)ldb * b_cols * 8, c->st));
+  if (ldc != m) CU(cudaMemsetAsync(dC.p, 0, (size_t)ldc * n * 8, c->st));
+  // C'(j, i) = sum_k opB(k, j) opA(i, k): left operand (j, k), right operand (k, i)
+  const int64_t lrs = transb ? 1 : ldb, lcs = transb ? ldb : 1;
+  const int64_t rrs = transa ? 1 : lda, rcs = transa ? lda : 1;
+  LAUNCH(c, gemm_any(n, m, k, dB.as<double>(), lrs, lcs, dA.as<double>(), rrs, rcs, dC.as<double>(), ldc, 1.0, nullptr,
+                     0.0, c->st));
+  MB_TRY(d2h(C, dC.p, (size_t)ldc * n * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+// Device-only timing of the large-matrix kernels on a synthetic SE + noise covariance of n equispaced points
+// (what = 0: C = A'B n^3 product, 1: Cholesky, 2: Cholesky + inverse).  ms_out[0] = mean ms per repetition.
+extern "C" int mb_bench_dense(mb_context* c, int what, int n, int reps, double* ms_out) {
+  MB_TRY(check_ctx(c));
+  if (n < 1 || reps < 1 || !ms_out) MB_FAIL(-1, "bad argument");
+  MB_TRY(c->ws1.ensure(n));
+  DenseWs& ws = c->ws1;
+  std::vector<double> x(n);
+  for (int i = 0; i < n; ++i) x[i] = -1.0 + 2.0 * i / (n > 1 ? n - 1 : 1);
+  static thread_local DBuf dx;
+  MB_TRY(dx.ensure((size_t)n * 8));
+  MB_TRY(h2d(dx.p, x.data(), (size_t)n * 8, c->st));
+  mb_kernel k;
+  MB_TRY(mb_kernel_parse("SE", 1, &k));
+  DevKern kd = make_devkern(&k);
+  const double hp[3] = {0.3, -5.0, -3.0};
+  LAUNCH(c, launch_dense_cov(kd, hp, dx.as<double>(), n, dx.as<double>(), n, 1, -1, 1, ws.Kmat.as<double>(), n, 1, c->st));
+  const int64_t ldw = ((int64_t)n + 7) / 8 * 8;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  for (int it = -1; it < reps; ++it) {   // it = -1: warm-up
+    if (it == 0) CU(cudaEventRecord(e0, c->st));
+    if (what == 0) {
+      LAUNCH(c, launch_big_gemm_plain(n, n, n, ws.Kmat.as<double>(), 1, n, ws.Kmat.as<double>(), n, 1, ws.T.as<double>(), n,
+                                      1.0, nullptr, 0.0, c->st));
+    } else {
+      CU(launch_big_cholinv_attempt(ws.Kmat.as<double>(), n, ws.Ap.as<double>(), ws.Bp.as<double>(), ldw, ws.A.as<double>(),
+                                    n, 1e-10, 0, what == 1 ? 1 : 0, ws.info.as<int>() + 4, ws.info.as<int>(),
+                                    ws.res.as<double>() + 16, c->st, &c->launches));
+    }
+  }
+  CU(cudaEventRecord(e1, c->st));
+  CU(cudaEventSynchronize(e1));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  MB_TRY(d2h(c->h_pin_i, ws.info.p, sizeof(int), c->st));
+  CU(cudaStreamSynchronize(c->st));
+  if (what != 0 && c->h_pin_i[0] != 0) MB_FAIL(1, "bench matrix did not factor");
+  ms_out[0] = ms / reps;
+  return 0;
+}
+
 // ---- pred_magma --------------------------------------------------------------------------------
 cudaError_t launch_pred_var(const DevKern& kd, const double* hp_host, const double* xp, int np, int D,
                             const double* sdiag, const double* C, const double* GC, int no,
@@ -1310,14 +1421,14 @@ extern "C" int mb_pred_magma(mb_context* c, const mb_kernel* k, const double* hp
   // mean = mu_pred + C' Gamma^{-1} (y - mu_obs)  (prediction.R:1184-1186)
   LAUNCH(c, launch_axpby(no, 1.0, dyo, -1.0, dmo, dmo, s));
   LAUNCH(c, launch_gemv(no, no, Ginv, no, dmo, nullptr, dvec, s));
-  LAUNCH(c, launch_gemm_dmma(np, 1, no, dC, no, 1, dvec, 1, 1, dmean, 1, 1.0, dmp, 1.0, s));
-  LAUNCH(c, launch_gemm_dmma(no, np, no, Ginv, no, 1, dC, 1, no, dGC, np, 1.0, nullptr, 0.0, s));
+  LAUNCH(c, gemm_any(np, 1, no, dC, no, 1, dvec, 1, 1, dmean, 1, 1.0, dmp, 1.0, s));
+  LAUNCH(c, gemm_any(no, np, no, Ginv, no, 1, dC, 1, no, dGC, np, 1.0, nullptr, 0.0, s));
   const double noise = kd.has_noise ? exp(hp[kd.n_hp - 1]) : 0.0;
   if (full) {
     // cov = K(pred) + S_pred - C' Gamma^{-1} C  (prediction.R:1189)
     LAUNCH(c, launch_dense_cov(kd, hp, dXp, np, dXp, np, d, -1, 0, dKp, np, 1, s));
     LAUNCH(c, launch_axpby((int64_t)np * np, 1.0, dKp, 1.0, dSp, dKp, s));
-    LAUNCH(c, launch_gemm_dmma(np, np, no, dC, no, 1, dGC, np, 1, dKp, np, -1.0, dKp, 1.0, s));
+    LAUNCH(c, gemm_any(np, np, no, dC, no, 1, dGC, np, 1, dKp, np, -1.0, dKp, 1.0, s));
     LAUNCH(c, launch_diag(np, dKp, np, noise, dvar, s));
     MB_TRY(d2h(pred_cov, dKp, (size_t)np * np * 8, s));
   } else {

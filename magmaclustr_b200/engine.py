@@ -261,6 +261,24 @@ class Context:
     def flush_l2(self, nbytes=256 << 20):
         check(L.lib().mb_flush_l2(self._h, int(nbytes)))
 
+    def matmul(self, a, b, transa=False, transb=False):
+        """R's `%*%` (crossprod / tcrossprod with the flags) on the FP64 tensor cores."""
+        a = np.asfortranarray(a, dtype=np.float64)
+        b = np.asfortranarray(b, dtype=np.float64)
+        m, k = (a.shape[1], a.shape[0]) if transa else a.shape
+        k2, n = (b.shape[1], b.shape[0]) if transb else b.shape
+        assert k == k2
+        out = np.zeros((m, n), order="F")
+        check(L.lib().mb_matmul(self._h, int(transa), int(transb), m, n, k, a.ctypes.data_as(L._dp), a.shape[0],
+                                b.ctypes.data_as(L._dp), b.shape[0], out.ctypes.data_as(L._dp), m))
+        return out
+
+    def bench_dense(self, what, n, reps=3):
+        """Device-only milliseconds per call: what = 0 n^3 product, 1 Cholesky, 2 Cholesky + inverse."""
+        ms = np.zeros(1)
+        check(L.lib().mb_bench_dense(self._h, int(what), int(n), int(reps), ptr(ms)))
+        return float(ms[0])
+
     def hyperposterior(self, k0, hp_0, ki, hp_i, grid_X, grid_index, m_0, pen_diag=1e-10,
                        shared=False):
         gX = f64(np.atleast_2d(np.asarray(grid_X, dtype=np.float64).T).T)
