@@ -34,6 +34,13 @@ int task3_max_ctas_per_sm(int nmax, int D);
 // kernel generation switch: v3 (default) = 4-warp CTAs on packed swizzled tiles, DMMA; MB_TASK_KERNEL=v2
 // selects the 8-warp DMMA version, v1 the first scalar shared-memory version (both kept as
 // independent cross-checks of v3)
+struct BigTaskPool;
+void big_pool_destroy(BigTaskPool* p);
+int big_tasks_objective(BigTaskPool** pp, const TaskObjArgs& a, const int64_t* h_offs, cudaStream_t st, int64_t* launches);
+int big_tasks_slots(BigTaskPool** pp, int nmax, int64_t n_tasks);
+int big_tasks_inverse(BigTaskPool** pp, const TaskInvArgs& a, const int64_t* h_offs, const int64_t* h_inv_offs,
+                      cudaStream_t st, int64_t* launches);
+
 static int task_kernel_version() {
   static int v = -1;
   if (v < 0) {
@@ -198,6 +205,8 @@ struct mb_context {
   size_t prof_used = 0;
   double prof_ms = 0.0;
   int64_t prof_launches = 0, prof_evals = 0;
+  // tasks with more than TK_MAXN points: multi-stream pipelines of the large-matrix kernels (bigtasks.cu)
+  BigTaskPool* big = nullptr;
   // multi-GPU hook
   mb_allreduce_fn ar = nullptr;
   void* ar_user = nullptr;
@@ -210,6 +219,7 @@ struct mb_context {
 // launch of the dominant kernel, optionally bracketed by events (mb_profile)
 static int launch_obj(mb_context* c, const TaskObjArgs& a, int n_launch, cudaStream_t st,
                       bool profiled = false) {
+  if (a.db.nmax > TK_MAXN) return big_tasks_objective(&c->big, a, c->h_offs.data(), st, &c->launches);
   if (!c->prof_on || !profiled) { LAUNCH(c, launch_task_objective_any(a, n_launch, st)); return 0; }
   if (c->prof_used == c->prof_ev.size()) {
     cudaEvent_t e0, e1;
@@ -289,6 +299,7 @@ extern "C" int mb_destroy(mb_context* c) {
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
   c->ws0.release();
   c->ws1.release();
+  big_pool_destroy(c->big);
   if (c->h_pin) cudaFreeHost(c->h_pin);
   if (c->h_pin_i) cudaFreeHost(c->h_pin_i);
   if (c->st) cudaStreamDestroy(c->st);
@@ -543,7 +554,6 @@ extern "C" int mb_upload_dataset(mb_context* c, int64_t n_tasks, const int64_t* 
 static int need_db(mb_context* c, bool need_grid) {
   MB_TRY(check_ctx(c));
   if (!c->have_db) MB_FAIL(-1, "no dataset uploaded (mb_upload_dataset)");
-  if (c->db.nmax > TK_MAXN) MB_FAIL(-4, "a task has more than 96 points: the large-task path is not built yet");
   if (need_grid && (!c->db.gidx || c->U < 1)) MB_FAIL(-1, "dataset was uploaded without a union grid");
   return 0;
 }
@@ -574,7 +584,6 @@ extern "C" int mb_list_kern_to_mat(mb_context* c, const mb_kernel* k, int64_t n_
     size_t end = (size_t)out_offs[t] + (size_t)n * n;
     if (end > total) total = end;
   }
-  if (inverse && nmax > TK_MAXN) MB_FAIL(-4, "a task has more than 96 points: the large-task path is not built yet");
   DevKern kd = make_devkern(k);
   DBuf b_offs, b_X, b_hp, b_oo, b_out, b_ret;
   size_t hp_rows = hp_shared ? 1 : (size_t)n_tasks;
@@ -602,9 +611,16 @@ extern "C" int mb_list_kern_to_mat(mb_context* c, const mb_kernel* k, int64_t n_
     a.db = db; a.kd = kd; a.hp = b_hp.as<double>(); a.hp_stride = hp_shared ? 0 : k->n_hp;
     a.pen = pen_diag; a.K = 1; a.inv_out = b_out.as<double>(); a.inv_offs = b_oo.as<int64_t>();
     a.retries = b_ret.as<int32_t>();
-    int g = c->sm_count * task_ctas_per_sm_any(nmax, d);
-    if (g > n_tasks) g = (int)n_tasks;
-    e = launch_task_inverse_any(a, g, c->st);
+    if (nmax > TK_MAXN) {
+      a.U = 0;
+      int brc = big_tasks_inverse(&c->big, a, offs, out_offs, c->st, &c->launches);
+      if (brc != 0) { cleanup(); return brc; }
+      e = cudaSuccess;
+    } else {
+      int g = c->sm_count * task_ctas_per_sm_any(nmax, d);
+      if (g > n_tasks) g = (int)n_tasks;
+      e = launch_task_inverse_any(a, g, c->st);
+    }
   }
   c->launches++;
   if (e == cudaSuccess) e = cudaMemcpyAsync(out, b_out.p, total * 8, cudaMemcpyDeviceToHost, c->st);
@@ -697,10 +713,17 @@ static int dev_e_step(mb_context* c, int K, const mb_kernel* kern_k, const doubl
     CU(cudaMemcpyAsync(c->inv0.as<double>() + k * UU, c->ws1.A.p, UU * 8, cudaMemcpyDeviceToDevice, c->st2));
   }
   // task inverses + deterministic partial sums
-  int G = c->sm_count * task_ctas_per_sm_any(c->db.nmax, c->db.D);
-  if (G > c->db.n_tasks) G = (int)c->db.n_tasks;
-  const size_t cap = (size_t)2 << 30;
-  while (G > 1 && (size_t)G * K * UU * 8 > cap) G = (G + 1) / 2;
+  const bool big = c->db.nmax > TK_MAXN;
+  int G;
+  if (big) {
+    G = big_tasks_slots(&c->big, c->db.nmax, c->db.n_tasks);
+    if (G < 1) return G < 0 ? G : -2;
+  } else {
+    G = c->sm_count * task_ctas_per_sm_any(c->db.nmax, c->db.D);
+    if (G > c->db.n_tasks) G = (int)c->db.n_tasks;
+    const size_t cap = (size_t)2 << 30;
+    while (G > 1 && (size_t)G * K * UU * 8 > cap) G = (G + 1) / 2;
+  }
   MB_TRY(c->part_inv.ensure((size_t)G * K * UU * 8));
   MB_TRY(c->part_w.ensure((size_t)G * K * U * 8));
   CU(cudaMemsetAsync(c->part_inv.p, 0, (size_t)G * K * UU * 8, c->st));
@@ -712,7 +735,8 @@ static int dev_e_step(mb_context* c, int K, const mb_kernel* kern_k, const doubl
   a.kd = kdi; a.hp = hp_i_dev; a.hp_stride = hp_stride; a.pen = pen; a.K = K; a.tau = tau_dev; a.U = U;
   a.part_inv = c->part_inv.as<double>(); a.part_w = c->part_w.as<double>();
   a.retries = c->retries.as<int32_t>();
-  LAUNCH(c, launch_task_inverse_any(a, G, c->st));
+  if (big) MB_TRY(big_tasks_inverse(&c->big, a, c->h_offs.data(), nullptr, c->st, &c->launches));
+  else LAUNCH(c, launch_task_inverse_any(a, G, c->st));
   CU(cudaStreamSynchronize(c->st2));
   // post_inv_k = inv_k (+) sum_i tau_ik inv_i ; weighted_k = inv_k m_k (+) sum_i tau_ik inv_i y_i
   if (c->world > 1) {
@@ -912,7 +936,6 @@ static int hyperposterior_any(mb_context* c, int K, const mb_kernel* kern_k, con
                               const double* tau, double pen_diag, double* post_mean, double* post_cov) {
   MB_TRY(check_ctx(c));
   if (!c->have_db) MB_FAIL(-1, "no dataset uploaded");
-  if (c->db.nmax > TK_MAXN) MB_FAIL(-4, "a task has more than 96 points: the large-task path is not built yet");
   if (!kern_k || !hp_k || !kern_i || !hp_i || !grid_X || !grid_index || n_grid < 1 || !m_k || !post_mean || !post_cov)
     MB_FAIL(-1, "bad argument");
   if (K < 1 || K > MB_MAX_CLUSTERS || (K > 1 && !tau)) MB_FAIL(-1, "bad cluster count / missing mixture");

@@ -451,7 +451,25 @@ cudaError_t launch_big_lauum(const double* Y, int64_t ldy, double* inv, int64_t 
   return launch_big_gemm(a, 1, 1, st);
 }
 
-// One attempt of chol_inv_jitter with a given total jitter (mode 0) or of the plain Cholesky log-diagonal
+// chol (+ inverse) of the matrix already sitting in W (upper triangle read); total_jitter / retries are only
+// reported.  mode 0: inv = W^{-1}; mode 1: factor + log-diagonal only.  The fail flag must have been cleared.
+cudaError_t launch_big_cholinv_inplace(double* W, double* Y, int64_t ldw, double* inv, int64_t ldi, int n,
+                                       double total_jitter, int retries, int mode, int* fail, int* info, double* out,
+                                       cudaStream_t st, int64_t* launches) {
+  BIG_OK(launch_big_potrf(W, ldw, n, fail, st, launches));
+  k_big_finish<<<1, 1024, 0, st>>>(W, ldw, n, fail, retries, total_jitter, mode, info, out);
+  if (launches) ++*launches;
+  if (mode == 1) return cudaGetLastError();
+  BIG_OK(launch_big_trtri_t(W, ldw, Y, ldw, n, fail, st, launches));
+  BIG_OK(launch_big_lauum(Y, ldw, inv, ldi, n, fail, st, launches));
+  return cudaGetLastError();
+}
+cudaError_t launch_big_clear_flag(int* fail, cudaStream_t st) {
+  k_big_clear_flag<<<1, 1, 0, st>>>(fail);
+  return cudaGetLastError();
+}
+
+// One attempt of chol_inv_jitter with `retries` escalations (mode 0) or of the plain Cholesky log-diagonal
 // (mode 1).  W, Y: n x ldw workspaces (ldw even, >= n); inv: n x n (ld n).  info/out as k_dense_cholinv_sm;
 // info[0] = -1 means "this jitter failed" -- the host escalates and calls again.
 cudaError_t launch_big_cholinv_attempt(const double* src, int64_t ld_src, double* W, double* Y, int64_t ldw, double* inv,
@@ -463,11 +481,5 @@ cudaError_t launch_big_cholinv_attempt(const double* src, int64_t ld_src, double
   if (mode == 0) { double p = pen; for (int r = 0; r <= retries; ++r) { total_jitter += p; p = 10 * p; } }
   k_big_load<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(src, ld_src, W, ldw, n, pen, mode == 0 ? retries : -1);
   if (launches) *launches += 2;
-  BIG_OK(launch_big_potrf(W, ldw, n, fail, st, launches));
-  k_big_finish<<<1, 1024, 0, st>>>(W, ldw, n, fail, retries, total_jitter, mode, info, out);
-  if (launches) ++*launches;
-  if (mode == 1) return cudaGetLastError();
-  BIG_OK(launch_big_trtri_t(W, ldw, Y, ldw, n, fail, st, launches));
-  BIG_OK(launch_big_lauum(Y, ldw, inv, n, n, fail, st, launches));
-  return cudaGetLastError();
+  return launch_big_cholinv_inplace(W, Y, ldw, inv, n, n, total_jitter, retries, mode, fail, info, out, st, launches);
 }

@@ -45,3 +45,7 @@ cudaError_t launch_big_lauum(const double* Y, int64_t ldy, double* inv, int64_t 
 cudaError_t launch_big_cholinv_attempt(const double* src, int64_t ld_src, double* W, double* Y, int64_t ldw, double* inv,
                                        int n, double pen, int retries, int mode, int* fail, int* info, double* out,
                                        cudaStream_t st, int64_t* launches);
+cudaError_t launch_big_cholinv_inplace(double* W, double* Y, int64_t ldw, double* inv, int64_t ldi, int n,
+                                       double total_jitter, int retries, int mode, int* fail, int* info, double* out,
+                                       cudaStream_t st, int64_t* launches);
+cudaError_t launch_big_clear_flag(int* fail, cudaStream_t st);

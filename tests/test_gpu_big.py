@@ -103,3 +103,141 @@ def test_big_cholesky_roundtrip_4096(ctx):
 def test_bench_dense_runs(ctx):
     for what in (0, 1, 2):
         assert ctx.bench_dense(what, 512, reps=1) > 0
+
+
+# ======================================================================================================
+# tasks with more than 96 points (bigtasks.cu): same assertions as test_gpu_magma.py / test_gpu_magmaclust.py
+# ======================================================================================================
+from helpers import make_case, upload, relerr, ulp_perturb  # noqa: E402
+from oracle import magma as OM  # noqa: E402
+from oracle import magmaclust as OC  # noqa: E402
+
+
+def _hp_dict(k, hp):
+    return dict(zip(L.hp_names(k), [float(v) for v in hp]))
+
+
+def test_big_list_kern_to_inv_ragged(ctx):
+    rng = np.random.default_rng(6)
+    sizes = [130, 97, 12, 190]
+    offs = np.r_[0, np.cumsum(sizes)]
+    pool = np.round(np.arange(-1, 1.001, 0.01), 2)
+    X = np.concatenate([np.sort(rng.choice(pool, n, replace=False)) for n in sizes])[:, None]
+    k = L.parse_kernel("SE", True)
+    hp = np.column_stack([rng.uniform(-0.7, 2.3, len(sizes)), rng.uniform(-3, 0, len(sizes)), rng.uniform(-5, -2, len(sizes))])
+    mats, r = ctx.list_kern_to_mat(k, offs, X, hp, inverse=True)
+    for t in range(len(sizes)):
+        xt = X[offs[t]:offs[t + 1]]
+        oinv, oretry = OK.chol_inv_jitter(OK.kern_to_cov(xt, "SE", _hp_dict(k, hp[t])), 1e-10, return_info=True)
+        assert r[t] == oretry
+        assert relerr(mats[t], oinv) < 1e-9          # cond <= 1e5 (noise floor exp(-5))
+        assert np.array_equal(mats[t], mats[t].T)
+
+
+@pytest.mark.parametrize("M,N,seed,common", [(4, 128, 3, False), (3, 150, 11, True), (3, 97, 5, False)])
+def test_big_task_objective_and_gradient(ctx, M, N, seed, common):
+    case = make_case(M, N, seed, common_input=common)
+    upload(ctx, case)
+    odb = case["odb"]
+    pm, pc = OM.e_step(odb, 0.0, "SE", "SE", case["o_hp0"], case["o_hpi"], 1e-10)
+    f, g, r = ctx.logL_GP_mod_tasks(case["ki"], case["hpi"], pm, pc)
+    for t, i in enumerate(case["prep"].ids):
+        Xi, yi, mi, Si = OM._task_views(odb, pm, pc, i)
+        of = OM.logL_GP_mod(case["o_hpi"][i], Xi, yi, mi, "SE", Si, 1e-10)
+        og = OM.gr_GP_mod(case["o_hpi"][i], Xi, yi, mi, "SE", Si, 1e-10)
+        assert abs(f[t] - of) <= 1e-9 * abs(of)
+        np.testing.assert_allclose(g[t], og, rtol=1e-8, atol=1e-9 * np.max(np.abs(og)))
+        assert r[t] == 0
+
+
+def test_big_task_compound_kernel_gradient(ctx):
+    case = make_case(3, 110, 8, kern_i="SE + PERIO")
+    upload(ctx, case)
+    odb = case["odb"]
+    pm, pc = OM.e_step(odb, 0.0, "SE", "SE + PERIO", case["o_hp0"], case["o_hpi"], 1e-10)
+    f, g, r = ctx.logL_GP_mod_tasks(case["ki"], case["hpi"], pm, pc)
+    for t, i in enumerate(case["prep"].ids):
+        Xi, yi, mi, Si = OM._task_views(odb, pm, pc, i)
+        of = OM.logL_GP_mod(case["o_hpi"][i], Xi, yi, mi, "SE + PERIO", Si, 1e-10)
+        og = OM.gr_GP_mod(case["o_hpi"][i], Xi, yi, mi, "SE + PERIO", Si, 1e-10)
+        assert abs(f[t] - of) <= 1e-9 * abs(of)
+        np.testing.assert_allclose(g[t], og, rtol=1e-8, atol=1e-9 * np.max(np.abs(og)))
+
+
+def test_big_e_step(ctx):
+    case = make_case(5, 120, 7)
+    upload(ctx, case)
+    pm, pc, info = ctx.e_step(case["k0"], case["hp0"], case["ki"], case["hpi"], np.zeros(ctx.U))
+    opm, opc, oinfo = OM.e_step(case["odb"], 0.0, "SE", "SE", case["o_hp0"], case["o_hpi"], 1e-10, return_info=True)
+    assert info[0] == oinfo["inv_0"] and info[1] == oinfo["post"] and info[2] == max(oinfo["tasks"].values())
+    rng = np.random.default_rng(0)
+    sens_c = sens_m = 0.0
+    for _ in range(3):   # measured sensitivity of the oracle to a one-ulp change of the HPs (cond(K_0) ~ 1e12)
+        h0 = dict(zip(case["names_0"], ulp_perturb(case["hp0"], rng)))
+        hi = {i: dict(zip(case["names_i"], ulp_perturb(case["hpi"][t], rng))) for t, i in enumerate(case["prep"].ids)}
+        ppm, ppc = OM.e_step(case["odb"], 0.0, "SE", "SE", h0, hi, 1e-10)
+        sens_c, sens_m = max(sens_c, relerr(ppc, opc)), max(sens_m, relerr(ppm, opm))
+    assert relerr(pc, opc) < 30 * sens_c + 1e-12
+    assert relerr(pm, opm) < 30 * sens_m + 1e-12
+    assert np.array_equal(pc, pc.T)
+
+
+def test_big_m_step_matches_oracle(ctx):
+    case = make_case(3, 100, 21)
+    upload(ctx, case)
+    odb = case["odb"]
+    pm, pc = OM.e_step(odb, 0.0, "SE", "SE", case["o_hp0"], case["o_hpi"], 1e-10)
+    stats = {}
+    o0, oi = OM.m_step(odb, 0.0, "SE", "SE", case["o_hp0"], case["o_hpi"], pm, pc, False, 1e-10, stats)
+    h0, hi, st = ctx.m_step(case["k0"], case["hp0"], case["ki"], case["hpi"], np.zeros(ctx.U), pm, pc)
+    conv, nev = ctx.last_task_status()
+    # identical optimiser trajectories task by task (evaluation counts and convergence codes), HPs to 1e-6
+    assert [int(v) for v in nev] == [stats["tasks"][i]["counts"] for i in case["prep"].ids]
+    assert [int(v) for v in conv] == [stats["tasks"][i]["convergence"] for i in case["prep"].ids]
+    for t, i in enumerate(case["prep"].ids):
+        np.testing.assert_allclose(hi[t], [oi[i][n] for n in case["names_i"]], rtol=1e-6, atol=1e-7)
+    ll = ctx.logL_monitoring(case["k0"], h0, case["ki"], hi, np.zeros(ctx.U), pm, pc)
+    oll = OM.logL_monitoring(dict(zip(case["names_0"], h0)), {i: dict(zip(case["names_i"], hi[t])) for t, i in enumerate(case["prep"].ids)},
+                             odb, 0.0, "SE", "SE", pm, pc, 1e-10)
+    rng = np.random.default_rng(2)
+    f0 = OM.logL_GP_mod(dict(zip(case["names_0"], h0)), odb.grid_X, pm, 0.0, "SE", pc, 1e-10)
+    sf = max(abs(OM.logL_GP_mod(dict(zip(case["names_0"], ulp_perturb(h0, rng))), odb.grid_X, pm, 0.0, "SE", pc, 1e-10) - f0)
+             for _ in range(4))
+    assert abs(ll - oll) < 30 * sf + 1e-9 * abs(oll)
+
+
+def test_big_elbo_and_mixture(ctx):
+    KC = 3
+    case = make_case(4, 105, 4, shared=True, K=KC)
+    upload(ctx, case)
+    rng = np.random.default_rng(4)
+    M = 4
+    lab = rng.integers(0, KC, size=M)
+    mix = np.zeros((M, KC))
+    mix[np.arange(M), lab] = 1.0
+    hp_k = np.array([[1.0 + 0.3 * k, -1.5 - 0.2 * k] for k in range(KC)])
+    o_hp_k = [dict(zip(case["names_0"], hp_k[k])) for k in range(KC)]
+    U = case["odb"].grid_X.shape[0]
+    omean, ocov, _ = OC.ve_step(case["odb"], [np.zeros(U)] * KC, "SE", "SE", o_hp_k, case["o_hpi"], mix, 1, 1e-10, None)
+    soft = np.round(0.8 * mix + 0.2 / KC, 5)
+    f, g = ctx.elbo_clust_tasks(KC, case["ki"], case["hpi"], np.array(omean), np.array(ocov), soft)
+    for t, i in enumerate(case["prep"].ids):
+        of = OC.elbo_clust_multi_GP(case["o_hpi"][i], case["odb"], i, t, omean, ocov, soft, "SE", 1e-10)
+        og = OC.gr_clust_multi_GP(case["o_hpi"][i], case["odb"], i, t, omean, ocov, soft, "SE", 1e-10)
+        assert abs(f[t] - of) <= 1e-9 * abs(of)
+        np.testing.assert_allclose(g[t], og, rtol=1e-8, atol=1e-9 * np.max(np.abs(og)))
+    prop = mix.mean(axis=0)
+    otau = OC.update_mixture(case["odb"], omean, ocov, case["o_hpi"], "SE", prop, 1e-10)
+    gtau = ctx.update_mixture(KC, case["ki"], case["hpi"], np.array(omean), np.array(ocov), prop)
+    assert np.array_equal(np.argmax(gtau, axis=1), np.argmax(otau, axis=1))
+    assert np.max(np.abs(gtau - otau)) <= 1e-5 + 1e-12
+    # VE step through the large-task inverse path
+    pm, pc, tau = ctx.ve_step(KC, case["k0"], hp_k, case["ki"], case["hpi"], np.zeros((KC, U)), mix)
+    for k in range(KC):
+        sens = 0.0
+        for _ in range(3):
+            hk = [dict(zip(case["names_0"], ulp_perturb(hp_k[q], rng))) for q in range(KC)]
+            pmean, pcov, _ = OC.ve_step(case["odb"], [np.zeros(U)] * KC, "SE", "SE", hk, case["o_hpi"], mix, 1, 1e-10, None)
+            sens = max(sens, relerr(pcov[k], ocov[k]), relerr(pmean[k], omean[k]))
+        assert relerr(pc[k], ocov[k]) < 30 * sens + 1e-12
+        assert relerr(pm[k], omean[k]) < 30 * sens + 1e-12
