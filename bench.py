@@ -304,7 +304,9 @@ def main():
                      "algorithmic_flops_per_eval": FLOPS_PER_EVAL * N_POINTS ** 3,
                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (no FP64 figure in MEASURED_PEAKS.json)",
                      "kernel_ms_per_step": prof["ms"] / args.steps,
-                     "kernel_share_of_step": prof["ms"] / float(np.sum(ms))},
+                     "kernel_share_of_step": prof["ms"] / float(np.sum(ms)),
+                     "round_overhead_ms_per_step": prof["round_gap_ms"] / args.steps,
+                     "e_step_and_monitoring_ms_per_step": prof["other_ms"] / args.steps},
     }
     if fit:
         line["fit"] = fit

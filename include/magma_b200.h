@@ -250,6 +250,9 @@ int mb_timer_ms(mb_context*, double* ms);
  * out[2] = task evaluations (active CTAs) since the last read, and resets the counters. */
 int mb_profile(mb_context*, int enable);
 int mb_profile_read(mb_context*, double* out3);
+/* Call BEFORE mb_profile_read: out2[0] = stream milliseconds between consecutive profiled launches inside the
+ * lock-step M step (optimiser advance kernel + host round trip), out2[1] = the longer gaps (E step, monitoring). */
+int mb_profile_read_gaps(mb_context*, double* out2);
 /* Write `bytes` of device memory (L2 flush between timed iterations). */
 int mb_flush_l2(mb_context*, int64_t bytes);
 

@@ -200,10 +200,11 @@ struct mb_context {
   bool have_state = false;
   // timing / profiling
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t ev_ring[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool prof_on = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
   size_t prof_used = 0;
-  double prof_ms = 0.0;
+  double prof_ms = 0.0, prof_gap_ms = 0.0, prof_other_ms = 0.0;
   int64_t prof_launches = 0, prof_evals = 0;
   // tasks with more than TK_MAXN points: multi-stream pipelines of the large-matrix kernels (bigtasks.cu)
   BigTaskPool* big = nullptr;
@@ -240,6 +241,13 @@ static int prof_collect(mb_context* c) {
     CU(cudaEventElapsedTime(&ms, c->prof_ev[i].first, c->prof_ev[i].second));
     c->prof_ms += ms;
     c->prof_launches++;
+    if (i + 1 < c->prof_used) {   // stream time between two profiled launches: advance kernel + host round trip
+      float gap = 0;
+      CU(cudaEventSynchronize(c->prof_ev[i + 1].first));
+      CU(cudaEventElapsedTime(&gap, c->prof_ev[i].second, c->prof_ev[i + 1].first));
+      if (gap < 5.0f) c->prof_gap_ms += gap;   // longer gaps are step boundaries (E step, monitoring)
+      else c->prof_other_ms += gap;
+    }
   }
   c->prof_used = 0;
   return 0;
@@ -297,6 +305,7 @@ extern "C" int mb_destroy(mb_context* c) {
   for (auto& ev : c->prof_ev) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+  for (int i = 0; i < 8; ++i) if (c->ev_ring[i]) cudaEventDestroy(c->ev_ring[i]);
   c->ws0.release();
   c->ws1.release();
   big_pool_destroy(c->big);
@@ -857,12 +866,21 @@ static int optimise(mb_context* c, std::vector<SingleProblem>& singles, bool tas
     a.want_grad = 1;
   }
   size_t cur = 0;  // singles are optimised one after the other (they share ws0)
+  // The host runs LB_LAG round(s) ahead of the device: round r + LB_LAG is enqueued before the active count of
+  // round r is read, so the stream never drains between rounds.  The price is LB_LAG empty rounds at the end
+  // (every CTA / thread sees an inactive problem and returns).
+  const int LB_LAG = 1, RING = 8;
+  int enq = 0;          // rounds enqueued
+  for (int i = 0; i < RING; ++i)
+    if (!c->ev_ring[i]) CU(cudaEventCreateWithFlags(&c->ev_ring[i], cudaEventDisableTiming));
   while (tasks_active || cur < singles.size()) {
     if (tasks_active) {
-      if (rounds >= 4095) MB_FAIL(2, "L-BFGS-B lock-step did not terminate");
+      if (enq >= 4095) MB_FAIL(2, "L-BFGS-B lock-step did not terminate");
       MB_TRY(launch_obj(c, a, (int)M, c->st, true));
-      LAUNCH(c, launch_lbfgsb_advance(c->lb.as<LbfgsbState>(), M, P_i, a.f, a.g, c->counters.as<int>() + rounds, c->st));
-      MB_TRY(d2h(c->h_pin_i, c->counters.as<int>() + rounds, sizeof(int), c->st));
+      LAUNCH(c, launch_lbfgsb_advance(c->lb.as<LbfgsbState>(), M, P_i, a.f, a.g, c->counters.as<int>() + enq, c->st));
+      MB_TRY(d2h(c->h_pin_i + 64 + (enq % RING), c->counters.as<int>() + enq, sizeof(int), c->st));
+      CU(cudaEventRecord(c->ev_ring[enq % RING], c->st));
+      enq++;
     }
     if (cur < singles.size()) {
       SingleProblem& sp = singles[cur];
@@ -874,10 +892,10 @@ static int optimise(mb_context* c, std::vector<SingleProblem>& singles, bool tas
         if (!sp.s.active) cur++;
       }
     }
-    if (tasks_active) {
-      CU(cudaStreamSynchronize(c->st));
-      rounds++;
-      if (c->h_pin_i[0] == 0) tasks_active = false;
+    if (tasks_active && enq > LB_LAG) {
+      const int r = enq - 1 - LB_LAG;
+      CU(cudaEventSynchronize(c->ev_ring[r % RING]));
+      if (c->h_pin_i[64 + (r % RING)] == 0) { tasks_active = false; rounds = r + 1; }
     }
   }
   if (tasks_on) {
@@ -1300,6 +1318,13 @@ extern "C" int mb_profile_read(mb_context* c, double* out3) {
   MB_TRY(prof_collect(c));
   out3[0] = c->prof_ms; out3[1] = (double)c->prof_launches; out3[2] = (double)c->prof_evals;
   c->prof_ms = 0; c->prof_launches = 0; c->prof_evals = 0;
+  return 0;
+}
+extern "C" int mb_profile_read_gaps(mb_context* c, double* out2) {
+  MB_TRY(check_ctx(c));
+  MB_TRY(prof_collect(c));
+  out2[0] = c->prof_gap_ms; out2[1] = c->prof_other_ms;
+  c->prof_gap_ms = 0; c->prof_other_ms = 0;
   return 0;
 }
 extern "C" int mb_flush_l2(mb_context* c, int64_t bytes) {

@@ -18,44 +18,61 @@ __global__ void k_lbfgsb_init(LbfgsbState* st, int64_t m, int n, const double* x
 }
 
 // Feed (f[t], g[t,:]) to every still-active problem; n_active[0] += problems still active.
-// One warp per 32 problems.  The 2192-byte states of the ACTIVE problems are staged through shared memory
-// with warp-cooperative, fully coalesced 16-byte copies (a padded stride of 275 doubles keeps the per-thread
-// accesses of the state machine bank-conflict free); inactive problems cost one 4-byte read.
+// One CTA of 8 warps per 32 problems.  The 2192-byte states of the ACTIVE problems are staged through shared
+// memory by all 8 warps (each warp moves 4 states, nine independent coalesced loads in flight per lane -- a
+// single warp moving 32 states one after the other spent ~60 us waiting on HBM), then warp 0 advances one
+// problem per lane on its staged copy (padded stride of 275 doubles: bank-conflict free), then all warps
+// write the states back.  Inactive problems cost one 4-byte read.
 #define LB_STRIDE_D 275   /* doubles per staged state: 274 + 1 pad (odd => conflict-free half-warps) */
-__global__ void __launch_bounds__(32) k_lbfgsb_advance(LbfgsbState* st, int64_t m, int n, const double* f,
-                                                      const double* g, int* n_active) {
+#define LB_ADV_THREADS 256
+__global__ void __launch_bounds__(LB_ADV_THREADS) k_lbfgsb_advance(LbfgsbState* st, int64_t m, int n, const double* f,
+                                                                   const double* g, int* n_active) {
   extern __shared__ double lb_smem[];
+  __shared__ int act[32];
   static_assert(sizeof(LbfgsbState) == 274 * 8, "LbfgsbState layout changed: update LB_STRIDE_D");
-  const int lane = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t t0 = (int64_t)blockIdx.x * 32;
-  const int64_t t = t0 + lane;
-  const bool mine = t < m && st[t].active;
-  const unsigned act = __ballot_sync(0xffffffffu, mine);
-  if (act == 0) return;
-  for (int q = 0; q < 32; ++q) {
-    if (!((act >> q) & 1u)) continue;
+  if (tid < 32) act[tid] = (t0 + tid < m) ? st[t0 + tid].active : 0;
+  __syncthreads();
+  unsigned any = 0;
+  for (int q = 0; q < 32; ++q) any |= (unsigned)act[q];
+  if (!any) return;
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    const int q = warp + 8 * h;
+    if (!act[q]) continue;
     const double* src = reinterpret_cast<const double*>(&st[t0 + q]);
     double* dst = lb_smem + (size_t)q * LB_STRIDE_D;
-    for (int i = lane; i < 274; i += 32) dst[i] = src[i];
+    double v[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { const int e = lane + 32 * i; v[i] = (e < 274) ? src[e] : 0.0; }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { const int e = lane + 32 * i; if (e < 274) dst[e] = v[i]; }
   }
-  __syncwarp();
-  int still = 0;
-  if (mine) {
-    LbfgsbState* s = reinterpret_cast<LbfgsbState*>(lb_smem + (size_t)lane * LB_STRIDE_D);
-    double gl[LB_NP];
-    for (int p = 0; p < n; ++p) gl[p] = g[t * n + p];
-    lb_advance(s, f[t], gl);
-    still = s->active;
+  __syncthreads();
+  if (warp == 0) {
+    int still = 0;
+    if (act[lane]) {
+      const int64_t t = t0 + lane;
+      LbfgsbState* s = reinterpret_cast<LbfgsbState*>(lb_smem + (size_t)lane * LB_STRIDE_D);
+      double gl[LB_NP];
+      for (int p = 0; p < n; ++p) gl[p] = g[t * n + p];
+      lb_advance(s, f[t], gl);
+      still = s->active;
+    }
+    const unsigned alive = __ballot_sync(0xffffffffu, still != 0);
+    if (lane == 0 && alive) atomicAdd(n_active, __popc(alive));
   }
-  __syncwarp();
-  for (int q = 0; q < 32; ++q) {
-    if (!((act >> q) & 1u)) continue;
+  __syncthreads();
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    const int q = warp + 8 * h;
+    if (!act[q]) continue;
     double* dst = reinterpret_cast<double*>(&st[t0 + q]);
     const double* src = lb_smem + (size_t)q * LB_STRIDE_D;
-    for (int i = lane; i < 274; i += 32) dst[i] = src[i];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { const int e = lane + 32 * i; if (e < 274) dst[e] = src[e]; }
   }
-  const unsigned alive = __ballot_sync(0xffffffffu, still != 0);
-  if (lane == 0 && alive) atomicAdd(n_active, __popc(alive));
 }
 
 // x -> HP table; fail codes and evaluation counts out.
@@ -85,7 +102,7 @@ cudaError_t launch_lbfgsb_advance(LbfgsbState* st, int64_t m, int n, const doubl
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  k_lbfgsb_advance<<<(unsigned)((m + 31) / 32), 32, smem, s>>>(st, m, n, f, g, n_active);
+  k_lbfgsb_advance<<<(unsigned)((m + 31) / 32), LB_ADV_THREADS, smem, s>>>(st, m, n, f, g, n_active);
   return cudaGetLastError();
 }
 

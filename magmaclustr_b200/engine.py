@@ -254,9 +254,12 @@ class Context:
         check(L.lib().mb_profile(self._h, 1 if enable else 0))
 
     def profile_read(self):
+        gaps = np.zeros(2)
+        check(L.lib().mb_profile_read_gaps(self._h, ptr(gaps)))
         out = np.zeros(3)
         check(L.lib().mb_profile_read(self._h, ptr(out)))
-        return {"ms": out[0], "launches": int(out[1]), "evals": int(out[2])}
+        return {"ms": out[0], "launches": int(out[1]), "evals": int(out[2]), "round_gap_ms": gaps[0],
+                "other_ms": gaps[1]}
 
     def flush_l2(self, nbytes=256 << 20):
         check(L.lib().mb_flush_l2(self._h, int(nbytes)))
