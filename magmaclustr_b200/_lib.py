@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmagma_b200.so")
+LIB_PATH = os.environ.get("MB_LIB") or os.path.join(_HERE, "lib", "libmagma_b200.so")
 
 MB_MAX_TERMS = 4
 MB_MAX_HP = 12

@@ -20,6 +20,19 @@ def _newer(src_list, target):
     return any(os.path.getmtime(s) > t for s in src_list)
 
 
+def build_timing():
+    """Diagnostic variant: libmagma_b200_timing.so with per-phase clock64() marks in the per-task kernels
+    (-DT3_TIMING).  Loaded instead of the product library when MB_LIB points at it (scripts/phase_timing.py)."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    build()
+    obj = os.path.join(LIBDIR, "tasks3_timing.o")
+    subprocess.check_call([nvcc] + ARCH + COMMON + ["-DT3_TIMING", "-c", os.path.join(CSRC, "tasks3.cu"), "-o", obj])
+    objs = [obj if name == "tasks3.cu" else os.path.join(LIBDIR, name.replace(".cu", ".o")) for name, _ in UNITS]
+    out = os.path.join(LIBDIR, "libmagma_b200_timing.so")
+    subprocess.check_call([nvcc] + ARCH + ["-shared", "-o", out] + objs + ["-lcudart_static", "-ldl", "-lrt", "-lpthread"])
+    return out
+
+
 def build(verbose=False, force=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(LIBDIR, exist_ok=True)

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(DSM_THREADS, 1) k_dense_cholinv_sm(const doubl
       s.T1[(size_t)(d3_tri(ti, n8) + tj - ti) * 64 + sw(i & 7, j & 7)] = v;
     }
     __syncthreads();
-    const int f = d3_chol(s, n8, L);
+    const int f = d3_chol<NWS>(s, n8, L);
     if (f == 0) break;
     __syncthreads();
     if (mode == 1) { if (threadIdx.x == 0) { info[0] = f; out[0] = NAN; } return; }
@@ -76,8 +76,8 @@ __global__ void __launch_bounds__(DSM_THREADS, 1) k_dense_cholinv_sm(const doubl
     }
   }
   if (mode == 1) return;
-  d3_trtri(s, n8, L);
-  d3_lauum(s, n8, L);
+  d3_trtri<NWS, 2>(s, n8, L);
+  d3_lauum<NWS, 2>(s, n8, L);
   for (int e = threadIdx.x; e < n * n; e += DSM_THREADS) {
     const int r = e / n, c = e - r * n;
     const int i = r >> 3, j = c >> 3;

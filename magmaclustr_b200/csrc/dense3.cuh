@@ -43,11 +43,16 @@ __device__ __forceinline__ void d3_update_tile(double* T1, int idx, int e, int k
 
 // blocked upper Cholesky in place; every panel tile is a substitution solve with the factored diagonal
 // tile (no explicit inverse anywhere in the factorisation).  0 or failing pivot code.
-__device__ inline int d3_chol(const SmD& s, int n8, const Ln& L) {
+template <int NW>
+__device__ inline int d3_chol(const SmD& s, int n8, const Ln& L, int rot = 0) {
+  // `rot` rotates the roles of the warps: the panel warp (virtual warp 0) of co-resident CTAs then sits on
+  // different SM sub-partitions instead of all serial pivot chains sharing sub-partition 0
+  static_assert((NW & (NW - 1)) == 0, "NW must be a power of two");
+  const int vw = (L.warp + rot) & (NW - 1);
   const int ntri = n8 * (n8 + 1) / 2;
   if (threadIdx.x == 0) *s.flag = 0;
   __syncthreads();
-  if (L.warp == 0) {
+  if (vw == 0) {
     const int f = warp_factor_panel(s.T1, n8 < 4 ? n8 : 4, s.rinv, L.lane);
     if (f && L.lane == 0) *s.flag = f;
   }
@@ -57,14 +62,14 @@ __device__ inline int d3_chol(const SmD& s, int n8, const Ln& L) {
     const int dk = d3_tri(k, n8);
     if (k + 4 < n8) {
       // remaining panel tiles R_kj = R_kk^{-T} A_kj, four tiles per warp
-      for (int j = k + 4 + 4 * L.warp; j < n8; j += 4 * NWS)
+      for (int j = k + 4 + 4 * vw; j < n8; j += 4 * NW)
         warp_panel_solve(s.T1 + (size_t)dk * 64, s.rinv + 8 * k, s.T1 + (size_t)(dk + j - k) * 64,
                          (n8 - j) < 4 ? (n8 - j) : 4, L.lane);
       __syncthreads();
     }
     const int m = n8 - k - 1, nla = m < 4 ? m : 4;
     const int j0 = d3_tri(k + 1, n8);
-    if (L.warp == 0) {
+    if (vw == 0) {
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         if (q < nla) d3_update_tile(s.T1, j0 + q, s.tab[j0 + q], k, dk, L);
@@ -72,7 +77,7 @@ __device__ inline int d3_chol(const SmD& s, int n8, const Ln& L) {
       const int f = warp_factor_panel(s.T1 + (size_t)j0 * 64, nla, s.rinv + 8 * (k + 1), L.lane);
       if (f && L.lane == 0) *s.flag = 8 * (k + 1) + f;
     } else {
-      for (int idx = j0 + nla + L.warp - 1; idx < ntri; idx += NWS - 1) d3_update_tile(s.T1, idx, s.tab[idx], k, dk, L);
+      for (int idx = j0 + nla + vw - 1; idx < ntri; idx += NW - 1) d3_update_tile(s.T1, idx, s.tab[idx], k, dk, L);
     }
     __syncthreads();
     if (*s.flag) return *s.flag;
@@ -84,16 +89,17 @@ __device__ inline int d3_chol(const SmD& s, int n8, const Ln& L) {
 //   W_ij = -sum_{i<m<=j} R_im X_mj  (DMMA, held in registers until every read of row i is done),
 //   X_ij = R_ii^{-1} W_ij           (back substitution with the diagonal tile, like dtrsm);
 // finally the diagonal tiles X_ii are copied in.
+template <int NW, int HT>
 __device__ inline void d3_trtri(const SmD& s, int n8, const Ln& L) {
-  for (int k = L.warp; k < n8; k += NWS)
+  for (int k = L.warp; k < n8; k += NW)
     warp_diag_inverse(s.T1 + (size_t)d3_tri(k, n8) * 64, s.rinv + 8 * k, s.Xd + (size_t)k * 64, L.lane);
   __syncthreads();
   for (int i = n8 - 2; i >= 0; --i) {
     double* Ti = s.T1 + (size_t)(d3_tri(i, n8) - i) * 64;   // tile (i, m) at Ti + m * 64
-    double res[2][2];
+    double res[HT][2];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int j = i + 1 + L.warp + h * NWS;
+    for (int h = 0; h < HT; ++h) {
+      const int j = i + 1 + L.warp + h * NW;
       double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
       if (j < n8) {
         int m = i + 1;
@@ -122,27 +128,28 @@ __device__ inline void d3_trtri(const SmD& s, int n8, const Ln& L) {
     }
     __syncthreads();
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int j = i + 1 + L.warp + h * NWS;
+    for (int h = 0; h < HT; ++h) {
+      const int j = i + 1 + L.warp + h * NW;
       if (j < n8) *reinterpret_cast<double2*>(Ti + (size_t)j * 64 + L.o_c) = make_double2(res[h][0], res[h][1]);
     }
     __syncthreads();
-    for (int j = i + 1 + 4 * L.warp; j < n8; j += 4 * NWS)
+    for (int j = i + 1 + 4 * L.warp; j < n8; j += 4 * NW)
       warp_row_backsolve(Ti + (size_t)i * 64, s.rinv + 8 * i, Ti + (size_t)j * 64, (n8 - j) < 4 ? (n8 - j) : 4, L.lane);
     __syncthreads();
   }
-  for (int e = threadIdx.x; e < n8 * 64; e += DSM_THREADS) s.T1[(size_t)d3_tri(e >> 6, n8) * 64 + (e & 63)] = s.Xd[e];
+  for (int e = threadIdx.x; e < n8 * 64; e += (32 * NW)) s.T1[(size_t)d3_tri(e >> 6, n8) * 64 + (e & 63)] = s.Xd[e];
   __syncthreads();
 }
 
 // in place A = X X' (upper tiles), rows top-down; diagonal tiles mirrored afterwards
+template <int NW, int HT>
 __device__ inline void d3_lauum(const SmD& s, int n8, const Ln& L) {
   for (int i = 0; i < n8; ++i) {
     const double* Ti = s.T1 + (size_t)(d3_tri(i, n8) - i) * 64;
-    double res[2][2];
+    double res[HT][2];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int j = i + L.warp + h * NWS;
+    for (int h = 0; h < HT; ++h) {
+      const int j = i + L.warp + h * NW;
       double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
       if (j < n8) {
         const double* Tj = s.T1 + (size_t)(d3_tri(j, n8) - j) * 64;
@@ -171,13 +178,13 @@ __device__ inline void d3_lauum(const SmD& s, int n8, const Ln& L) {
     }
     __syncthreads();
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int j = i + L.warp + h * NWS;
+    for (int h = 0; h < HT; ++h) {
+      const int j = i + L.warp + h * NW;
       if (j < n8) *reinterpret_cast<double2*>(const_cast<double*>(Ti) + (size_t)j * 64 + L.o_c) = make_double2(res[h][0], res[h][1]);
     }
     __syncthreads();
   }
-  for (int e = threadIdx.x; e < n8 * 64; e += DSM_THREADS) {
+  for (int e = threadIdx.x; e < n8 * 64; e += (32 * NW)) {
     const int k = e >> 6, r = (e >> 3) & 7, c = e & 7;
     double* Tk = s.T1 + (size_t)d3_tri(k, n8) * 64;
     if (r > c) Tk[sw(r, c)] = Tk[sw(c, r)];

@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(DSM_THREADS, 1) k_big_potrf_diag(double* W, in
     s.T1[(size_t)(d3_tri(ti, n8) + tj - ti) * 64 + sw(i & 7, j & 7)] = v;
   }
   __syncthreads();
-  const int f = d3_chol(s, n8, L);
+  const int f = d3_chol<NWS>(s, n8, L);
   if (f) { if (threadIdx.x == 0) *fail = k + f; return; }
   for (int e = threadIdx.x; e < np * np; e += DSM_THREADS) {
     const int i = e / np, j = e - i * np;

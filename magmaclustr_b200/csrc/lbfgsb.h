@@ -40,18 +40,31 @@ struct LbfgsbState {
 
 #define LB_EPS 2.220446049250313e-16
 
+// Loops whose bounds are template constants in the device specialisations (n = number of HPs, col = stored
+// corrections) are fully unrolled there, so the small work arrays live in registers; the arithmetic and its
+// order are those of the generic code.
+#ifdef __CUDA_ARCH__
+#define LB_UNROLL _Pragma("unroll")
+#else
+#define LB_UNROLL
+#endif
+
 MB_HD double lb_ddot(int n, const double* a, const double* b) {
   double s = 0.0;
+  LB_UNROLL
   for (int i = 0; i < n; ++i) s += a[i] * b[i];
   return s;
 }
 
 // LINPACK dpofa on the leading n x n upper triangle of a (row stride lda).
 MB_HD int lb_dpofa(double* a, int lda, int n) {
+  LB_UNROLL
   for (int j = 0; j < n; ++j) {
     double s = 0.0;
+    LB_UNROLL
     for (int k = 0; k < j; ++k) {
       double t = a[k * lda + j];
+      LB_UNROLL
       for (int i = 0; i < k; ++i) t -= a[i * lda + k] * a[i * lda + j];
       t = t / a[k * lda + k];
       a[k * lda + j] = t;
@@ -67,20 +80,25 @@ MB_HD int lb_dpofa(double* a, int lda, int n) {
 // LINPACK dtrsl with t upper triangular: trans = 0 solves t x = b (job 01), trans = 1
 // solves t' x = b (job 11).  b has stride bs.
 MB_HD int lb_dtrsl(const double* t, int ldt, int n, double* b, int bs, int trans) {
+  LB_UNROLL
   for (int j = 0; j < n; ++j)
     if (t[j * ldt + j] == 0.0) return j + 1;
   if (!trans) {
     b[(n - 1) * bs] = b[(n - 1) * bs] / t[(n - 1) * ldt + (n - 1)];
+    LB_UNROLL
     for (int jj = 2; jj <= n; ++jj) {
       int j = n - jj;
       double temp = -b[(j + 1) * bs];
+      LB_UNROLL
       for (int i = 0; i <= j; ++i) b[i * bs] += temp * t[i * ldt + (j + 1)];
       b[j * bs] = b[j * bs] / t[j * ldt + j];
     }
   } else {
     b[0] = b[0] / t[0];
+    LB_UNROLL
     for (int j = 1; j < n; ++j) {
       double s = 0.0;
+      LB_UNROLL
       for (int i = 0; i < j; ++i) s += t[i * ldt + j] * b[i * bs];
       b[j * bs] = b[j * bs] - s;
       b[j * bs] = b[j * bs] / t[j * ldt + j];
@@ -262,6 +280,101 @@ MB_HD void lb_init(LbfgsbState* s, int n, const double* x0, double factr, double
   lb_reset_memory(s);
 }
 
+// The col > 0 branch of the search direction (formk + cmprlb + subsm of mainlb without bounds): z from the
+// compact L-BFGS matrices.  NT / CT > 0 fix n / col at compile time.  Returns 1 when a factorisation fails
+// (the caller resets the memory and starts over).
+template <int NT, int CT>
+MB_HD int lb_sd_core(LbfgsbState* s) {
+  const int n = NT > 0 ? NT : s->n;
+  const int col = CT > 0 ? CT : s->col, m2 = 2 * col;
+  const double theta = s->theta;
+  double wn[2 * LB_M * 2 * LB_M];
+  const int ld = 2 * LB_M;
+  LB_UNROLL
+  for (int i = 0; i < m2; ++i) {
+    LB_UNROLL
+    for (int j = 0; j < m2; ++j) wn[i * ld + j] = 0.0;
+  }
+  LB_UNROLL
+  for (int iy = 0; iy < col; ++iy) {
+    LB_UNROLL
+    for (int jy = 0; jy <= iy; ++jy)
+      wn[jy * ld + iy] = lb_ddot(n, s->wy[iy], s->wy[jy]) / theta;
+    LB_UNROLL
+    for (int jy = iy; jy < col; ++jy)
+      wn[jy * ld + col + iy] = lb_ddot(n, s->ws[iy], s->wy[jy]);
+    wn[iy * ld + iy] += s->sy[iy][iy];
+  }
+  int info = lb_dpofa(wn, ld, col);
+  if (info == 0) {
+    LB_UNROLL
+    for (int js = col; js < m2; ++js) lb_dtrsl(wn, ld, col, &wn[js], ld, 1);
+    LB_UNROLL
+    for (int is = col; is < m2; ++is) {
+      LB_UNROLL
+      for (int js = is; js < m2; ++js) {
+        double sum = 0.0;
+        LB_UNROLL
+        for (int k = 0; k < col; ++k) sum += wn[k * ld + is] * wn[k * ld + js];
+        wn[is * ld + js] += sum;
+      }
+    }
+    info = lb_dpofa(&wn[col * ld + col], ld, col);
+  }
+  if (info != 0) return 1;
+  double r[LB_NP], wv[2 * LB_M];
+  LB_UNROLL
+  for (int i = 0; i < n; ++i) r[i] = -s->g[i];
+  LB_UNROLL
+  for (int i = 0; i < col; ++i) {
+    double t1 = 0.0, t2 = 0.0;
+    LB_UNROLL
+    for (int k = 0; k < n; ++k) {
+      t1 += s->wy[i][k] * r[k];
+      t2 += s->ws[i][k] * r[k];
+    }
+    wv[i] = t1;
+    wv[col + i] = theta * t2;
+  }
+  info = lb_dtrsl(wn, ld, m2, wv, 1, 1);
+  if (info == 0) {
+    LB_UNROLL
+    for (int i = 0; i < col; ++i) wv[i] = -wv[i];
+    info = lb_dtrsl(wn, ld, m2, wv, 1, 0);
+  }
+  if (info != 0) return 1;
+  LB_UNROLL
+  for (int jy = 0; jy < col; ++jy) {
+    const int js = col + jy;
+    LB_UNROLL
+    for (int i = 0; i < n; ++i) r[i] += s->wy[jy][i] * wv[jy] / theta + s->ws[jy][i] * wv[js];
+  }
+  LB_UNROLL
+  for (int i = 0; i < n; ++i) r[i] /= theta;
+  LB_UNROLL
+  for (int i = 0; i < n; ++i) s->z[i] = s->x[i] + 1.0 * r[i];
+  return 0;
+}
+
+template <int NT>
+MB_HD int lb_sd_col(LbfgsbState* s) {
+  switch (s->col) {
+    case 1: return lb_sd_core<NT, 1>(s);
+    case 2: return lb_sd_core<NT, 2>(s);
+    case 3: return lb_sd_core<NT, 3>(s);
+    case 4: return lb_sd_core<NT, 4>(s);
+    default: return lb_sd_core<NT, 5>(s);
+  }
+}
+MB_HD int lb_sd_dispatch(LbfgsbState* s) {
+#ifdef __CUDA_ARCH__
+  static_assert(LB_M == 5, "lb_sd_col enumerates col = 1..5");
+  if (s->n == 3) return lb_sd_col<3>(s);
+  if (s->n == 4) return lb_sd_col<4>(s);
+#endif
+  return lb_sd_core<0, 0>(s);
+}
+
 // L222..L555 of mainlb: search direction d = z - x.  Returns after refreshing the memory
 // as often as the factorisations demand.
 MB_HD void lb_search_direction(LbfgsbState* s) {
@@ -279,54 +392,7 @@ MB_HD void lb_search_direction(LbfgsbState* s) {
       if (dtm <= 0.0) dtm = 0.0;
       for (int i = 0; i < n; ++i) s->z[i] = s->x[i] + dtm * s->d[i];
     } else {
-      const int col = s->col, m2 = 2 * s->col;
-      const double theta = s->theta;
-      double wn[2 * LB_M * 2 * LB_M];
-      const int ld = 2 * LB_M;
-      for (int i = 0; i < m2; ++i)
-        for (int j = 0; j < m2; ++j) wn[i * ld + j] = 0.0;
-      for (int iy = 0; iy < col; ++iy) {
-        for (int jy = 0; jy <= iy; ++jy)
-          wn[jy * ld + iy] = lb_ddot(n, s->wy[iy], s->wy[jy]) / theta;
-        for (int jy = iy; jy < col; ++jy)
-          wn[jy * ld + col + iy] = lb_ddot(n, s->ws[iy], s->wy[jy]);
-        wn[iy * ld + iy] += s->sy[iy][iy];
-      }
-      int info = lb_dpofa(wn, ld, col);
-      if (info == 0) {
-        for (int js = col; js < m2; ++js) lb_dtrsl(wn, ld, col, &wn[js], ld, 1);
-        for (int is = col; is < m2; ++is)
-          for (int js = is; js < m2; ++js) {
-            double sum = 0.0;
-            for (int k = 0; k < col; ++k) sum += wn[k * ld + is] * wn[k * ld + js];
-            wn[is * ld + js] += sum;
-          }
-        info = lb_dpofa(&wn[col * ld + col], ld, col);
-      }
-      if (info != 0) { lb_reset_memory(s); continue; }
-      double r[LB_NP], wv[2 * LB_M];
-      for (int i = 0; i < n; ++i) r[i] = -s->g[i];
-      for (int i = 0; i < col; ++i) {
-        double t1 = 0.0, t2 = 0.0;
-        for (int k = 0; k < n; ++k) {
-          t1 += s->wy[i][k] * r[k];
-          t2 += s->ws[i][k] * r[k];
-        }
-        wv[i] = t1;
-        wv[col + i] = theta * t2;
-      }
-      info = lb_dtrsl(wn, ld, m2, wv, 1, 1);
-      if (info == 0) {
-        for (int i = 0; i < col; ++i) wv[i] = -wv[i];
-        info = lb_dtrsl(wn, ld, m2, wv, 1, 0);
-      }
-      if (info != 0) { lb_reset_memory(s); continue; }
-      for (int jy = 0; jy < col; ++jy) {
-        int js = col + jy;
-        for (int i = 0; i < n; ++i) r[i] += s->wy[jy][i] * wv[jy] / theta + s->ws[jy][i] * wv[js];
-      }
-      for (int i = 0; i < n; ++i) r[i] /= theta;
-      for (int i = 0; i < n; ++i) s->z[i] = s->x[i] + 1.0 * r[i];
+      if (lb_sd_dispatch(s)) { lb_reset_memory(s); continue; }
     }
     for (int i = 0; i < n; ++i) s->d[i] = s->z[i] - s->x[i];
     return;
@@ -418,19 +484,38 @@ MB_HD void lb_matupd(LbfgsbState* s, const double* d, const double* r, double rr
   s->theta = rr / dr;
 }
 
-MB_HD int lb_formt(LbfgsbState* s) {
-  const int col = s->col;
+template <int CT>
+MB_HD int lb_formt_core(LbfgsbState* s) {
+  const int col = CT > 0 ? CT : s->col;
   const double theta = s->theta;
   double wt[LB_M * LB_M];
+  LB_UNROLL
   for (int j = 0; j < col; ++j) wt[j] = theta * s->ss[0][j];
-  for (int i = 1; i < col; ++i)
+  LB_UNROLL
+  for (int i = 1; i < col; ++i) {
+    LB_UNROLL
     for (int j = i; j < col; ++j) {
-      int k1 = (i < j) ? i : j;
+      const int k1 = (i < j) ? i : j;
       double ddum = 0.0;
+      LB_UNROLL
       for (int k = 0; k < k1; ++k) ddum += s->sy[i][k] * s->sy[j][k] / s->sy[k][k];
       wt[i * LB_M + j] = ddum + theta * s->ss[i][j];
     }
+  }
   return lb_dpofa(wt, LB_M, col) == 0;
+}
+MB_HD int lb_formt(LbfgsbState* s) {
+#ifdef __CUDA_ARCH__
+  switch (s->col) {
+    case 1: return lb_formt_core<1>(s);
+    case 2: return lb_formt_core<2>(s);
+    case 3: return lb_formt_core<3>(s);
+    case 4: return lb_formt_core<4>(s);
+    case 5: return lb_formt_core<5>(s);
+    default: break;
+  }
+#endif
+  return lb_formt_core<0>(s);
 }
 
 // Feed (f, g) evaluated at s->x.  A non-finite f ends the problem with fail = 99 (R raises

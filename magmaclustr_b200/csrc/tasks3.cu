@@ -217,26 +217,38 @@ __device__ __forceinline__ int t3_npair(int n8) {
 template <class CovT>
 __device__ inline void build_cov3(const Sm3& s, int n, int n8, const CovT& cov, double pen, int retries, const Ln& L) {
   const int ntri = t3_ntri(n8);
-  for (int idx = L.warp; idx < ntri; idx += NW3) {
-    const int e = s.tab[idx], i = (e >> 4) & 15, j = e & 15;
-    const int r = 8 * i + L.g;
-    double o[2];
+  // three tiles (six independent exponentials) per lane and iteration: the evaluation is latency bound
+  for (int idx0 = L.warp; idx0 < ntri; idx0 += 3 * NW3) {
+    double o[3][2];
+    int dst[3];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int c = 8 * j + 2 * L.t + q;
-      double v = 0.0;
-      if (r < n && c < n) {
-        v = cov.value(r, c);
-        if (r == c) {
-          double p = pen;
-          for (int k = 0; k <= retries; ++k) { v += p; p = 10 * p; }
+    for (int u = 0; u < 3; ++u) {
+      const int idx = idx0 + u * NW3;
+      dst[u] = -1;
+      if (idx < ntri) {
+        const int e = s.tab[idx], i = (e >> 4) & 15, j = e & 15;
+        dst[u] = e >> 8;
+        const int r = 8 * i + L.g;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int c = 8 * j + 2 * L.t + q;
+          double v = 0.0;
+          if (r < n && c < n) {
+            v = cov.value(r, c);
+            if (r == c) {
+              double p = pen;
+              for (int k = 0; k <= retries; ++k) { v += p; p = 10 * p; }
+            }
+          } else if (r == c) {
+            v = 1.0;
+          }
+          o[u][q] = v;
         }
-      } else if (r == c) {
-        v = 1.0;
       }
-      o[q] = v;
     }
-    *reinterpret_cast<double2*>(s.T1 + (size_t)(e >> 8) * 64 + L.o_c) = make_double2(o[0], o[1]);
+#pragma unroll
+    for (int u = 0; u < 3; ++u)
+      if (dst[u] >= 0) *reinterpret_cast<double2*>(s.T1 + (size_t)dst[u] * 64 + L.o_c) = make_double2(o[u][0], o[u][1]);
   }
   __syncthreads();
 }
@@ -260,10 +272,11 @@ __device__ __forceinline__ void chol_update_tile(double* T1, int e, int k, int d
 // Returns 0 or a non-zero code (uniform) when a pivot fails.
 template <int N8C>
 __device__ inline int chol3(const Sm3& s, int n8, const Ln& L) {
+  const int vw = L.warp;
   const int ntri = t3_ntri(n8);
   if (threadIdx.x == 0) *s.flag = 0;
   __syncthreads();
-  if (L.warp == 0) {
+  if (vw == 0) {
     const int f = warp_factor_panel(s.T1, n8 < 4 ? n8 : 4, s.rinv, L.lane);
     if (f) { if (L.lane == 0) *s.flag = f; }
     else if (4 < n8 || n8 == 1) warp_diag_inverse(s.T1, s.rinv, s.T2, L.lane);
@@ -276,7 +289,7 @@ __device__ inline int chol3(const Sm3& s, int n8, const Ln& L) {
     const bool far = (k + 4 < n8);
     if (far) {
       // remaining panel tiles: R_kj = X_kk' A_kj
-      for (int j = k + 4 + L.warp; j < n8; j += NW3) {
+      for (int j = k + 4 + vw; j < n8; j += NW3) {
         double* Tkj = s.T1 + (size_t)(dk + j - k) * 64;
         double a0, a1, b0, b1, c0 = 0.0, c1 = 0.0;
         cf(Xkk, L, a0, a1);
@@ -291,7 +304,7 @@ __device__ inline int chol3(const Sm3& s, int n8, const Ln& L) {
     // trailing update A_ij -= R_ki' R_kj, k < i <= j: jobs [j0, ntri) of the table
     const int m = n8 - k - 1, nla = m < 4 ? m : 4;
     const int j0 = (k + 1) * n8 - (((k + 1) * k) >> 1);
-    if (L.warp == 0) {
+    if (vw == 0) {
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         if (q < nla) chol_update_tile(s.T1, s.tab[j0 + q], k, dk, L);
@@ -302,8 +315,8 @@ __device__ inline int chol3(const Sm3& s, int n8, const Ln& L) {
         warp_diag_inverse(s.T1 + (size_t)Lay<N8C>::tri(k + 1) * 64, s.rinv + 8 * (k + 1),
                           s.T2 + (size_t)((k + 1) * N8C + k + 1) * 64, L.lane);
     } else {
-      if (!far && L.warp == NW3 - 1) warp_diag_inverse(s.T1 + (size_t)dk * 64, s.rinv + 8 * k, Xkk, L.lane);
-      for (int idx = j0 + nla + L.warp - 1; idx < ntri; idx += NW3 - 1) chol_update_tile(s.T1, s.tab[idx], k, dk, L);
+      if (!far && vw == NW3 - 1) warp_diag_inverse(s.T1 + (size_t)dk * 64, s.rinv + 8 * k, Xkk, L.lane);
+      for (int idx = j0 + nla + vw - 1; idx < ntri; idx += NW3 - 1) chol_update_tile(s.T1, s.tab[idx], k, dk, L);
     }
     __syncthreads();
     if (*s.flag) return *s.flag;
@@ -407,11 +420,32 @@ __device__ inline void lauum3(const Sm3& s, int n8, const Ln& L) {
 
 // chol_inv_jitter(K(x; hp)): T1 <- inverse (packed, exactly symmetric).  Returns retries or -1;
 // *sumlog = sum_j log R_jj (uniform).
+// Optional phase timing (compile with -DT3_TIMING): thread 0 of every CTA adds the SM clock cycles spent
+// between marks to t3_phase_cycles[]; read with mb_debug_phase_cycles().  Not compiled into product builds.
+#ifdef T3_TIMING
+__device__ unsigned long long t3_phase_cycles[16];
+#define T3_MARK(idx) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&t3_phase_cycles[idx], (unsigned long long)(now_ - t3_last_)); t3_last_ = now_; } } while (0)
+#define T3_MARK_DECL long long t3_last_ = clock64()
+#define T3_MARK_ARG , long long& t3_last_
+#define T3_MARK_PASS , t3_last_
+extern "C" int mb_debug_phase_cycles(unsigned long long* out16, int reset) {
+  if (cudaMemcpyFromSymbol(out16, t3_phase_cycles, sizeof(unsigned long long) * 16) != cudaSuccess) return -2;
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(t3_phase_cycles, z, sizeof(z)); }
+  return 0;
+}
+#else
+#define T3_MARK(idx) do { } while (0)
+#define T3_MARK_DECL do { } while (0)
+#define T3_MARK_ARG
+#define T3_MARK_PASS
+#endif
+
 template <int N8C, class CovT>
-__device__ inline int task_inverse3(const Sm3& s, int n, int n8, const CovT& cov, double pen, double* sumlog, const Ln& L) {
+__device__ inline int task_inverse3(const Sm3& s, int n, int n8, const CovT& cov, double pen, double* sumlog, const Ln& L T3_MARK_ARG) {
   int retries = 0;
   for (;;) {
     build_cov3(s, n, n8, cov, pen, retries, L);
+    T3_MARK(1);
     if (chol3<N8C>(s, n8, L) == 0) break;
     __syncthreads();
     if (++retries > TK_MAX_RETRY) return -1;
@@ -420,9 +454,12 @@ __device__ inline int task_inverse3(const Sm3& s, int n, int n8, const CovT& cov
   for (int j = threadIdx.x; j < n; j += T3_THREADS) v[0] += log(s.T1[(size_t)Lay<N8C>::tri(j >> 3) * 64 + sw(j & 7, j & 7)]);
   red3<1>(v, s.red);
   *sumlog = v[0];
+  T3_MARK(2);
   scale3<N8C>(s, n8, L);
   trtri3<N8C>(s, n8, L);
+  T3_MARK(3);
   lauum3<N8C>(s, n8, L);
+  T3_MARK(4);
   return retries;
 }
 
@@ -494,9 +531,11 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_objecti
   double* c1v = s.vin + np;
   double* al = s.vout;
   double* be = s.vout + np;
+  T3_MARK_DECL;
   load_task3<N8C>(s, a.db, row0, n, np);
   Cov<KS, D1> cov;
   cov.init(a.kd, a.lb ? a.lb[task].x : a.hp + task * a.hp_stride, s.xs, D);
+  T3_MARK(0);
   for (int i = tid; i < np; i += T3_THREADS) {
     double r = 0.0, c = 0.0;
     if (i < n) {
@@ -511,7 +550,7 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_objecti
     c1v[i] = c;
   }
   double sumlog;
-  const int retries = task_inverse3<N8C>(s, n, n8, cov, a.pen, &sumlog, L);
+  const int retries = task_inverse3<N8C>(s, n, n8, cov, a.pen, &sumlog, L T3_MARK_PASS);
   if (a.retries && tid == 0) a.retries[task] = retries;
   if (retries < 0) {
     if (tid == 0) {
@@ -567,6 +606,7 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_objecti
 
   if (a.mode == TK_OBJ_ELBO) gemv3<N8C, 2>(s, n8, s.vin, s.vout, L);
   else gemv3<N8C, 1>(s, n8, s.vin, s.vout, L);
+  T3_MARK(5);
 
   // B = S A with S taken from L2 as A-fragments; tr(A o S) on the way.  All (k, j) are compile-time:
   // one accumulator tile per column block, every shared-memory address register + immediate.
@@ -615,6 +655,7 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_objecti
       v[0] += rv[i] * al[i];
       if (a.mode == TK_OBJ_ELBO) v[2] += al[i] * c1v[i];
     }
+    T3_MARK(6);
     red3<3>(v, s.red);   // also orders the B writes before the reads below
     if (tid == 0) {
       double f = 0.5 * (n * LOG_2PI - logdetA + v[0]);
@@ -623,6 +664,7 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_objecti
       a.f[task] = f;
     }
   }
+  T3_MARK(7);
   if (!a.want_grad) return;
 
   // gradient: upper tiles of T = A B, two tiles of one row per job (shared A fragments), contracted with
@@ -675,6 +717,7 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_objecti
     }
   }
 #pragma unroll
+  T3_MARK(8);
   for (int p0 = 0; p0 < NG; p0 += 4) {
     if (p0 < P) {
       double v[4];
@@ -708,7 +751,8 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_inverse
     Cov<KS, D1> cov;
     cov.init(a.kd, a.hp + task * a.hp_stride, s.xs, D);
     double sumlog;
-    const int retries = task_inverse3<N8C>(s, n, n8, cov, a.pen, &sumlog, L);
+    T3_MARK_DECL;
+    const int retries = task_inverse3<N8C>(s, n, n8, cov, a.pen, &sumlog, L T3_MARK_PASS);
     if (a.retries && tid == 0) a.retries[task] = retries;
     const bool bad = retries < 0;
     if (a.inv_out) {
@@ -737,6 +781,7 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_inverse
     __syncthreads();
   }
 }
+
 
 // ---- launchers --------------------------------------------------------------------------------------
 static inline bool is_se(const DevKern& kd) { return kd.n_terms == 1 && kd.types[0] == MB_KERN_SE; }
