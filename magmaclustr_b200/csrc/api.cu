@@ -178,7 +178,7 @@ struct DenseWs {   // workspace of one dense n x n problem
 struct mb_context {
   int device = 0;
   int sm_count = 148;
-  cudaStream_t st = nullptr, st2 = nullptr;
+  cudaStream_t st = nullptr, st2 = nullptr, st3 = nullptr;   // st3: device-to-host copies of the round counters
   int64_t launches = 0;
   int logdet_chol = 0;
   // resident dataset
@@ -201,6 +201,7 @@ struct mb_context {
   // timing / profiling
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
   cudaEvent_t ev_ring[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_cp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool prof_on = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
   size_t prof_used = 0;
@@ -306,6 +307,7 @@ extern "C" int mb_destroy(mb_context* c) {
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
   for (int i = 0; i < 8; ++i) if (c->ev_ring[i]) cudaEventDestroy(c->ev_ring[i]);
+  for (int i = 0; i < 8; ++i) if (c->ev_cp[i]) cudaEventDestroy(c->ev_cp[i]);
   c->ws0.release();
   c->ws1.release();
   big_pool_destroy(c->big);
@@ -313,6 +315,7 @@ extern "C" int mb_destroy(mb_context* c) {
   if (c->h_pin_i) cudaFreeHost(c->h_pin_i);
   if (c->st) cudaStreamDestroy(c->st);
   if (c->st2) cudaStreamDestroy(c->st2);
+  if (c->st3) cudaStreamDestroy(c->st3);
   delete c;
   return 0;
 }
@@ -488,7 +491,7 @@ static cudaError_t gemm_any(int m, int n, int k, const double* A, int64_t ars, i
                             int64_t brs, int64_t bcs, double* C, int64_t ldc, double alpha, const double* Cin,
                             double beta, cudaStream_t st) {
   const bool unit = (ars == 1 || acs == 1) && (brs == 1 || bcs == 1);
-  if (unit && (int64_t)m * n >= 192 * 192 && k >= 64)
+  if (unit && (int64_t)m * n >= 512 * 512 && k >= 64)
     return launch_big_gemm_plain(m, n, k, A, ars, acs, B, brs, bcs, C, ldc, alpha, Cin, beta, st);
   return launch_gemm_dmma(m, n, k, A, ars, acs, B, brs, bcs, C, ldc, alpha, Cin, beta, st);
 }
@@ -871,15 +874,22 @@ static int optimise(mb_context* c, std::vector<SingleProblem>& singles, bool tas
   // (every CTA / thread sees an inactive problem and returns).
   const int LB_LAG = 1, RING = 8;
   int enq = 0;          // rounds enqueued
-  for (int i = 0; i < RING; ++i)
+  for (int i = 0; i < RING; ++i) {
     if (!c->ev_ring[i]) CU(cudaEventCreateWithFlags(&c->ev_ring[i], cudaEventDisableTiming));
+    if (!c->ev_cp[i]) CU(cudaEventCreateWithFlags(&c->ev_cp[i], cudaEventDisableTiming));
+  }
+  if (!c->st3) CU(cudaStreamCreateWithFlags(&c->st3, cudaStreamNonBlocking));
   while (tasks_active || cur < singles.size()) {
     if (tasks_active) {
       if (enq >= 4095) MB_FAIL(2, "L-BFGS-B lock-step did not terminate");
       MB_TRY(launch_obj(c, a, (int)M, c->st, true));
       LAUNCH(c, launch_lbfgsb_advance(c->lb.as<LbfgsbState>(), M, P_i, a.f, a.g, c->counters.as<int>() + enq, c->st));
-      MB_TRY(d2h(c->h_pin_i + 64 + (enq % RING), c->counters.as<int>() + enq, sizeof(int), c->st));
+      // the active count travels on a side stream: a copy between two kernels of the main stream would put a
+      // kernel -> copy engine -> kernel hand-over (~20 us) into every round
       CU(cudaEventRecord(c->ev_ring[enq % RING], c->st));
+      CU(cudaStreamWaitEvent(c->st3, c->ev_ring[enq % RING], 0));
+      MB_TRY(d2h(c->h_pin_i + 64 + (enq % RING), c->counters.as<int>() + enq, sizeof(int), c->st3));
+      CU(cudaEventRecord(c->ev_cp[enq % RING], c->st3));
       enq++;
     }
     if (cur < singles.size()) {
@@ -894,7 +904,7 @@ static int optimise(mb_context* c, std::vector<SingleProblem>& singles, bool tas
     }
     if (tasks_active && enq > LB_LAG) {
       const int r = enq - 1 - LB_LAG;
-      CU(cudaEventSynchronize(c->ev_ring[r % RING]));
+      CU(cudaEventSynchronize(c->ev_cp[r % RING]));
       if (c->h_pin_i[64 + (r % RING)] == 0) { tasks_active = false; rounds = r + 1; }
     }
   }
