@@ -191,7 +191,7 @@ struct mb_context {
   // workspaces
   DenseWs ws0, ws1;                 // ws0: mean/cluster process on st2 ; ws1: generic on st
   DBuf hp_i, hp_k, f_t, g_t, retries, lb, counters, part_inv, part_w, sums, pm, pc, m0, tau,
-      inv0, post_inv, weighted, fails, nfgv, scratch;
+      inv0, post_inv, weighted, fails, nfgv, scratch, kcache;
   double* h_pin = nullptr;          // pinned host scratch (256 doubles)
   int* h_pin_i = nullptr;           // pinned host ints (1024)
   // resident EM state (mb_set_state): pristine + working HP tables
@@ -222,7 +222,15 @@ struct mb_context {
 static int launch_obj(mb_context* c, const TaskObjArgs& a, int n_launch, cudaStream_t st,
                       bool profiled = false) {
   if (a.db.nmax > TK_MAXN) return big_tasks_objective(&c->big, a, c->h_offs.data(), st, &c->launches);
-  if (!c->prof_on || !profiled) { LAUNCH(c, launch_task_objective_any(a, n_launch, st)); return 0; }
+  TaskObjArgs a2 = a;
+  if (a.want_grad && task_kernel_version() == 3) {
+    const int n8 = (a.db.nmax + 7) / 8;
+    a2.kcache_stride = (int64_t)(a.db.nmax <= 64 ? 36 : 78) * 64;   // packed upper tiles of the 8 / 12-tile layouts
+    (void)n8;
+    MB_TRY(c->kcache.ensure((size_t)a.db.n_tasks * a2.kcache_stride * 8));
+    a2.kcache = c->kcache.as<double>();
+  }
+  if (!c->prof_on || !profiled) { LAUNCH(c, launch_task_objective_any(a2, n_launch, st)); return 0; }
   if (c->prof_used == c->prof_ev.size()) {
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
@@ -231,7 +239,7 @@ static int launch_obj(mb_context* c, const TaskObjArgs& a, int n_launch, cudaStr
   }
   auto& ev = c->prof_ev[c->prof_used++];
   CU(cudaEventRecord(ev.first, st));
-  LAUNCH(c, launch_task_objective_any(a, n_launch, st));
+  LAUNCH(c, launch_task_objective_any(a2, n_launch, st));
   CU(cudaEventRecord(ev.second, st));
   return 0;
 }
@@ -299,7 +307,7 @@ extern "C" int mb_destroy(mb_context* c) {
   DBuf* bufs[] = {&c->d_offs, &c->d_X, &c->d_y, &c->d_gidx, &c->d_gridX, &c->hp_i, &c->hp_k, &c->f_t,
                   &c->g_t, &c->retries, &c->lb, &c->counters, &c->part_inv, &c->part_w, &c->sums,
                   &c->pm, &c->pc, &c->m0, &c->tau, &c->inv0, &c->post_inv, &c->weighted, &c->fails,
-                  &c->nfgv, &c->scratch};
+                  &c->nfgv, &c->scratch, &c->kcache};
   for (DBuf* b : bufs) b->release();
   c->st_hp_i0.release();
   c->st_hp_i.release();

@@ -48,6 +48,10 @@ struct TaskObjArgs {
   double* g;                 // n_tasks x n_hp
   int32_t* retries;          // n_tasks (may be NULL)
   int ld;                    // shared-memory leading dimension (odd, >= nmax)
+  // optional scratch (n_tasks x kcache_stride doubles): the SE kernel values computed while K is built are kept
+  // here (L2 / HBM) and re-read by the gradient contraction instead of evaluating exp() a second time
+  double* kcache;
+  int64_t kcache_stride;
 };
 
 struct TaskInvArgs {       // E step / list_kern_to_inv

@@ -152,10 +152,13 @@ template <bool D1> struct Cov<KS_SE, D1> {
       for (int q = 0; q < D; ++q) { double df = xs[r * D + q] - xs[c * D + q]; d2 += df * df; l1 += fabs(df); }
     }
   }
-  __device__ __forceinline__ double value(int r, int c) const {
+  static constexpr bool CACHEABLE = true;
+  // value and, in raw, the noise-free kernel value exp(v - top) that grad() needs again
+  __device__ __forceinline__ double value(int r, int c, double& raw) const {
     double d2, l1;
     sums(r, c, d2, l1);
     double k = exp(v - hel * d2);
+    raw = k;
     if (l1 < 0.000001) k += en;   // en == 0 without a noise HP
     return k;
   }
@@ -166,6 +169,16 @@ template <bool D1> struct Cov<KS_SE, D1> {
     const double wk = w * exp(v - top);
     gacc[0] += wk;
     gacc[1] += wk * top;   // w * exp(v) * top * exp(-top) of the reference up to rounding
+    if (l1 < 0.000001) gacc[2] += w * en;
+  }
+  // same with exp(v - top) read back from the cache written by value() (bit-identical)
+  __device__ __forceinline__ void grad_cached(double w, int r, int c, double raw, double* gacc) const {
+    double d2, l1;
+    sums(r, c, d2, l1);
+    const double top = hel * d2;
+    const double wk = w * raw;
+    gacc[0] += wk;
+    gacc[1] += wk * top;
     if (l1 < 0.000001) gacc[2] += w * en;
   }
 };
@@ -183,9 +196,12 @@ template <bool D1> struct Cov<KS_GEN, D1> {
     prep_hp(kd_, hp, hpe);
     xs = xs_; D = D_;
   }
-  __device__ __forceinline__ double value(int r, int c) const {
+  static constexpr bool CACHEABLE = false;
+  __device__ __forceinline__ double value(int r, int c, double& raw) const {
+    raw = 0.0;
     return cov_eval<false>(*kd, hp, hpe, xs + r * D, xs + c * D, D, true, nullptr);
   }
+  __device__ __forceinline__ void grad_cached(double w, int r, int c, double, double* gacc) const { grad(w, r, c, gacc); }
   __device__ __forceinline__ void grad(double w, int r, int c, double* gacc) const {
     double dv[MB_MAX_HP];
     cov_eval<true>(*kd, hp, hpe, xs + r * D, xs + c * D, D, true, dv);
@@ -215,11 +231,12 @@ __device__ __forceinline__ int t3_npair(int n8) {
 // ---- building blocks ---------------------------------------------------------------------------------
 // upper tiles of K + cumulative jitter (identity on the padding) into T1
 template <class CovT>
-__device__ inline void build_cov3(const Sm3& s, int n, int n8, const CovT& cov, double pen, int retries, const Ln& L) {
+__device__ inline void build_cov3(const Sm3& s, int n, int n8, const CovT& cov, double pen, int retries, const Ln& L,
+                                  double* kc = nullptr) {
   const int ntri = t3_ntri(n8);
   // three tiles (six independent exponentials) per lane and iteration: the evaluation is latency bound
   for (int idx0 = L.warp; idx0 < ntri; idx0 += 3 * NW3) {
-    double o[3][2];
+    double o[3][2], raw[3][2];
     int dst[3];
 #pragma unroll
     for (int u = 0; u < 3; ++u) {
@@ -233,8 +250,9 @@ __device__ inline void build_cov3(const Sm3& s, int n, int n8, const CovT& cov, 
         for (int q = 0; q < 2; ++q) {
           const int c = 8 * j + 2 * L.t + q;
           double v = 0.0;
+          raw[u][q] = 0.0;
           if (r < n && c < n) {
-            v = cov.value(r, c);
+            v = cov.value(r, c, raw[u][q]);
             if (r == c) {
               double p = pen;
               for (int k = 0; k <= retries; ++k) { v += p; p = 10 * p; }
@@ -248,7 +266,11 @@ __device__ inline void build_cov3(const Sm3& s, int n, int n8, const CovT& cov, 
     }
 #pragma unroll
     for (int u = 0; u < 3; ++u)
-      if (dst[u] >= 0) *reinterpret_cast<double2*>(s.T1 + (size_t)dst[u] * 64 + L.o_c) = make_double2(o[u][0], o[u][1]);
+      if (dst[u] >= 0) {
+        *reinterpret_cast<double2*>(s.T1 + (size_t)dst[u] * 64 + L.o_c) = make_double2(o[u][0], o[u][1]);
+        if (CovT::CACHEABLE && kc)
+          reinterpret_cast<double2*>(kc + (size_t)dst[u] * 64)[L.lane] = make_double2(raw[u][0], raw[u][1]);
+      }
   }
   __syncthreads();
 }
@@ -441,10 +463,11 @@ extern "C" int mb_debug_phase_cycles(unsigned long long* out16, int reset) {
 #endif
 
 template <int N8C, class CovT>
-__device__ inline int task_inverse3(const Sm3& s, int n, int n8, const CovT& cov, double pen, double* sumlog, const Ln& L T3_MARK_ARG) {
+__device__ inline int task_inverse3(const Sm3& s, int n, int n8, const CovT& cov, double pen, double* sumlog, const Ln& L,
+                                    double* kc T3_MARK_ARG) {
   int retries = 0;
   for (;;) {
-    build_cov3(s, n, n8, cov, pen, retries, L);
+    build_cov3(s, n, n8, cov, pen, retries, L, kc);
     T3_MARK(1);
     if (chol3<N8C>(s, n8, L) == 0) break;
     __syncthreads();
@@ -550,7 +573,8 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_objecti
     c1v[i] = c;
   }
   double sumlog;
-  const int retries = task_inverse3<N8C>(s, n, n8, cov, a.pen, &sumlog, L T3_MARK_PASS);
+  double* kc = (Cov<KS, D1>::CACHEABLE && a.kcache && a.want_grad) ? a.kcache + task * a.kcache_stride : nullptr;
+  const int retries = task_inverse3<N8C>(s, n, n8, cov, a.pen, &sumlog, L, kc T3_MARK_PASS);
   if (a.retries && tid == 0) a.retries[task] = retries;
   if (retries < 0) {
     if (tid == 0) {
@@ -695,6 +719,12 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_objecti
     }
     const int r = 8 * i + L.g;
     const double* Arow = s.T1 + (size_t)(Lay<N8C>::tri(i) + j - i) * 64 + L.o_c;
+    double2 kv[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
+    if (kc) {
+      const double2* kp = reinterpret_cast<const double2*>(kc + (size_t)(Lay<N8C>::tri(i) + j - i) * 64) + L.lane;
+      kv[0] = kp[0];
+      if (two) kv[1] = kp[32];
+    }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       if (h == 0 || two) {
@@ -710,14 +740,15 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_objecti
             double w;
             if (r == c) w = lr * al[r] + tij - arc;
             else w = (lr * al[c] + lc * al[r]) + 2.0 * (tij - arc);
-            cov.grad(w, r, c, gacc);
+            if (kc) cov.grad_cached(w, r, c, qq ? kv[h].y : kv[h].x, gacc);
+            else cov.grad(w, r, c, gacc);
           }
         }
       }
     }
   }
-#pragma unroll
   T3_MARK(8);
+#pragma unroll
   for (int p0 = 0; p0 < NG; p0 += 4) {
     if (p0 < P) {
       double v[4];
@@ -752,7 +783,7 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_inverse
     cov.init(a.kd, a.hp + task * a.hp_stride, s.xs, D);
     double sumlog;
     T3_MARK_DECL;
-    const int retries = task_inverse3<N8C>(s, n, n8, cov, a.pen, &sumlog, L T3_MARK_PASS);
+    const int retries = task_inverse3<N8C>(s, n, n8, cov, a.pen, &sumlog, L, nullptr T3_MARK_PASS);
     if (a.retries && tid == 0) a.retries[task] = retries;
     const bool bad = retries < 0;
     if (a.inv_out) {
