@@ -63,7 +63,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -217,14 +217,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident steps ------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                     # started before the warm-up: the timed region itself is < 100 ms
     for _ in range(args.warmup):
         ctx.em_step_resident(k0, ki, restart=True)
     ctx.profile(True)
     ctx.profile_read()
-    sampler = ClockSampler(local_rank)
     launches0 = ctx.launches
-    if rank == 0:
-        sampler.start()
     ms = []
     stats = None
     logL = None
@@ -310,6 +310,19 @@ def main():
     }
     if fit:
         line["fit"] = fit
+    if world == 1:
+        # second half of BASELINE.json's metric: batched Cholesky FP64 TFLOP/s, device-only
+        ms_inv, fl = ctx.bench_task_inverse(ki, reps=5)
+        bc = {"tasks": {"kernel": "k_task_inverse3", "M": M_TASKS, "N": N_POINTS, "ms": ms_inv,
+                        "tflops_chol_plus_inverse_n3": fl / ms_inv / 1e9,
+                        "frac_of_dgemm": fl / ms_inv / 1e9 / peak if peak else None}}
+        n_big = 4096
+        for what, key, flops in ((1, "chol_n3_over_3", n_big ** 3 / 3.0), (2, "chol_plus_inverse_n3", float(n_big) ** 3),
+                                 (0, "gemm_2n3", 2.0 * n_big ** 3)):
+            ms_d = ctx.bench_dense(what, n_big, reps=3)
+            bc.setdefault("dense_4096", {})[key] = {"ms": ms_d, "tflops": flops / ms_d / 1e9,
+                                                    "frac_of_dgemm": flops / ms_d / 1e9 / peak if peak else None}
+        line["batched_chol"] = bc
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count()
         m_sample = args.cpu_sample

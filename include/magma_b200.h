@@ -265,6 +265,10 @@ int mb_matmul(mb_context*, int transa, int transb, int m, int n, int k, const do
  * on an n-point SE + noise covariance: what = 0 product (2 n^3 flops), 1 chol() (n^3 / 3), 2 chol2inv(chol())
  * (n^3).  ms_out[0] = mean milliseconds per repetition, CUDA events on the library's stream. */
 int mb_bench_dense(mb_context*, int what, int n, int reps, double* ms_out);
+/* Same for the batched per-task path on the resident dataset (after mb_set_state): every task's
+ * chol2inv(chol(K_i + jitter)) in one persistent launch, nothing written.  flops_out[0] = sum_i N_i^3. */
+int mb_bench_task_inverse(mb_context*, const mb_kernel* kern_i, double pen_diag, int reps, double* ms_out,
+                          double* flops_out);
 
 /* ---- optimiser, exposed for tests: optim(method="L-BFGS-B") on a built-in test function
  * (0 = Rosenbrock n=2), run by the same state machine the M step uses (host build). */

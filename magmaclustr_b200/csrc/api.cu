@@ -1424,6 +1424,43 @@ extern "C" int mb_bench_dense(mb_context* c, int what, int n, int reps, double* 
   return 0;
 }
 
+// Device-only timing of the batched per-task factorisation (BASELINE.json: "batched chol FP64 TFLOP/s"): every
+// task's K(x; hp_i) + jitter -> Cholesky -> inverse with the resident dataset and the pristine HP table of
+// mb_set_state, no accumulation or output (the E step's kernel without its scatter).  flops_out = sum N_i^3.
+extern "C" int mb_bench_task_inverse(mb_context* c, const mb_kernel* kern_i, double pen_diag, int reps, double* ms_out,
+                                     double* flops_out) {
+  MB_TRY(need_db(c, false));
+  if (!c->have_state || !kern_i || reps < 1 || !ms_out) MB_FAIL(-1, "mb_set_state first");
+  if (c->db.nmax > TK_MAXN) MB_FAIL(-4, "use mb_bench_dense for large tasks");
+  TaskInvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.db = c->db; a.kd = make_devkern(kern_i); a.hp = c->st_hp_i0.as<double>(); a.hp_stride = kern_i->n_hp;
+  a.pen = pen_diag; a.K = 1; a.U = c->U;
+  MB_TRY(c->retries.ensure(c->db.n_tasks * 4));
+  a.retries = c->retries.as<int32_t>();
+  int G = c->sm_count * task_ctas_per_sm_any(c->db.nmax, c->db.D);
+  if (G > c->db.n_tasks) G = (int)c->db.n_tasks;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  LAUNCH(c, launch_task_inverse_any(a, G, c->st));
+  CU(cudaEventRecord(e0, c->st));
+  for (int r = 0; r < reps; ++r) LAUNCH(c, launch_task_inverse_any(a, G, c->st));
+  CU(cudaEventRecord(e1, c->st));
+  CU(cudaEventSynchronize(e1));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  ms_out[0] = ms / reps;
+  if (flops_out) {
+    double fl = 0;
+    for (int64_t t = 0; t < c->db.n_tasks; ++t) { const double n = (double)(c->h_offs[t + 1] - c->h_offs[t]); fl += n * n * n; }
+    flops_out[0] = fl;
+  }
+  return 0;
+}
+
 // ---- pred_magma --------------------------------------------------------------------------------
 cudaError_t launch_pred_var(const DevKern& kd, const double* hp_host, const double* xp, int np, int D,
                             const double* sdiag, const double* C, const double* GC, int no,

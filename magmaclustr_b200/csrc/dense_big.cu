@@ -278,20 +278,25 @@ __global__ void __launch_bounds__(DSM_THREADS, 1) k_big_potrf_diag(double* W, in
 }
 
 // Z = R_kk^{-T} B in place for a row panel of up to 64 rows: one thread per column, forward substitution
-// in registers against the factored diagonal block held in shared memory (broadcast reads).
-#define TRS_THREADS 64
+// in registers against the factored diagonal block held in shared memory (broadcast reads).  256 columns per
+// CTA so that the 64 x 64 block is fetched with 16 independent loads per thread (with 64 threads the fetch
+// alone was 64 dependent round trips to L2, ~20 us).
+#define TRS_THREADS 256
 __global__ void __launch_bounds__(TRS_THREADS) k_big_trsm_rt(const double* __restrict__ Rkk, int64_t ldr, double* Bm,
                                                              int64_t ldb, int kb, int ncols, const int* fail) {
   if (*fail) return;
   __shared__ double Rs[64][64];
   __shared__ double rinv[64];
   const int tid = threadIdx.x;
-  for (int e = tid; e < 64 * 64; e += TRS_THREADS) {
-    const int i = e >> 6, j = e & 63;
-    double v = 0.0;
-    if (i < kb && j < kb) { if (j >= i) v = Rkk[(int64_t)i * ldr + j]; }
-    else if (i == j) v = 1.0;
-    Rs[i][j] = v;
+  {
+    double v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int e = tid + TRS_THREADS * q, i = e >> 6, j = e & 63;
+      v[q] = (i < kb && j < kb && j >= i) ? Rkk[(int64_t)i * ldr + j] : ((i == j && i >= kb) ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { const int e = tid + TRS_THREADS * q; Rs[e >> 6][e & 63] = v[q]; }
   }
   __syncthreads();
   if (tid < 64) rinv[tid] = 1.0 / Rs[tid][tid];

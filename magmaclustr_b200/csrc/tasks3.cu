@@ -33,6 +33,30 @@
 
 enum { KS_GEN = 0, KS_SE = 1 };
 
+// Optional phase timing (compile with -DT3_TIMING): thread 0 of every CTA adds the SM clock cycles spent
+// between marks to t3_phase_cycles[]; read with mb_debug_phase_cycles().  Not compiled into product builds.
+#ifdef T3_TIMING
+__device__ unsigned long long t3_phase_cycles[16];
+#define T3_MARK(idx) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&t3_phase_cycles[idx], (unsigned long long)(now_ - t3_last_)); t3_last_ = now_; } } while (0)
+#define T3_MARK_DECL long long t3_last_ = clock64()
+#define T3_MARK_ARG , long long& t3_last_
+#define T3_MARK_PASS , t3_last_
+extern "C" int mb_debug_phase_cycles(unsigned long long* out16, int reset) {
+  if (cudaMemcpyFromSymbol(out16, t3_phase_cycles, sizeof(unsigned long long) * 16) != cudaSuccess) return -2;
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(t3_phase_cycles, z, sizeof(z)); }
+  return 0;
+}
+#define T3_SUB_DECL long long t3c_ = clock64()
+#define T3_SUB(idx) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&t3_phase_cycles[idx], (unsigned long long)(now_ - t3c_)); t3c_ = now_; } } while (0)
+#else
+#define T3_SUB_DECL do { } while (0)
+#define T3_SUB(idx) do { } while (0)
+#define T3_MARK(idx) do { } while (0)
+#define T3_MARK_DECL do { } while (0)
+#define T3_MARK_ARG
+#define T3_MARK_PASS
+#endif
+
 template <int N8C>
 struct Lay {
   static constexpr int NTRI = N8C * (N8C + 1) / 2;
@@ -298,12 +322,14 @@ __device__ inline int chol3(const Sm3& s, int n8, const Ln& L) {
   const int ntri = t3_ntri(n8);
   if (threadIdx.x == 0) *s.flag = 0;
   __syncthreads();
+  T3_SUB_DECL;
   if (vw == 0) {
     const int f = warp_factor_panel(s.T1, n8 < 4 ? n8 : 4, s.rinv, L.lane);
     if (f) { if (L.lane == 0) *s.flag = f; }
     else if (4 < n8 || n8 == 1) warp_diag_inverse(s.T1, s.rinv, s.T2, L.lane);
   }
   __syncthreads();
+  T3_SUB(9);
   if (*s.flag) return *s.flag;
   for (int k = 0; k + 1 < n8; ++k) {
     const int dk = Lay<N8C>::tri(k);
@@ -323,6 +349,7 @@ __device__ inline int chol3(const Sm3& s, int n8, const Ln& L) {
       }
       __syncthreads();
     }
+    T3_SUB(10);
     // trailing update A_ij -= R_ki' R_kj, k < i <= j: jobs [j0, ntri) of the table
     const int m = n8 - k - 1, nla = m < 4 ? m : 4;
     const int j0 = (k + 1) * n8 - (((k + 1) * k) >> 1);
@@ -331,7 +358,9 @@ __device__ inline int chol3(const Sm3& s, int n8, const Ln& L) {
       for (int q = 0; q < 4; ++q)
         if (q < nla) chol_update_tile(s.T1, s.tab[j0 + q], k, dk, L);
       __syncwarp();
+      T3_SUB(11);
       const int f = warp_factor_panel(s.T1 + (size_t)Lay<N8C>::tri(k + 1) * 64, nla, s.rinv + 8 * (k + 1), L.lane);
+      T3_SUB(12);
       if (f) { if (L.lane == 0) *s.flag = 8 * (k + 1) + f; }
       else if (k + 5 < n8 || k + 2 == n8)
         warp_diag_inverse(s.T1 + (size_t)Lay<N8C>::tri(k + 1) * 64, s.rinv + 8 * (k + 1),
@@ -340,7 +369,9 @@ __device__ inline int chol3(const Sm3& s, int n8, const Ln& L) {
       if (!far && vw == NW3 - 1) warp_diag_inverse(s.T1 + (size_t)dk * 64, s.rinv + 8 * k, Xkk, L.lane);
       for (int idx = j0 + nla + vw - 1; idx < ntri; idx += NW3 - 1) chol_update_tile(s.T1, s.tab[idx], k, dk, L);
     }
+    T3_SUB(13);
     __syncthreads();
+    T3_SUB(14);
     if (*s.flag) return *s.flag;
   }
   return 0;
@@ -442,25 +473,6 @@ __device__ inline void lauum3(const Sm3& s, int n8, const Ln& L) {
 
 // chol_inv_jitter(K(x; hp)): T1 <- inverse (packed, exactly symmetric).  Returns retries or -1;
 // *sumlog = sum_j log R_jj (uniform).
-// Optional phase timing (compile with -DT3_TIMING): thread 0 of every CTA adds the SM clock cycles spent
-// between marks to t3_phase_cycles[]; read with mb_debug_phase_cycles().  Not compiled into product builds.
-#ifdef T3_TIMING
-__device__ unsigned long long t3_phase_cycles[16];
-#define T3_MARK(idx) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&t3_phase_cycles[idx], (unsigned long long)(now_ - t3_last_)); t3_last_ = now_; } } while (0)
-#define T3_MARK_DECL long long t3_last_ = clock64()
-#define T3_MARK_ARG , long long& t3_last_
-#define T3_MARK_PASS , t3_last_
-extern "C" int mb_debug_phase_cycles(unsigned long long* out16, int reset) {
-  if (cudaMemcpyFromSymbol(out16, t3_phase_cycles, sizeof(unsigned long long) * 16) != cudaSuccess) return -2;
-  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(t3_phase_cycles, z, sizeof(z)); }
-  return 0;
-}
-#else
-#define T3_MARK(idx) do { } while (0)
-#define T3_MARK_DECL do { } while (0)
-#define T3_MARK_ARG
-#define T3_MARK_PASS
-#endif
 
 template <int N8C, class CovT>
 __device__ inline int task_inverse3(const Sm3& s, int n, int n8, const CovT& cov, double pen, double* sumlog, const Ln& L,

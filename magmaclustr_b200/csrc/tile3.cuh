@@ -19,34 +19,50 @@ __device__ __forceinline__ void rf(const double* P, const Ln& L, double& x0, dou
 // column fragment (P[t][g], P[t+4][g]): B operand of P, or A operand of P'
 __device__ __forceinline__ void cf(const double* P, const Ln& L, double& x0, double& x1) { x0 = P[L.o_tg]; x1 = P[L.o_tg + 32]; }
 
-// One warp: eliminate the row panel [A_kk | A_k,k+1 | A_k,k+2 | A_k,k+3] in registers, lane c owning
-// column c & 7 of tile k + (c >> 3).  dpotf2 rule: fail on a pivot <= 0 or NaN.  R_kj = R_kk^{-T} A_kj
-// falls out of the same row operations, so the first three panel tiles cost nothing extra.
+// One warp: eliminate the row panel [A_kk | A_k,k+1 | A_k,k+2 | A_k,k+3], lane c owning column c & 7 of
+// tile k + (c >> 3).  dpotf2 rule: fail on a pivot <= 0 or NaN.
+// Every lane first factors the 8 x 8 diagonal tile FOR ITSELF in registers (36 broadcast loads, 84 FMAs with
+// plenty of instruction-level parallelism, no shuffles), then runs the forward substitution R_kk^{-T} a on
+// its own column -- for the columns of the diagonal tile this reproduces R_kk, for the panel tiles it is
+// R_kj = R_kk^{-T} A_kj.  The earlier version passed every multiplier through a 64-bit warp shuffle: 8 x 7
+// shuffle pairs on the serial pivot chain of the factorisation; the arithmetic (and hence every bit of the
+// result) is the same.
 // Returns 0 or the failing pivot (1-based), uniform across the warp.
 // Pkk: tile (k, k); the next tiles of row k follow contiguously; navail = min(4, n8 - k); rinv8 receives
 // the reciprocals of the eight pivots.
 __device__ __forceinline__ int warp_factor_panel(double* Pkk, int navail, double* rinv8, int lane) {
   const int cb = lane >> 3, cc = lane & 7;
   const bool act = cb < navail;
-  double* P = Pkk + (size_t)(act ? cb : 0) * 64;
-  double a[8], ri[8];
+  double R[8][8], ri[8];
 #pragma unroll
-  for (int r = 0; r < 8; ++r) a[r] = P[sw(r, cc)];
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = i; j < 8; ++j) R[i][j] = Pkk[sw(i, j)];
   int fail = 0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const double ajj = __shfl_sync(FULLMASK, a[j], j);
+    const double ajj = R[j][j];
     if (!(ajj > 0.0) && fail == 0) fail = j + 1;
     const double rj = rsqrt(ajj);
     ri[j] = rj;
-    a[j] = (lane == j) ? ajj * rj : a[j] * rj;
 #pragma unroll
-    for (int i = j + 1; i < 8; ++i) {
-      const double rji = __shfl_sync(FULLMASK, a[j], i);
-      if (lane >= i) a[i] -= rji * a[j];
-    }
+    for (int c = j + 1; c < 8; ++c) R[j][c] *= rj;
+#pragma unroll
+    for (int i = j + 1; i < 8; ++i)
+#pragma unroll
+      for (int c = i; c < 8; ++c) R[i][c] -= R[j][i] * R[j][c];
   }
   if (fail) return fail;
+  double* P = Pkk + (size_t)(act ? cb : 0) * 64;
+  double a[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) a[r] = P[sw(r, cc)];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a[j] *= ri[j];
+#pragma unroll
+    for (int i = j + 1; i < 8; ++i) a[i] -= R[j][i] * a[j];
+  }
   if (act) {
 #pragma unroll
     for (int r = 0; r < 8; ++r) P[sw(r, cc)] = (cb == 0 && r > cc) ? 0.0 : a[r];

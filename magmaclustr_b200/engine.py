@@ -282,6 +282,12 @@ class Context:
         check(L.lib().mb_bench_dense(self._h, int(what), int(n), int(reps), ptr(ms)))
         return float(ms[0])
 
+    def bench_task_inverse(self, ki, reps=5, pen_diag=1e-10):
+        """(ms per launch, sum N_i^3) of the batched chol2inv(chol(K_i)) over the resident dataset."""
+        ms, fl = np.zeros(1), np.zeros(1)
+        check(L.lib().mb_bench_task_inverse(self._h, C.byref(ki), float(pen_diag), int(reps), ptr(ms), ptr(fl)))
+        return float(ms[0]), float(fl[0])
+
     def hyperposterior(self, k0, hp_0, ki, hp_i, grid_X, grid_index, m_0, pen_diag=1e-10,
                        shared=False):
         gX = f64(np.atleast_2d(np.asarray(grid_X, dtype=np.float64).T).T)

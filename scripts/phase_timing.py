@@ -13,7 +13,8 @@ from magmaclustr_b200 import _lib as L  # noqa: E402
 from magmaclustr_b200.engine import Context  # noqa: E402
 
 NAMES = ["load+hp", "cov build", "chol+logdet", "trtri", "lauum", "vectors+gemv", "S gather + B=SA", "f reduce",
-         "gradient (AB o dK)"]
+         "gradient (AB o dK)", "  chol: first panel", "  chol: far panel tiles + sync", "  chol: look-ahead update (warp 0)",
+         "  chol: panel factor (warp 0)", "  chol: diag inverse (warp 0)", "  chol: wait for trailing update"]
 
 
 def main():
@@ -31,7 +32,7 @@ def main():
     lib.mb_debug_phase_cycles(buf, 1)
     tot = float(sum(buf[:9]))
     for i, nme in enumerate(NAMES):
-        print("%-22s %12d cycles/task  %5.1f%%" % (nme, buf[i] / ctx.n_tasks, 100.0 * buf[i] / tot))
+        print("%-38s %12d cycles/task  %5.1f%%" % (nme, buf[i] / ctx.n_tasks, 100.0 * buf[i] / tot))
     print("total %.0f cycles per task (CTA latency)" % (tot / ctx.n_tasks))
     ctx.close()
 
