@@ -33,7 +33,7 @@ M_TASKS, N_POINTS = 10000, 64
 DATA_SEED, HP0_SEED, HPI_SEED = 2024, 6, 106
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-grid launch of the dominant kernel (10 000
 # evaluations), from the ncu --set full capture summarised in profiles/ (None until captured)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 13577472
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 144334080
 METRIC = "train_magma EM steps/sec at M=10k,N=64"
 FLOPS_PER_EVAL = 5.0  # x N^3: chol+inverse N^3, S A and A (S A) 4 N^3; log-det read off the Cholesky diagonal
 
