@@ -323,6 +323,20 @@ def main():
             bc.setdefault("dense_4096", {})[key] = {"ms": ms_d, "tflops": flops / ms_d / 1e9,
                                                     "frac_of_dgemm": flops / ms_d / 1e9 / peak if peak else None}
         line["batched_chol"] = bc
+        # HBM-bound kernels of the path: stand-alone covariance build and the E step's reduction,
+        # device-only, against the measured copy bandwidth of MEASURED_PEAKS.json
+        hbm_peak = None
+        try:
+            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            hbm_peak = float(pk.get("hbm_gbps_burst") or pk.get("hbm_gbps") or pk.get("hbm_gbs") or 0) or None
+        except Exception:
+            pass
+        hk = {"peak_gbps": hbm_peak}
+        for what, key in ((0, "list_kern_to_cov"), (1, "e_step_reduce_partials")):
+            ms_h, by = ctx.bench_hbm(what, ki, reps=10)
+            hk[key] = {"ms": ms_h, "algorithmic_bytes": by, "gbps": by / ms_h / 1e6,
+                       "frac_of_hbm": (by / ms_h / 1e6 / hbm_peak) if hbm_peak else None}
+        line["hbm_kernels"] = hk
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count()
         m_sample = args.cpu_sample

@@ -270,6 +270,12 @@ int mb_bench_dense(mb_context*, int what, int n, int reps, double* ms_out);
 int mb_bench_task_inverse(mb_context*, const mb_kernel* kern_i, double pen_diag, int reps, double* ms_out,
                           double* flops_out);
 
+/* Device-only timing of the HBM-bound kernels of the path on the resident dataset (after mb_set_state):
+ * what = 0 list_kern_to_cov (/root/reference/R/kernel-to-matrices.R:586-652), every task's covariance matrix
+ * written to HBM; what = 1 the E step's deterministic reduction of the per-CTA partial precision sums
+ * (/root/reference/R/em-magma.R:39-46).  bytes_out[0] = algorithmic bytes per repetition. */
+int mb_bench_hbm(mb_context*, int what, const mb_kernel* kern_i, int reps, double* ms_out, double* bytes_out);
+
 /* ---- optimiser, exposed for tests: optim(method="L-BFGS-B") on a built-in test function
  * (0 = Rosenbrock n=2), run by the same state machine the M step uses (host build). */
 int mb_lbfgsb_selftest(int which, double* x, int n, double factr, int maxit, double* fval,

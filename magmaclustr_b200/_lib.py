@@ -89,6 +89,7 @@ _SIGS = {
     "mb_matmul": [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int],
     "mb_bench_dense": [_vp, C.c_int, C.c_int, C.c_int, _dp],
     "mb_bench_task_inverse": [_vp, _kp, C.c_double, C.c_int, _dp, _dp],
+    "mb_bench_hbm": [_vp, C.c_int, _kp, C.c_int, _dp, _dp],
     "mb_lbfgsb_selftest": [C.c_int, _dp, C.c_int, C.c_double, C.c_int, _dp, _ip, _ip],
 }
 

@@ -10,7 +10,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmagma_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
-UNITS = [("tasks.cu", []), ("tasks2.cu", []), ("tasks3.cu", []), ("dense.cu", []), ("dense3.cu", []), ("dense_big.cu", []), ("bigtasks.cu", []), ("api.cu", []), ("lbfgsb_dev.cu", ["-fmad=false"])]
+UNITS = [("tasks.cu", []), ("tasks2.cu", []), ("tasks3.cu", []), ("covbuild.cu", []), ("dense.cu", []), ("dense3.cu", []), ("dense_big.cu", []), ("bigtasks.cu", []), ("api.cu", []), ("lbfgsb_dev.cu", ["-fmad=false"])]
 
 
 def _newer(src_list, target):
@@ -38,16 +38,21 @@ def build(verbose=False, force=False):
     os.makedirs(LIBDIR, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(HERE, "..", "include", "magma_b200.h"))
-    objs = []
+    objs, cmds = [], []
     for name, extra in UNITS:
         src = os.path.join(CSRC, name)
         obj = os.path.join(LIBDIR, name.replace(".cu", ".o"))
         objs.append(obj)
         if force or _newer([src] + headers, obj):
-            cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmds.append([nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
+    if cmds:   # translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+        def run(cmd):
             if verbose:
                 print(" ".join(cmd))
             subprocess.check_call(cmd)
+        with ThreadPoolExecutor(max_workers=min(len(cmds), os.cpu_count() or 1)) as ex:
+            list(ex.map(run, cmds))
     if force or _newer(objs, LIB):
         cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart_static", "-ldl", "-lrt", "-lpthread"]
         if verbose:

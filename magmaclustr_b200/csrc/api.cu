@@ -23,6 +23,8 @@ cudaError_t launch_task_inverse(TaskInvArgs a, int n_ctas, cudaStream_t st);
 cudaError_t launch_task_cov(TaskData db, DevKern kd, const double* hp, int64_t hp_stride,
                             int deriv, double* out, const int64_t* out_offs, cudaStream_t st);
 int task_max_ctas_per_sm(int nmax, int D);
+cudaError_t launch_task_cov_sym(TaskData db, DevKern kd, const double* hp, int64_t hp_stride, int deriv, double* out,
+                                const int64_t* out_offs, int sm_count, cudaStream_t st);
 cudaError_t launch_task_objective2(TaskObjArgs a, int n_launch, cudaStream_t st);
 cudaError_t launch_task_inverse2(TaskInvArgs a, int n_ctas, cudaStream_t st);
 int task2_max_ctas_per_sm(int nmax, int D);
@@ -622,8 +624,13 @@ extern "C" int mb_list_kern_to_mat(mb_context* c, const mb_kernel* k, int64_t n_
   db.D = d; db.n_tasks = n_tasks; db.nmax = nmax;
   cudaError_t e;
   if (!inverse) {
-    e = launch_task_cov(db, kd, b_hp.as<double>(), hp_shared ? 0 : k->n_hp, deriv, b_out.as<double>(),
-                        b_oo.as<int64_t>(), c->st);
+    e = launch_task_cov_sym(db, kd, b_hp.as<double>(), hp_shared ? 0 : k->n_hp, deriv, b_out.as<double>(),
+                            b_oo.as<int64_t>(), c->sm_count, c->st);
+    if (e == cudaErrorInvalidValue) {   // task rows larger than the staging buffer: element-per-thread kernel
+      cudaGetLastError();
+      e = launch_task_cov(db, kd, b_hp.as<double>(), hp_shared ? 0 : k->n_hp, deriv, b_out.as<double>(),
+                          b_oo.as<int64_t>(), c->st);
+    }
   } else {
     if (deriv >= 0) { cleanup(); MB_FAIL(-1, "inverse of a derivative matrix is not part of the hot path"); }
     TaskInvArgs a;
@@ -1458,6 +1465,62 @@ extern "C" int mb_bench_task_inverse(mb_context* c, const mb_kernel* kern_i, dou
     for (int64_t t = 0; t < c->db.n_tasks; ++t) { const double n = (double)(c->h_offs[t + 1] - c->h_offs[t]); fl += n * n * n; }
     flops_out[0] = fl;
   }
+  return 0;
+}
+
+// Device-only timing of the HBM-bound kernels of the path on the resident dataset:
+//   what = 0  list_kern_to_cov: every task's covariance matrix written to HBM (bytes = 8 sum n_i^2 + table reads)
+//   what = 1  the E step's deterministic reduction of the per-CTA partial precision sums (bytes = 8 (G + 2) U^2)
+// ms_out[0] = mean ms per repetition, bytes_out[0] = algorithmic bytes per repetition.
+extern "C" int mb_bench_hbm(mb_context* c, int what, const mb_kernel* kern_i, int reps, double* ms_out, double* bytes_out) {
+  MB_TRY(need_db(c, what == 1));
+  if (!c->have_state || !kern_i || reps < 1 || !ms_out || !bytes_out) MB_FAIL(-1, "mb_set_state first");
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  static thread_local DBuf d_out, d_oo;
+  if (what == 0) {
+    const int64_t M = c->db.n_tasks;
+    std::vector<int64_t> oo(M);
+    size_t total = 0;
+    for (int64_t t = 0; t < M; ++t) { const size_t n = (size_t)(c->h_offs[t + 1] - c->h_offs[t]); oo[t] = (int64_t)total; total += n * n; }
+    MB_TRY(d_out.ensure(total * 8));
+    MB_TRY(d_oo.ensure(M * 8));
+    MB_TRY(h2d(d_oo.p, oo.data(), M * 8, c->st));
+    DevKern kd = make_devkern(kern_i);
+    for (int it = -1; it < reps; ++it) {
+      if (it == 0) CU(cudaEventRecord(e0, c->st));
+      cudaError_t e = launch_task_cov_sym(c->db, kd, c->st_hp_i0.as<double>(), kern_i->n_hp, -1, d_out.as<double>(),
+                                          d_oo.as<int64_t>(), c->sm_count, c->st);
+      if (e != cudaSuccess) { mb_set_error(__FILE__, __LINE__, cudaGetErrorString(e)); return -2; }
+      c->launches++;
+    }
+    bytes_out[0] = 8.0 * (double)total + 8.0 * (double)c->h_offs[M] * c->db.D + 8.0 * (double)M * kern_i->n_hp;
+  } else if (what == 1) {
+    const size_t UU = (size_t)c->U * c->U;
+    int G = c->sm_count * task_ctas_per_sm_any(c->db.nmax > TK_MAXN ? TK_MAXN : c->db.nmax, c->db.D);
+    if (G > c->db.n_tasks) G = (int)c->db.n_tasks;
+    MB_TRY(c->part_inv.ensure((size_t)G * UU * 8));
+    MB_TRY(c->inv0.ensure(UU * 8));
+    MB_TRY(c->post_inv.ensure(UU * 8));
+    CU(cudaMemsetAsync(c->part_inv.p, 0, (size_t)G * UU * 8, c->st));
+    CU(cudaMemsetAsync(c->inv0.p, 0, UU * 8, c->st));
+    for (int it = -1; it < reps; ++it) {
+      if (it == 0) CU(cudaEventRecord(e0, c->st));
+      LAUNCH(c, launch_reduce_partials(UU, G, c->inv0.as<double>(), c->part_inv.as<double>(), UU, c->post_inv.as<double>(), c->st));
+    }
+    bytes_out[0] = 8.0 * (double)UU * (G + 2);
+  } else {
+    MB_FAIL(-1, "what must be 0 or 1");
+  }
+  CU(cudaEventRecord(e1, c->st));
+  CU(cudaEventSynchronize(e1));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (what == 0) { d_out.release(); d_oo.release(); }
+  ms_out[0] = ms / reps;
   return 0;
 }
 

@@ -269,13 +269,35 @@ __global__ void k_dense_obj_final(int n, int P, int nparts, const double* part, 
 
 // ---- small utilities -------------------------------------------------------------------
 // out[e] = base[e] + sum_g part[g][e], g ascending (deterministic): post_inv = inv_0 (+) sum_i.
-__global__ void k_reduce_partials(int64_t count, int nparts, const double* base,
-                                  const double* part, int64_t part_stride, double* out) {
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < count;
-       e += (int64_t)gridDim.x * blockDim.x) {
-    double acc = base ? base[e] : 0.0;
-    for (int g = 0; g < nparts; ++g) acc += part[(size_t)g * part_stride + e];
-    out[e] = acc;
+// Two levels: the partials are cut into RP_SLICES contiguous slices; 32 x RP_SLICES threads per block sum "their"
+// slice of 32 consecutive elements in ascending g (unit-stride 256-byte reads per warp), then the first warp adds the
+// slice sums in slice order on top of base.  The summation tree is fixed by (nparts) alone -- deterministic and
+// independent of the launch geometry -- and keeps 8x more loads in flight than one thread per element.
+#define RP_SLICES 8
+__global__ void __launch_bounds__(32 * RP_SLICES) k_reduce_partials(int64_t count, int nparts, const double* __restrict__ base,
+                                                                    const double* __restrict__ part, int64_t part_stride,
+                                                                    double* __restrict__ out) {
+  __shared__ double sh[RP_SLICES][32];
+  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int per = (nparts + RP_SLICES - 1) / RP_SLICES;
+  const int g0 = sl * per, g1 = min(nparts, g0 + per);
+  for (int64_t e0 = (int64_t)blockIdx.x * 32; e0 < count; e0 += (int64_t)gridDim.x * 32) {
+    const int64_t e = e0 + lane;
+    double acc = 0.0;
+    if (e < count) {
+      const double* p = part + e;
+#pragma unroll 8
+      for (int g = g0; g < g1; ++g) acc += __ldcs(p + (size_t)g * part_stride);
+    }
+    sh[sl][lane] = acc;
+    __syncthreads();
+    if (sl == 0 && e < count) {
+      double r = base ? base[e] : 0.0;
+#pragma unroll
+      for (int q = 0; q < RP_SLICES; ++q) r += sh[q][lane];
+      out[e] = r;
+    }
+    __syncthreads();
   }
 }
 
@@ -431,8 +453,9 @@ cudaError_t launch_dense_obj(const DevKern& kd, const double* hp_host, const dou
 cudaError_t launch_reduce_partials(int64_t count, int nparts, const double* base,
                                    const double* part, int64_t part_stride, double* out,
                                    cudaStream_t st) {
-  k_reduce_partials<<<grid_for(count, 256), 256, 0, st>>>(count, nparts, base, part, part_stride,
-                                                          out);
+  int64_t blocks = (count + 31) / 32;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  k_reduce_partials<<<(unsigned)blocks, 32 * RP_SLICES, 0, st>>>(count, nparts, base, part, part_stride, out);
   return cudaGetLastError();
 }
 

@@ -288,6 +288,12 @@ class Context:
         check(L.lib().mb_bench_task_inverse(self._h, C.byref(ki), float(pen_diag), int(reps), ptr(ms), ptr(fl)))
         return float(ms[0]), float(fl[0])
 
+    def bench_hbm(self, what, ki, reps=5):
+        """(ms per launch, algorithmic bytes) of an HBM-bound kernel: what = 0 list_kern_to_cov, 1 E-step reduction."""
+        ms, by = np.zeros(1), np.zeros(1)
+        check(L.lib().mb_bench_hbm(self._h, int(what), C.byref(ki), int(reps), ptr(ms), ptr(by)))
+        return float(ms[0]), float(by[0])
+
     def hyperposterior(self, k0, hp_0, ki, hp_i, grid_X, grid_index, m_0, pen_diag=1e-10,
                        shared=False):
         gX = f64(np.atleast_2d(np.asarray(grid_X, dtype=np.float64).T).T)

@@ -115,6 +115,33 @@ def test_list_kern_to_inv_ragged(ctx):
         assert relerr(mats[t], oinv) < 1e-9
 
 
+# ---- list_kern_to_cov: symmetric blocked builder (covbuild.cu) against the element-wise oracle --------------------
+@pytest.mark.parametrize("kern,noise,d", [("SE", True, 1), ("SE", False, 2), ("SE + PERIO", True, 1),
+                                          ("RQ * LIN", True, 2), ("PERIO", False, 1)])
+def test_list_kern_to_cov_blocks(ctx, kern, noise, d):
+    """Ragged tasks around the 64-point block edge (odd / even sizes, several blocks), values and every derivative:
+    each matrix equals the element-wise kernel (test-kern_to_cov.R:1-35) and is exactly symmetric."""
+    rng = np.random.default_rng(23 + d)
+    sizes = [1, 2, 3, 31, 63, 64, 65, 96, 129, 200, 10]
+    offs = np.r_[0, np.cumsum(sizes)]
+    X = np.concatenate([np.round(rng.uniform(-1, 1, size=(n, d)), 3) for n in sizes])
+    X[offs[3] + 1] = X[offs[3]]          # a coincident pair inside one task: noise lands off the diagonal too (Q4)
+    k = L.parse_kernel(kern, noise)
+    names = L.hp_names(k)
+    hp = rng.uniform(0.2, 1.5, size=(len(sizes), len(names)))
+    for dv in [None] + list(range(len(names))):
+        covs, _ = ctx.list_kern_to_mat(k, offs, X, hp, inverse=False, deriv=-1 if dv is None else dv)
+        for t in range(len(sizes)):
+            xt = X[offs[t]:offs[t + 1]]
+            ref = OK.kern_to_cov(xt, kern, dict(zip(names, hp[t])), deriv=None if dv is None else names[dv])
+            np.testing.assert_allclose(covs[t], ref, rtol=5e-13, atol=1e-14, err_msg="%s task %d deriv %s" % (kern, t, dv))
+            assert np.array_equal(covs[t], covs[t].T)
+    # one HP row shared by every task (list_kern_to_cov with a single-row hp tibble, kernel-to-matrices.R:600-612)
+    covs, _ = ctx.list_kern_to_mat(k, offs, X, hp[:1], shared=True, inverse=False)
+    ref = OK.kern_to_cov(X[offs[5]:offs[6]], kern, dict(zip(names, hp[0])))
+    np.testing.assert_allclose(covs[5], ref, rtol=5e-13, atol=1e-14)
+
+
 # ---- logL_GP_mod / gr_GP_mod check values (SURVEY.md 8c; test-gradients-logL.R:32-58) ------------
 def test_logL_GP_mod_check_values(ctx):
     X = np.column_stack([np.arange(1, 6), np.arange(3, 8)]).astype(float)
