@@ -270,6 +270,38 @@ int mb_bench_dense(mb_context*, int what, int n, int reps, double* ms_out);
 int mb_bench_task_inverse(mb_context*, const mb_kernel* kern_i, double pen_diag, int reps, double* ms_out,
                           double* flops_out);
 
+/* ---- new tasks against a resident hyper-posterior --------------------------------------------------------------
+ * pred_magma / pred_magmaclust process ONE new task per call in the reference and carry G x G matrices through R
+ * (/root/reference/R/prediction.R:822-1250, 1883-2476).  Here the hyper-posterior evaluated on the union grid
+ * (training inputs U prediction grid U new-task inputs) stays on the device, the new tasks are uploaded as the
+ * resident dataset (mb_upload_dataset, grid_index = position of every observation in that union grid) and all of
+ * them are trained / predicted in one call.
+ *
+ * mb_hyperpost_keep(ctx, 1): the next mb_hyperposterior / mb_hyperposterior_clust leaves its result resident
+ * (its host outputs may then be NULL); keep = 0 stops that, keep < 0 also frees the resident copy.
+ * mb_hyperpost_set: upload one (n_clusters x n_grid means, n_clusters x n_grid x n_grid covariances; post_cov may
+ * be NULL = zero covariance, which turns mb_logL_GP_tasks into the terms of sum_logL_GP, R/likelihoods.R:113-129). */
+int mb_hyperpost_keep(mb_context*, int keep);
+int mb_hyperpost_set(mb_context*, int n_clusters, int32_t n_grid, const double* post_mean, const double* post_cov);
+/* logL_GP + gr_GP (/root/reference/R/likelihoods.R:73-86, R/gradients-likelihoods.R:22-49) of every resident task
+ * against cluster `cluster` of the resident hyper-posterior: cov = K(x; hp) + post_cov[t, t] inverted with
+ * chol_inv_jitter, f[t] = -log N(y; mean[t], cov), g[t, p] = -1/2 tr((aa' - inv) dK/dhp_p).  g, retries may be NULL. */
+int mb_logL_GP_tasks(mb_context*, const mb_kernel* kern, const double* hp, int hp_shared, int cluster,
+                     double pen_diag, double* f, double* g, int32_t* retries);
+/* train_gp (/root/reference/R/training.R:78-287) for every resident task at once: optim(L-BFGS-B, factr = 1e13,
+ * maxit = 25) of logL_GP / gr_GP from hp[t, ] (n_tasks x n_hp, overwritten; a task whose result is not finite keeps
+ * its initial values, :277-284).  stats as mb_m_step; mb_last_task_status gives convergence codes / counts. */
+int mb_train_gp_tasks(mb_context*, const mb_kernel* kern, double* hp, int cluster, double pen_diag, int64_t* stats);
+/* pred_magma (K = 1) / pred_magmaclust (K > 1, tau = n_tasks x K mixture probabilities of the new tasks) on n_pred
+ * points for every resident task (/root/reference/R/prediction.R:1146-1197, 2319-2404): pred_mean, pred_var are
+ * n_tasks x n_pred row-major (Var includes exp(noise) like the reference's `Var` column); the optional
+ * pred_mean_k / pred_var_k (n_tasks x K x n_pred) receive the cluster-specific predictions.  pred_index[g] is the
+ * position of prediction point g in the union grid.  retries: n_tasks x K (may be NULL).  Only the diagonal of the
+ * predictive covariance is formed; the full matrix of one task is mb_pred_magma's business. */
+int mb_pred_magma_tasks(mb_context*, const mb_kernel* kern, const double* hp, const double* tau, int32_t n_pred,
+                        const double* x_pred, const int32_t* pred_index, double pen_diag, double* pred_mean,
+                        double* pred_var, double* pred_mean_k, double* pred_var_k, int32_t* retries);
+
 /* Device-only timing of the HBM-bound kernels of the path on the resident dataset (after mb_set_state):
  * what = 0 list_kern_to_cov (/root/reference/R/kernel-to-matrices.R:586-652), every task's covariance matrix
  * written to HBM; what = 1 the E step's deterministic reduction of the per-CTA partial precision sums

@@ -25,6 +25,7 @@ cudaError_t launch_task_cov(TaskData db, DevKern kd, const double* hp, int64_t h
 int task_max_ctas_per_sm(int nmax, int D);
 cudaError_t launch_task_cov_sym(TaskData db, DevKern kd, const double* hp, int64_t hp_stride, int deriv, double* out,
                                 const int64_t* out_offs, int sm_count, cudaStream_t st);
+cudaError_t launch_task_pred(TaskPredArgs a, int n_launch_tasks, cudaStream_t st);
 cudaError_t launch_task_objective2(TaskObjArgs a, int n_launch, cudaStream_t st);
 cudaError_t launch_task_inverse2(TaskInvArgs a, int n_ctas, cudaStream_t st);
 int task2_max_ctas_per_sm(int nmax, int D);
@@ -200,6 +201,10 @@ struct mb_context {
   DBuf st_hp_i0, st_hp_i;
   double st_hp_00[MB_MAX_HP], st_hp_0[MB_MAX_HP];
   bool have_state = false;
+  // resident hyper-posterior on a union grid (mb_hyperpost_set / mb_hyperpost_keep): K x U means, K x U x U covariances
+  DBuf hpr_mean, hpr_cov;
+  int hpr_K = 0, hpr_U = 0;
+  bool hpr_keep = false, hpr_has_cov = false;
   // timing / profiling
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
   cudaEvent_t ev_ring[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -313,6 +318,8 @@ extern "C" int mb_destroy(mb_context* c) {
   for (DBuf* b : bufs) b->release();
   c->st_hp_i0.release();
   c->st_hp_i.release();
+  c->hpr_mean.release();
+  c->hpr_cov.release();
   for (auto& ev : c->prof_ev) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
@@ -979,7 +986,8 @@ static int hyperposterior_any(mb_context* c, int K, const mb_kernel* kern_k, con
                               const double* tau, double pen_diag, double* post_mean, double* post_cov) {
   MB_TRY(check_ctx(c));
   if (!c->have_db) MB_FAIL(-1, "no dataset uploaded");
-  if (!kern_k || !hp_k || !kern_i || !hp_i || !grid_X || !grid_index || n_grid < 1 || !m_k || !post_mean || !post_cov)
+  if (!kern_k || !hp_k || !kern_i || !hp_i || !grid_X || !grid_index || n_grid < 1 || !m_k ||
+      ((!post_mean || !post_cov) && !c->hpr_keep))
     MB_FAIL(-1, "bad argument");
   if (K < 1 || K > MB_MAX_CLUSTERS || (K > 1 && !tau)) MB_FAIL(-1, "bad cluster count / missing mixture");
   for (int64_t r = 0; r < c->n_rows; ++r)
@@ -1002,9 +1010,15 @@ static int hyperposterior_any(mb_context* c, int K, const mb_kernel* kern_k, con
                              m0.as<double>(), tau ? dtau.as<double>() : nullptr, gX.as<double>(), n_grid,
                              gi.as<int32_t>(), pen_diag, pm.as<double>(), pc.as<double>(), nullptr);
     if (!rc) {
-      cudaMemcpyAsync(post_mean, pm.p, (size_t)K * n_grid * 8, cudaMemcpyDeviceToHost, c->st);
-      cudaMemcpyAsync(post_cov, pc.p, K * UU * 8, cudaMemcpyDeviceToHost, c->st);
+      if (post_mean) cudaMemcpyAsync(post_mean, pm.p, (size_t)K * n_grid * 8, cudaMemcpyDeviceToHost, c->st);
+      if (post_cov) cudaMemcpyAsync(post_cov, pc.p, K * UU * 8, cudaMemcpyDeviceToHost, c->st);
       if (cudaStreamSynchronize(c->st) != cudaSuccess) { mb_set_error(__FILE__, __LINE__, "copy back failed"); rc = -2; }
+    }
+    if (!rc && c->hpr_keep) {   // the result stays on the device for the new-task entry points (no G x G round trip)
+      c->hpr_mean.release(); c->hpr_cov.release();
+      c->hpr_mean = pm; c->hpr_cov = pc;
+      pm = DBuf(); pc = DBuf();
+      c->hpr_K = K; c->hpr_U = n_grid; c->hpr_has_cov = true;
     }
   }
   gX.release(); gi.release(); pm.release(); pc.release(); m0.release(); dtau.release();
@@ -1027,6 +1041,160 @@ extern "C" int mb_hyperposterior_clust(mb_context* c, int n_clusters, const mb_k
                                        double* post_mean, double* post_cov) {
   return hyperposterior_any(c, n_clusters, kern_k, hp_k, kern_i, hp_i, hp_i_shared, n_grid, grid_X, grid_index,
                             m_k, tau, pen_diag, post_mean, post_cov);
+}
+
+// ================================================================================================
+// New tasks against a resident hyper-posterior: logL_GP / gr_GP (marginal forms), train_gp and pred_magma(clust)
+// batched over the tasks of the resident dataset.
+// ================================================================================================
+extern "C" int mb_hyperpost_keep(mb_context* c, int keep) {
+  MB_TRY(check_ctx(c));
+  c->hpr_keep = keep != 0;
+  if (keep < 0) { c->hpr_mean.release(); c->hpr_cov.release(); c->hpr_K = c->hpr_U = 0; c->hpr_keep = false; }
+  return 0;
+}
+
+extern "C" int mb_hyperpost_set(mb_context* c, int n_clusters, int32_t n_grid, const double* post_mean,
+                                const double* post_cov) {
+  MB_TRY(check_ctx(c));
+  if (n_clusters < 1 || n_clusters > MB_MAX_CLUSTERS || n_grid < 1 || !post_mean) MB_FAIL(-1, "bad argument");
+  const size_t UU = (size_t)n_grid * n_grid;
+  MB_TRY(c->hpr_mean.ensure((size_t)n_clusters * n_grid * 8));
+  MB_TRY(h2d(c->hpr_mean.p, post_mean, (size_t)n_clusters * n_grid * 8, c->st));
+  if (post_cov) {
+    MB_TRY(c->hpr_cov.ensure(n_clusters * UU * 8));
+    MB_TRY(h2d(c->hpr_cov.p, post_cov, n_clusters * UU * 8, c->st));
+  }
+  CU(cudaStreamSynchronize(c->st));
+  c->hpr_K = n_clusters; c->hpr_U = n_grid; c->hpr_has_cov = post_cov != nullptr;
+  return 0;
+}
+
+static int need_hyperpost(mb_context* c, int cluster, bool need_cov) {
+  MB_TRY(need_db(c, true));
+  if (c->hpr_K < 1) MB_FAIL(-1, "no resident hyper-posterior (mb_hyperpost_set / mb_hyperpost_keep)");
+  if (c->hpr_U != c->U) MB_FAIL(-1, "the resident dataset's grid is not the hyper-posterior's grid");
+  if (cluster < 0 || cluster >= c->hpr_K) MB_FAIL(-1, "cluster out of range");
+  if (need_cov && !c->hpr_has_cov) MB_FAIL(-1, "this entry point needs the hyper-posterior covariance");
+  if (c->db.nmax > TK_MAXN) MB_FAIL(-4, "new tasks with more than 96 points are not supported by the batched new-task path");
+  return 0;
+}
+
+static TaskObjArgs marg_args(mb_context* c, const DevKern& kd, const double* hp_dev, int64_t stride, int cluster,
+                             int want_grad, double pen) {
+  const size_t UU = (size_t)c->U * c->U;
+  return make_obj_args(c, kd, hp_dev, stride, TK_OBJ_MARG, want_grad, pen, 1,
+                       c->hpr_mean.as<double>() + (size_t)cluster * c->U,
+                       c->hpr_has_cov ? c->hpr_cov.as<double>() + (size_t)cluster * UU : nullptr, nullptr,
+                       c->f_t.as<double>(), c->g_t.as<double>());
+}
+
+extern "C" int mb_logL_GP_tasks(mb_context* c, const mb_kernel* kern, const double* hp, int hp_shared, int cluster,
+                                double pen_diag, double* f, double* g, int32_t* retries) {
+  MB_TRY(need_hyperpost(c, cluster, false));
+  if (!kern || !hp || !f) MB_FAIL(-1, "null argument");
+  MB_TRY(ensure_em_buffers(c, 1));
+  int64_t stride;
+  MB_TRY(put_hp_i(c, kern, hp, hp_shared, &stride));
+  DevKern kd = make_devkern(kern);
+  TaskObjArgs a = marg_args(c, kd, c->hp_i.as<double>(), stride, cluster, g != nullptr, pen_diag);
+  MB_TRY(c->retries.ensure(c->db.n_tasks * 4));
+  a.retries = c->retries.as<int32_t>();
+  MB_TRY(launch_obj(c, a, (int)c->db.n_tasks, c->st));
+  MB_TRY(d2h(f, c->f_t.p, c->db.n_tasks * 8, c->st));
+  if (g) MB_TRY(d2h(g, c->g_t.p, (size_t)c->db.n_tasks * kd.n_hp * 8, c->st));
+  if (retries) MB_TRY(d2h(retries, c->retries.p, c->db.n_tasks * 4, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+extern "C" int mb_train_gp_tasks(mb_context* c, const mb_kernel* kern, double* hp, int cluster, double pen_diag,
+                                 int64_t* stats) {
+  MB_TRY(need_hyperpost(c, cluster, false));
+  if (!kern || !hp) MB_FAIL(-1, "null argument");
+  MB_TRY(ensure_em_buffers(c, 1));
+  const int P = kern->n_hp;
+  const int64_t M = c->db.n_tasks;
+  MB_TRY(c->hp_k.ensure((size_t)M * P * 8));
+  MB_TRY(h2d(c->hp_k.p, hp, (size_t)M * P * 8, c->st));
+  DevKern kd = make_devkern(kern);
+  TaskObjArgs a = marg_args(c, kd, c->hp_k.as<double>(), P, cluster, 1, pen_diag);
+  std::vector<SingleProblem> none;
+  int64_t st4[4] = {0, 0, 0, 0};
+  MB_TRY(optimise(c, none, true, a, c->hp_k.as<double>(), P, pen_diag, st4));
+  // training.R:277-284: a task whose optimisation produced a non-finite HP returns its initial values
+  std::vector<double> out((size_t)M * P);
+  MB_TRY(d2h(out.data(), c->hp_k.p, (size_t)M * P * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  for (int64_t t = 0; t < M; ++t) {
+    bool bad = false;
+    for (int p = 0; p < P; ++p) if (!std::isfinite(out[t * P + p])) bad = true;
+    if (!bad) for (int p = 0; p < P; ++p) hp[t * P + p] = out[t * P + p];
+  }
+  if (stats) for (int i = 0; i < 4; ++i) stats[i] = st4[i];
+  return 0;
+}
+
+extern "C" int mb_pred_magma_tasks(mb_context* c, const mb_kernel* kern, const double* hp, const double* tau,
+                                   int32_t n_pred, const double* x_pred, const int32_t* pred_index, double pen_diag,
+                                   double* pred_mean, double* pred_var, double* pred_mean_k, double* pred_var_k,
+                                   int32_t* retries) {
+  MB_TRY(need_hyperpost(c, 0, true));
+  const int K = c->hpr_K, D = c->db.D, P = kern ? kern->n_hp : 0;
+  const int64_t M = c->db.n_tasks;
+  if (!kern || !hp || !x_pred || !pred_index || !pred_mean || !pred_var || n_pred < 1 || (K > 1 && !tau) ||
+      ((pred_mean_k == nullptr) != (pred_var_k == nullptr)))
+    MB_FAIL(-1, "bad argument");
+  for (int32_t g = 0; g < n_pred; ++g)
+    if (pred_index[g] < 0 || pred_index[g] >= c->U) MB_FAIL(-1, "pred_index out of range");
+  const int nmax = c->db.nmax;
+  const size_t per_task = (size_t)K * ((size_t)nmax * nmax + nmax);
+  // tasks are processed in chunks so that the Gamma^-1 table and the outputs stay bounded
+  int64_t chunk = (int64_t)(((size_t)1 << 30) / (per_task * 8 + (size_t)n_pred * 8 * (2 + (pred_mean_k ? 2 * K : 0))));
+  if (chunk < 1) chunk = 1;
+  if (chunk > M) chunk = M;
+  if (chunk > 65535) chunk = 65535;
+  DBuf d_hp, d_tau, d_xp, d_pi, d_g, d_m, d_v, d_mk, d_vk, d_ret;
+  int rc = 0;
+  if (d_hp.ensure((size_t)M * P * 8) || (K > 1 && d_tau.ensure((size_t)M * K * 8)) || d_xp.ensure((size_t)n_pred * D * 8) ||
+      d_pi.ensure((size_t)n_pred * 4) || d_g.ensure((size_t)chunk * per_task * 8) || d_m.ensure((size_t)M * n_pred * 8) ||
+      d_v.ensure((size_t)M * n_pred * 8) || d_ret.ensure((size_t)M * K * 4) ||
+      (pred_mean_k && (d_mk.ensure((size_t)M * K * n_pred * 8) || d_vk.ensure((size_t)M * K * n_pred * 8)))) rc = -3;
+  auto cleanup = [&]() { d_hp.release(); d_tau.release(); d_xp.release(); d_pi.release(); d_g.release(); d_m.release();
+                         d_v.release(); d_mk.release(); d_vk.release(); d_ret.release(); };
+  if (rc) { cleanup(); return rc; }
+  cudaMemcpyAsync(d_hp.p, hp, (size_t)M * P * 8, cudaMemcpyHostToDevice, c->st);
+  if (K > 1) cudaMemcpyAsync(d_tau.p, tau, (size_t)M * K * 8, cudaMemcpyHostToDevice, c->st);
+  cudaMemcpyAsync(d_xp.p, x_pred, (size_t)n_pred * D * 8, cudaMemcpyHostToDevice, c->st);
+  cudaMemcpyAsync(d_pi.p, pred_index, (size_t)n_pred * 4, cudaMemcpyHostToDevice, c->st);
+  TaskPredArgs a;
+  memset(&a, 0, sizeof(a));
+  a.db = c->db; a.kd = make_devkern(kern); a.hp = d_hp.as<double>(); a.hp_stride = P;
+  a.hpst.K = K; a.hpst.U = c->U; a.hpst.mean = c->hpr_mean.as<double>(); a.hpst.cov = c->hpr_cov.as<double>();
+  a.tau = K > 1 ? d_tau.as<double>() : nullptr; a.pen = pen_diag; a.n_pred = n_pred;
+  a.x_pred = d_xp.as<double>(); a.pred_index = d_pi.as<int32_t>(); a.ginv = d_g.as<double>();
+  a.out_mean = d_m.as<double>(); a.out_var = d_v.as<double>();
+  a.out_mean_k = pred_mean_k ? d_mk.as<double>() : nullptr; a.out_var_k = pred_var_k ? d_vk.as<double>() : nullptr;
+  a.retries = d_ret.as<int32_t>();
+  cudaError_t e = cudaSuccess;
+  for (int64_t t0 = 0; t0 < M && e == cudaSuccess; t0 += chunk) {
+    a.t0 = t0;
+    e = launch_task_pred(a, (int)std::min<int64_t>(chunk, M - t0), c->st);
+    c->launches += 2;
+  }
+  std::vector<int32_t> hret((size_t)M * K);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pred_mean, d_m.p, (size_t)M * n_pred * 8, cudaMemcpyDeviceToHost, c->st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pred_var, d_v.p, (size_t)M * n_pred * 8, cudaMemcpyDeviceToHost, c->st);
+  if (e == cudaSuccess && pred_mean_k) e = cudaMemcpyAsync(pred_mean_k, d_mk.p, (size_t)M * K * n_pred * 8, cudaMemcpyDeviceToHost, c->st);
+  if (e == cudaSuccess && pred_var_k) e = cudaMemcpyAsync(pred_var_k, d_vk.p, (size_t)M * K * n_pred * 8, cudaMemcpyDeviceToHost, c->st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(hret.data(), d_ret.p, (size_t)M * K * 4, cudaMemcpyDeviceToHost, c->st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
+  cleanup();
+  if (e != cudaSuccess) { mb_set_error(__FILE__, __LINE__, cudaGetErrorString(e)); return -2; }
+  int bad = 0;
+  for (size_t i = 0; i < hret.size(); ++i) { if (retries) retries[i] = hret[i]; if (hret[i] < 0) bad = 1; }
+  if (bad) MB_FAIL(1, "chol_inv_jitter: no positive-definite jitter found for at least one new task");
+  return 0;
 }
 
 extern "C" int mb_logL_GP_mod_tasks(mb_context* c, const mb_kernel* kern_i, const double* hp_i,

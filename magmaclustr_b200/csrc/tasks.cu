@@ -100,6 +100,7 @@ extern __shared__ double4 task_smem_raw[];
 
 __global__ void __launch_bounds__(256) k_task_objective(TaskObjArgs a) {
   const int64_t t = a.active ? a.active[blockIdx.x] : blockIdx.x;
+  if (a.lb && !a.lb[t].active) return;
   const int64_t row0 = a.db.offs[t];
   const int n = (int)(a.db.offs[t + 1] - row0);
   const int ld = a.ld, D = a.db.D, P = a.kd.n_hp, K = a.hpst.K, U = a.hpst.U;
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(256) k_task_objective(TaskObjArgs a) {
           v = v + tau * (mk[s.gi[i]] * mk[s.gi[j]] + ck[(size_t)s.gi[i] * U + s.gi[j]]);
         }
       } else {
-        v = a.hpst.cov[(size_t)s.gi[i] * U + s.gi[j]];
+        v = a.hpst.cov ? a.hpst.cov[(size_t)s.gi[i] * U + s.gi[j]] : 0.0;   // NULL: post_cov = 0 (sum_logL_GP)
       }
       s.C[i * ld + j] = v;
     }
@@ -322,6 +323,122 @@ __global__ void k_task_cov(TaskData db, DevKern kd, const double* hp, int64_t hp
 }
 
 // ---------------------------------------------------------------------------------------
+// pred_magma / pred_magmaclust batched over new tasks (/root/reference/R/prediction.R:1146-1197, 2319-2404).
+// Step 1, one CTA per (task, cluster): Gamma = K(x; hp) + cov_k[t, t] (+ jitter), Gamma^-1 by chol_inv_jitter,
+// alpha = Gamma^-1 (y - mean_k[t]); both go to a scratch table in HBM (n_tasks x K x (nmax^2 + nmax) doubles).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_task_pred_prepare(TaskPredArgs a) {
+  const int64_t t = a.t0 + blockIdx.x / a.hpst.K;
+  const int k = blockIdx.x % a.hpst.K;
+  const int64_t row0 = a.db.offs[t];
+  const int n = (int)(a.db.offs[t + 1] - row0);
+  const int ld = a.ld, D = a.db.D, P = a.kd.n_hp, U = a.hpst.U, nmax = a.db.nmax;
+  TaskSmem s = carve((double*)task_smem_raw, nmax, ld, D);
+  double hp[MB_MAX_HP];
+  for (int p = 0; p < P; ++p) hp[p] = a.hp[t * a.hp_stride + p];
+  load_task(s, a.db, row0, n);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const double* mk = a.hpst.mean + (size_t)k * U;
+  const double* ck = a.hpst.cov + (size_t)k * U * U;
+  for (int e = tid; e < n * n; e += nt) {
+    const int i = e / n, j = e % n;
+    s.C[i * ld + j] = ck[(size_t)s.gi[i] * U + s.gi[j]];
+  }
+  for (int i = tid; i < n; i += nt) s.rv[i] = s.yv[i] - mk[s.gi[i]];
+  __syncthreads();
+  double ldchol;
+  const int retries = task_inverse(s, n, ld, D, a.kd, hp, s.C, a.pen, &ldchol);
+  if (a.retries && tid == 0) a.retries[t * a.hpst.K + k] = retries;
+  double* G = a.ginv + ((size_t)(blockIdx.x)) * ((size_t)nmax * nmax + nmax);
+  if (retries < 0) {
+    for (int e = tid; e < n * n + n; e += nt) G[e] = NAN;
+    return;
+  }
+  blk_gemv(s.al, s.A, s.rv, n, ld);
+  for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e % n; G[e] = s.A[i * ld + j]; }
+  for (int i = tid; i < n; i += nt) G[(size_t)n * n + i] = s.al[i];
+}
+
+// Step 2, one CTA per (block of PRED_T grid points, task): every thread owns one prediction point g.
+//   kv_i  = k(x_i, xp_g) without noise (prediction.R:1155-1156)                       -- once, shared by the clusters
+//   c_i   = kv_i + cov_k[t_i, g]                    mean_k = mean_k[g] + c' alpha_k    (prediction.R:1174-1186)
+//   var_k = k(xp_g, xp_g) + cov_k[g, g] - c' Gamma_k^-1 c + exp(noise)                 (prediction.R:1189-1197)
+//   K > 1: mean = sum_k tau_k mean_k ; var = sum_k tau_k (var_k + (mean_k - mean)^2)   (prediction.R:2386-2404)
+// Gamma^-1 and alpha sit in shared memory (every lane reads the same entry: broadcast), kv / c are per-thread
+// arrays in local memory (lane-interleaved by the hardware, i.e. unit stride across the warp).
+#define PRED_T 128
+__global__ void __launch_bounds__(PRED_T) k_task_pred_apply(TaskPredArgs a) {
+  extern __shared__ double pred_sh[];
+  const int64_t t = a.t0 + blockIdx.y;
+  const int64_t row0 = a.db.offs[t];
+  const int n = (int)(a.db.offs[t + 1] - row0);
+  const int D = a.db.D, P = a.kd.n_hp, U = a.hpst.U, K = a.hpst.K, nmax = a.db.nmax;
+  const int lda = n | 1;
+  double* A = pred_sh;                       // n x lda
+  double* al = A + (size_t)nmax * (nmax | 1);
+  double* xo = al + nmax;                    // n x D
+  int* gi = (int*)(xo + (size_t)nmax * D);
+  const int tid = threadIdx.x;
+  const int g = blockIdx.x * PRED_T + tid;
+  const bool live = g < a.n_pred;
+  double hp[MB_MAX_HP], hpe[MB_MAX_HP];
+  for (int p = 0; p < P; ++p) hp[p] = a.hp[t * a.hp_stride + p];
+  prep_hp(a.kd, hp, hpe);
+  for (int e = tid; e < n * D; e += PRED_T) xo[e] = a.db.X[row0 * D + e];
+  for (int i = tid; i < n; i += PRED_T) gi[i] = a.db.gidx[row0 + i];
+  const int pg = live ? a.pred_index[g] : 0;
+  const double* xp = a.x_pred + (size_t)(live ? g : 0) * D;
+  __syncthreads();
+  double kv[TK_MAXN], cv[TK_MAXN];
+  for (int i = 0; i < n; ++i) kv[i] = cov_eval<false>(a.kd, hp, hpe, xo + i * D, xp, D, false, nullptr);
+  const double kpp = cov_eval<false>(a.kd, hp, hpe, xp, xp, D, false, nullptr);
+  const double noise = a.kd.has_noise ? hpe[P - 1] : 0.0;
+  double mean_k[MB_MAX_CLUSTERS], var_k[MB_MAX_CLUSTERS];
+  for (int k = 0; k < K; ++k) {
+    const double* G = a.ginv + ((size_t)(blockIdx.y) * K + k) * ((size_t)nmax * nmax + nmax);
+    __syncthreads();
+    for (int e = tid; e < n * n; e += PRED_T) { const int i = e / n, j = e - i * n; A[i * lda + j] = G[e]; }
+    for (int i = tid; i < n; i += PRED_T) al[i] = G[(size_t)n * n + i];
+    __syncthreads();
+    const double* mk = a.hpst.mean + (size_t)k * U;
+    const double* ck = a.hpst.cov + (size_t)k * U * U;
+    double m = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double c = kv[i] + ck[(size_t)gi[i] * U + pg];   // symmetric: row t_i, unit stride across the warp in g
+      cv[i] = c;
+      m += c * al[i];
+    }
+    double q = 0.0;
+    for (int i = 0; i < n; ++i) {
+      double w = 0.0;
+      const double* Ai = A + i * lda;
+      for (int j = 0; j < n; ++j) w += Ai[j] * cv[j];
+      q += cv[i] * w;
+    }
+    mean_k[k] = mk[pg] + m;
+    var_k[k] = ((kpp + ck[(size_t)pg * U + pg]) - q) + noise;
+    if (live && a.out_mean_k) {
+      a.out_mean_k[((size_t)t * K + k) * a.n_pred + g] = mean_k[k];
+      a.out_var_k[((size_t)t * K + k) * a.n_pred + g] = var_k[k];
+    }
+  }
+  if (!live) return;
+  if (K == 1) {
+    a.out_mean[(size_t)t * a.n_pred + g] = mean_k[0];
+    a.out_var[(size_t)t * a.n_pred + g] = var_k[0];
+  } else {
+    double mm = 0.0, vv = 0.0;
+    for (int k = 0; k < K; ++k) mm = mm + a.tau[t * K + k] * mean_k[k];
+    for (int k = 0; k < K; ++k) {
+      const double d = mean_k[k] - mm;
+      vv = vv + a.tau[t * K + k] * (var_k[k] + d * d);
+    }
+    a.out_mean[(size_t)t * a.n_pred + g] = mm;
+    a.out_var[(size_t)t * a.n_pred + g] = vv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------
 static int pick_threads(int nmax) { return nmax <= 16 ? 64 : (nmax <= 32 ? 128 : 256); }
@@ -362,4 +479,21 @@ int task_max_ctas_per_sm(int nmax, int D) {
   cudaFuncSetAttribute(k_task_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_task_inverse, pick_threads(nmax), smem);
   return n > 0 ? n : 1;
+}
+
+cudaError_t launch_task_pred(TaskPredArgs a, int n_launch_tasks, cudaStream_t st) {
+  a.ld = task_pick_ld(a.db.nmax);
+  const size_t smem1 = task_smem_bytes(a.db.nmax, a.ld, a.db.D);
+  cudaError_t e = cudaFuncSetAttribute(k_task_pred_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+  if (e != cudaSuccess) return e;
+  k_task_pred_prepare<<<(unsigned)(n_launch_tasks * a.hpst.K), pick_threads(a.db.nmax), smem1, st>>>(a);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const size_t smem2 = ((size_t)a.db.nmax * (a.db.nmax | 1) + a.db.nmax + (size_t)a.db.nmax * a.db.D) * sizeof(double) +
+                       (size_t)a.db.nmax * sizeof(int) + 16;
+  e = cudaFuncSetAttribute(k_task_pred_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+  if (e != cudaSuccess) return e;
+  dim3 grid((unsigned)((a.n_pred + PRED_T - 1) / PRED_T), (unsigned)n_launch_tasks);
+  k_task_pred_apply<<<grid, PRED_T, smem2, st>>>(a);
+  return cudaGetLastError();
 }

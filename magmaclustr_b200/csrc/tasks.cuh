@@ -70,3 +70,24 @@ struct TaskInvArgs {       // E step / list_kern_to_inv
   int32_t* retries;
   int ld;
 };
+
+struct TaskPredArgs {      // pred_magma(clust) batched over the resident (new) tasks
+  TaskData db;
+  HyperPost hpst;            // resident hyper-posterior on the union grid (K clusters); tau unused here
+  DevKern kd;
+  const double* hp;          // n_tasks x n_hp
+  int64_t hp_stride;
+  const double* tau;         // n_tasks x K mixture probabilities of the new tasks (K > 1)
+  double pen;
+  int64_t t0;                // first task of this launch (the scratch table is indexed from t0)
+  int n_pred;
+  const double* x_pred;      // n_pred x D
+  const int32_t* pred_index; // n_pred: position of every prediction point in the union grid
+  double* ginv;              // scratch: launch tasks x K x (nmax^2 + nmax)
+  double* out_mean;          // n_tasks x n_pred
+  double* out_var;
+  double* out_mean_k;        // optional n_tasks x K x n_pred
+  double* out_var_k;
+  int32_t* retries;          // n_tasks x K
+  int ld;
+};

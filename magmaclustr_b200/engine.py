@@ -326,6 +326,44 @@ class Context:
                                     cov.ctypes.data_as(L._dp) if full_cov else None))
         return mean, var, cov
 
+    # ---- new tasks against a resident hyper-posterior (train_gp / pred_magma(clust) batched over tasks) ----------
+    def hyperpost_keep(self, keep=True):
+        check(L.lib().mb_hyperpost_keep(self._h, int(keep)))
+
+    def hyperpost_set(self, post_mean, post_cov=None):
+        pm = f64(np.atleast_2d(post_mean))
+        K, u = pm.shape
+        pc = None if post_cov is None else f64(np.asarray(post_cov, dtype=np.float64).reshape(K, u, u))
+        check(L.lib().mb_hyperpost_set(self._h, K, u, ptr(pm), ptr(pc) if pc is not None else None))
+
+    def logL_GP_tasks(self, k, hp, cluster=0, pen_diag=1e-10, shared=False, grad=True):
+        m = self.n_tasks
+        f = np.zeros(m)
+        g = np.zeros((m, k.n_hp)) if grad else None
+        r = np.zeros(m, dtype=np.int32)
+        check(L.lib().mb_logL_GP_tasks(self._h, C.byref(k), ptr(f64(hp)), 1 if shared else 0, int(cluster),
+                                       float(pen_diag), ptr(f), ptr(g) if grad else None, ptr(r)))
+        return f, g, r
+
+    def train_gp_tasks(self, k, hp, cluster=0, pen_diag=1e-10):
+        hp = f64(hp).copy()
+        stats = np.zeros(4, dtype=np.int64)
+        check(L.lib().mb_train_gp_tasks(self._h, C.byref(k), ptr(hp), int(cluster), float(pen_diag), ptr(stats)))
+        return hp, stats
+
+    def pred_magma_tasks(self, k, hp, x_pred, pred_index, tau=None, pen_diag=1e-10, per_cluster=False, K=1):
+        xp = f64(np.atleast_2d(np.asarray(x_pred, dtype=np.float64).T).T)
+        pi = np.ascontiguousarray(pred_index, dtype=np.int32)
+        m, g = self.n_tasks, xp.shape[0]
+        mean = np.zeros((m, g)); var = np.zeros((m, g))
+        mk = np.zeros((m, K, g)) if per_cluster else None
+        vk = np.zeros((m, K, g)) if per_cluster else None
+        r = np.zeros((m, K), dtype=np.int32)
+        check(L.lib().mb_pred_magma_tasks(self._h, C.byref(k), ptr(f64(hp)), ptr(f64(tau)) if tau is not None else None,
+                                          g, ptr(xp), ptr(pi), float(pen_diag), ptr(mean), ptr(var),
+                                          ptr(mk) if per_cluster else None, ptr(vk) if per_cluster else None, ptr(r)))
+        return mean, var, mk, vk, r
+
     # ---- MagmaClust ------------------------------------------------------------------------
     def ve_step(self, K, kk, hp_k, ki, hp_i, m_k, tau, prop_mixture=None, update=False, pen_diag=1e-10,
                 shared=False):

@@ -280,6 +280,16 @@ def train_magma(db, prior_mean, ini_hp_0, ini_hp_i, kern_0, kern_i, shared_hp=Tr
 
 
 # ---- prediction -------------------------------------------------------------
+def train_gp(X, y, mean, kern, ini_hp, post_cov, pen_diag=1e-10, return_info=False):
+    """training.R:78-287 (the optim call :263-274 and the NA fallback :277-284): HPs of one (new) task by
+    L-BFGS-B on logL_GP / gr_GP against the hyper-posterior (mean, post_cov) at the task's inputs."""
+    hp, res = _optim(ini_hp, lambda h: logL_GP(h, X, y, mean, kern, post_cov, pen_diag),
+                     lambda h: gr_GP(h, X, y, mean, kern, post_cov, pen_diag))
+    if any(not np.isfinite(v) for v in hp.values()):
+        hp = dict(ini_hp)
+    return (hp, res) if return_info else hp
+
+
 def hyperposterior(db, hp_0, hp_i, kern_0, kern_i, prior_mean, grid_X, pen_diag=1e-10):
     """prediction.R:467-727: E step re-evaluated on data U grid."""
     if grid_X is None:
