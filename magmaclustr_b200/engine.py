@@ -410,16 +410,19 @@ class Context:
                                          ptr(f64(tau)), ptr(f64(prop_mixture)), float(pen_diag), C.byref(out)))
         return out.value
 
-    def hyperposterior_clust(self, K, kk, hp_k, ki, hp_i, grid_X, grid_index, m_k, tau, pen_diag=1e-10, shared=False):
+    def hyperposterior_clust(self, K, kk, hp_k, ki, hp_i, grid_X, grid_index, m_k, tau, pen_diag=1e-10, shared=False,
+                             host_out=True):
+        """host_out=False (after hyperpost_keep(True)): the K x U x U result only stays on the device."""
         gX = f64(np.atleast_2d(np.asarray(grid_X, dtype=np.float64).T).T)
         gi = np.ascontiguousarray(grid_index, dtype=np.int32)
         u = gX.shape[0]
-        pm = np.zeros((K, u))
-        pc = np.zeros((K, u, u))
+        pm = np.zeros((K, u)) if host_out else None
+        pc = np.zeros((K, u, u)) if host_out else None
         mk = f64(np.broadcast_to(np.asarray(m_k, dtype=np.float64).reshape(K, -1), (K, u)))
         check(L.lib().mb_hyperposterior_clust(self._h, int(K), C.byref(kk), ptr(f64(hp_k)), C.byref(ki), ptr(f64(hp_i)),
                                               1 if shared else 0, u, ptr(gX), ptr(gi), ptr(mk), ptr(f64(tau)),
-                                              float(pen_diag), ptr(pm), ptr(pc)))
+                                              float(pen_diag), ptr(pm) if host_out else None,
+                                              ptr(pc) if host_out else None))
         return pm, pc
 
     def pred_magmaclust(self, K, k, hp, x_obs, y_obs, x_pred, mean_obs, mean_pred, cov_obs, cov_pred, cov_crossed,

@@ -1,0 +1,108 @@
+"""BASELINE config 5 end to end at full size: hyperposterior_clust re-evaluated on a 2-D 100 x 100 grid (U = 10 000,
+K clusters, kernel "RQ + PERIO"), then pred_magmaclust for 1000 new tasks on all 10 000 grid points in ONE call against the
+device-resident hyper-posterior (mb_hyperpost_keep + mb_pred_magma_tasks).  Wall-clock with host buffers in and out.
+--check: pulls the hyper-posterior back once and compares two new tasks on a subset of grid points with the oracle.
+usage: bench_c5.py [--tasks 1000] [--k 3] [--grid 100] [--check]"""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from magmaclustr_b200 import _lib as L
+from magmaclustr_b200.engine import Context
+from magmaclustr_b200.dataprep import Prepared, reference_keys, r_signif
+from magmaclustr_b200.simulate import ini_hp
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--tasks", type=int, default=1000)
+ap.add_argument("--train-tasks", type=int, default=200)
+ap.add_argument("--k", type=int, default=3)
+ap.add_argument("--grid", type=int, default=100)
+ap.add_argument("--n-obs", type=int, default=20)
+ap.add_argument("--check", action="store_true")
+args = ap.parse_args()
+KC, G1 = args.k, args.grid
+rng = np.random.default_rng(5)
+ax = np.linspace(0, 10, G1)
+grid = np.array([[a, b] for a in ax for b in ax])            # expand_grid(Input, Covariate)
+G = len(grid)
+KERN = "RQ + PERIO"
+
+
+def make_tasks(m, n, prefix, clusters):
+    ids, X, y = [], [], []
+    for t in range(m):
+        idx = rng.choice(G, size=n, replace=False)
+        x = grid[idx]
+        c = clusters[t]
+        f = (2.0 + c) * np.sin(0.6 * x[:, 0] + c) + 0.5 * (1 + c) * np.cos(0.9 * x[:, 1]) + 3.0 * c
+        ids += ["%s%05d" % (prefix, t)] * n
+        X.append(x)
+        y.append(f + 0.1 * rng.standard_normal(n))
+    return Prepared(np.array(ids), np.vstack(X), np.concatenate(y))
+
+
+cl_tr = rng.integers(0, KC, size=args.train_tasks)
+train = make_tasks(args.train_tasks, 30, "tr", cl_tr)
+train.set_grid(grid)
+assert train.grid_X.shape[0] == G, "training inputs must lie on the prediction grid"
+mix = np.zeros((train.n_tasks, KC)); mix[np.arange(train.n_tasks), cl_tr] = 1.0
+kk, ki = L.parse_kernel(KERN, False), L.parse_kernel(KERN, True)
+names_k, names_i = L.hp_names(kk), L.hp_names(ki)
+hk = ini_hp(KERN, [str(k) for k in range(KC)], False, False, 50)
+hp_k = hk[names_k].to_numpy(dtype=np.float64).copy()
+hp_k[:, names_k.index("rq_scale")] = np.abs(hp_k[:, names_k.index("rq_scale")]) + 0.5
+hi = ini_hp(KERN, ["x"], True, True, 51)
+hp_i_row = hi[names_i].to_numpy(dtype=np.float64)[0]
+hp_i_tr = np.tile(hp_i_row, (train.n_tasks, 1))
+
+ctx = Context(0)
+out = {"config": "C5: pred_magmaclust, grid %dx%d = %d points, %d new tasks x %d obs, K = %d, kernel %s" %
+                 (G1, G1, G, args.tasks, args.n_obs, KC, KERN)}
+ctx.upload_dataset(train.offs, train.X, train.y, train.grid_index, train.grid_X)
+ctx.hyperpost_keep(True)
+t0 = time.perf_counter()
+ctx.hyperposterior_clust(KC, kk, hp_k, ki, hp_i_tr, train.grid_X, train.grid_index, np.zeros((KC, 1)), mix, host_out=False)
+out["hyperposterior_clust_s"] = time.perf_counter() - t0
+t0 = time.perf_counter()
+ctx.hyperposterior_clust(KC, kk, hp_k, ki, hp_i_tr, train.grid_X, train.grid_index, np.zeros((KC, 1)), mix, host_out=False)
+out["hyperposterior_clust_warm_s"] = time.perf_counter() - t0
+out["hyperposterior_flops"] = 2.0 * KC * float(G) ** 3      # 2 K chol_inv_jitter of U x U at n^3 each
+out["hyperposterior_tflops_warm"] = out["hyperposterior_flops"] / out["hyperposterior_clust_warm_s"] / 1e12
+ctx.hyperpost_keep(False)
+
+cl_new = rng.integers(0, KC, size=args.tasks)
+new = make_tasks(args.tasks, args.n_obs, "nw", cl_new)
+gi_new = train.index_of(new.keys)
+hp_new = np.tile(hp_i_row, (new.n_tasks, 1))
+tau = rng.dirichlet(np.ones(KC), size=new.n_tasks)
+gp = r_signif(grid)
+kp = reference_keys(gp)
+op = np.argsort(kp, kind="stable")
+ip = train.index_of(kp[op])
+ctx.upload_dataset(new.offs, new.X, new.y, gi_new, train.grid_X)
+for rep in range(2):
+    l0 = ctx.launches
+    t0 = time.perf_counter()
+    mean, var, _, _, r = ctx.pred_magma_tasks(ki, hp_new, gp[op], ip, tau=tau, K=KC)
+    dt = time.perf_counter() - t0
+out["pred_magmaclust_1000_tasks_s"] = dt
+out["pred_launches"] = ctx.launches - l0
+out["predictions_per_s"] = new.n_tasks * G / dt
+out["max_jitter_retries"] = int(r.max())
+out["finite"] = bool(np.isfinite(mean).all() and np.isfinite(var).all())
+out["var_min"] = float(var.min())
+if args.check:
+    from oracle import magmaclust as OC
+    ctx.upload_dataset(train.offs, train.X, train.y, train.grid_index, train.grid_X)
+    pm, pc = ctx.hyperposterior_clust(KC, kk, hp_k, ki, hp_i_tr, train.grid_X, train.grid_index, np.zeros((KC, 1)), mix)
+    hyp = {"keys": [k.decode() for k in train.grid_keys], "mean": list(pm), "cov": list(pc)}
+    sub = np.sort(rng.choice(G, size=60, replace=False))
+    worst_m, worst_v = 0.0, 0.0
+    for t in (0, new.n_tasks // 2, new.n_tasks - 1):
+        sl = slice(new.offs[t], new.offs[t + 1])
+        o = OC.pred_magmaclust(new.X[sl], new.y[sl], gp[op][sub], KERN, dict(zip(names_i, hp_new[t])), hyp, tau[t])
+        oo = np.argsort(reference_keys(gp[op][sub]), kind="stable")      # the oracle returns its rows in key order
+        worst_m = max(worst_m, float(np.max(np.abs(mean[t][sub][oo] - o["Mean"]) / np.maximum(1.0, np.abs(o["Mean"])))))
+        worst_v = max(worst_v, float(np.max(np.abs(var[t][sub][oo] - o["Var"]) / np.maximum(1e-3, np.abs(o["Var"])))))
+    out["check_max_rel_mean"] = worst_m
+    out["check_max_rel_var"] = worst_v
+print(json.dumps(out))
