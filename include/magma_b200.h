@@ -292,6 +292,14 @@ int mb_logL_GP_tasks(mb_context*, const mb_kernel* kern, const double* hp, int h
  * maxit = 25) of logL_GP / gr_GP from hp[t, ] (n_tasks x n_hp, overwritten; a task whose result is not finite keeps
  * its initial values, :277-284).  stats as mb_m_step; mb_last_task_status gives convergence codes / counts. */
 int mb_train_gp_tasks(mb_context*, const mb_kernel* kern, double* hp, int cluster, double pen_diag, int64_t* stats);
+/* train_gp_clust (/root/reference/R/training.R:1923-2217) for every resident task at once against the K resident cluster
+ * hyper-posteriors: per task the reference's EM loop (M step optim(L-BFGS-B) of sum_logL_GP_clust / gr_sum_logL_GP_clust
+ * (R/likelihoods.R:349-398, R/gradients-likelihoods.R:192-227), E step update_mixture, monitoring with prop_mixture),
+ * each task stopping at its own iteration.  hp: n_tasks x n_hp in/out; prop_mixture: K; mixture_out: n_tasks x K;
+ * n_iter_out / converged_out (n_tasks) and stats may be NULL. */
+int mb_train_gp_clust_tasks(mb_context*, const mb_kernel* kern, double* hp, const double* prop_mixture, double pen_diag,
+                            int n_iter_max, double cv_threshold, double* mixture_out, int32_t* n_iter_out,
+                            int32_t* converged_out, int64_t* stats);
 /* pred_magma (K = 1) / pred_magmaclust (K > 1, tau = n_tasks x K mixture probabilities of the new tasks) on n_pred
  * points for every resident task (/root/reference/R/prediction.R:1146-1197, 2319-2404): pred_mean, pred_var are
  * n_tasks x n_pred row-major (Var includes exp(noise) like the reference's `Var` column); the optional

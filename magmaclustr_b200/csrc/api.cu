@@ -55,7 +55,7 @@ static int task_kernel_version() {
 }
 static cudaError_t launch_task_objective_any(TaskObjArgs a, int n_launch, cudaStream_t st) {
   const int v = task_kernel_version();
-  if (a.mode == TK_OBJ_MARG || v == 1) return launch_task_objective(a, n_launch, st);
+  if (a.mode == TK_OBJ_MARG || a.mode == TK_OBJ_MARG_MIX || v == 1) return launch_task_objective(a, n_launch, st);
   return v == 2 ? launch_task_objective2(a, n_launch, st) : launch_task_objective3(a, n_launch, st);
 }
 static cudaError_t launch_task_inverse_any(TaskInvArgs a, int n_ctas, cudaStream_t st) {
@@ -125,6 +125,7 @@ cudaError_t launch_lbfgsb_init(LbfgsbState* st, int64_t m, int n, const double* 
                                cudaStream_t s);
 cudaError_t launch_lbfgsb_advance(LbfgsbState* st, int64_t m, int n, const double* f,
                                   const double* g, int* n_active, cudaStream_t s);
+cudaError_t launch_lbfgsb_mask(LbfgsbState* st, int64_t m, const int32_t* skip, cudaStream_t s);
 cudaError_t launch_lbfgsb_export(const LbfgsbState* st, int64_t m, int n, double* x,
                                  int64_t x_stride, int* fail, int* nfgv, cudaStream_t s);
 
@@ -877,7 +878,8 @@ static int run_single_eval(mb_context* c, SingleProblem& sp, double pen, double*
 }
 
 static int optimise(mb_context* c, std::vector<SingleProblem>& singles, bool tasks_on,
-                    TaskObjArgs a, double* hp_i_dev, int P_i, double pen, int64_t* stats) {
+                    TaskObjArgs a, double* hp_i_dev, int P_i, double pen, int64_t* stats,
+                    const int32_t* skip_dev = nullptr) {
   const int64_t M = c->db.n_tasks;
   int rounds = 0;
   bool tasks_active = tasks_on;
@@ -886,6 +888,7 @@ static int optimise(mb_context* c, std::vector<SingleProblem>& singles, bool tas
     MB_TRY(c->counters.ensure(4096 * sizeof(int)));
     CU(cudaMemsetAsync(c->counters.p, 0, 4096 * sizeof(int), c->st));
     LAUNCH(c, launch_lbfgsb_init(c->lb.as<LbfgsbState>(), M, P_i, hp_i_dev, P_i, 1e13, 0.0, 25, c->st));
+    if (skip_dev) LAUNCH(c, launch_lbfgsb_mask(c->lb.as<LbfgsbState>(), M, skip_dev, c->st));
     a.lb = c->lb.as<LbfgsbState>();
     a.hp = nullptr;
     a.want_grad = 1;
@@ -1134,6 +1137,15 @@ extern "C" int mb_train_gp_tasks(mb_context* c, const mb_kernel* kern, double* h
   if (stats) for (int i = 0; i < 4; ++i) stats[i] = st4[i];
   return 0;
 }
+
+// train_gp_clust (/root/reference/R/training.R:1923-2217) for every resident task at once.  Each task runs the
+// reference's own EM loop -- M step: optim(L-BFGS-B) of sum_logL_GP_clust / gr_sum_logL_GP_clust with its current mixture;
+// E step: update_mixture with prop_mixture; monitoring: sum_logL_GP_clust(new_hp, new_mixture, prop_mixture) -- and stops
+// at its own iteration (|eps| < cv_threshold, a non-finite HP, or n_iter_max); tasks that have stopped are masked out of
+// the following lock-step M steps, so every task's iterates are those of a stand-alone call.
+extern "C" int mb_train_gp_clust_tasks(mb_context* c, const mb_kernel* kern, double* hp, const double* prop_mixture,
+                                       double pen_diag, int n_iter_max, double cv_threshold, double* mixture_out,
+                                       int32_t* n_iter_out, int32_t* converged_out, int64_t* stats);
 
 extern "C" int mb_pred_magma_tasks(mb_context* c, const mb_kernel* kern, const double* hp, const double* tau,
                                    int32_t n_pred, const double* x_pred, const int32_t* pred_index, double pen_diag,
@@ -1886,6 +1898,93 @@ extern "C" int mb_update_mixture(mb_context* c, int n_clusters, const mb_kernel*
   MB_TRY(put_hyperpost(c, n_clusters, post_mean, post_cov, nullptr));
   return dev_update_mixture(c, n_clusters, make_devkern(kern_i), c->hp_i.as<double>(), stride, c->pm.as<double>(),
                             c->pc.as<double>(), prop_mixture, pen_diag, tau_out);
+}
+
+extern "C" int mb_train_gp_clust_tasks(mb_context* c, const mb_kernel* kern, double* hp, const double* prop_mixture,
+                                       double pen_diag, int n_iter_max, double cv_threshold, double* mixture_out,
+                                       int32_t* n_iter_out, int32_t* converged_out, int64_t* stats) {
+  MB_TRY(need_hyperpost(c, 0, true));
+  if (!kern || !hp || !prop_mixture || !mixture_out || n_iter_max < 1) MB_FAIL(-1, "bad argument");
+  const int K = c->hpr_K, P = kern->n_hp;
+  const int64_t M = c->db.n_tasks;
+  MB_TRY(ensure_em_buffers(c, K));
+  DevKern kd = make_devkern(kern);
+  DBuf d_hp, d_tau, d_skip, d_fk;
+  int rc = 0;
+  if (d_hp.ensure((size_t)M * P * 8) || d_tau.ensure((size_t)M * K * 8) || d_skip.ensure((size_t)M * 4) ||
+      d_fk.ensure((size_t)M * K * 8)) rc = -3;
+  auto cleanup = [&]() { d_hp.release(); d_tau.release(); d_skip.release(); d_fk.release(); };
+  if (rc) { cleanup(); return rc; }
+  std::vector<double> cur_hp(hp, hp + (size_t)M * P), new_hp((size_t)M * P), mix((size_t)M * K), new_mix((size_t)M * K),
+      fk((size_t)M * K), LL(M, -INFINITY);
+  std::vector<int32_t> done(M, 0), iters(M, 0), conv(M, 0);
+  for (int64_t t = 0; t < M; ++t) for (int k = 0; k < K; ++k) mix[t * K + k] = prop_mixture[k];
+  int64_t tot_evals = 0, tot_rounds = 0;
+  auto fail = [&](int code) { cleanup(); return code; };
+  for (int it = 1; it <= n_iter_max; ++it) {
+    int64_t live = 0;
+    for (int64_t t = 0; t < M; ++t) live += !done[t];
+    if (!live) break;
+    // ---- M step on the live tasks
+    if (h2d(d_hp.p, cur_hp.data(), (size_t)M * P * 8, c->st) || h2d(d_tau.p, mix.data(), (size_t)M * K * 8, c->st) ||
+        h2d(d_skip.p, done.data(), (size_t)M * 4, c->st)) return fail(-2);
+    TaskObjArgs a = make_obj_args(c, kd, d_hp.as<double>(), P, TK_OBJ_MARG_MIX, 1, pen_diag, K, c->hpr_mean.as<double>(),
+                                  c->hpr_cov.as<double>(), d_tau.as<double>(), c->f_t.as<double>(), c->g_t.as<double>());
+    std::vector<SingleProblem> none;
+    int64_t st4[4] = {0, 0, 0, 0};
+    rc = optimise(c, none, true, a, d_hp.as<double>(), P, pen_diag, st4, d_skip.as<int32_t>());
+    if (rc) return fail(rc);
+    tot_rounds += st4[1]; tot_evals += st4[2];
+    if (d2h(new_hp.data(), d_hp.p, (size_t)M * P * 8, c->st) || cudaStreamSynchronize(c->st) != cudaSuccess) return fail(-2);
+    for (int64_t t = 0; t < M; ++t) {
+      if (done[t]) { for (int p = 0; p < P; ++p) new_hp[t * P + p] = cur_hp[t * P + p]; continue; }
+      bool bad = false;
+      for (int p = 0; p < P; ++p) if (!std::isfinite(new_hp[t * P + p])) bad = true;
+      if (bad) {   // training.R:2122-2129: stop, keep the last valid values
+        done[t] = 1;
+        for (int p = 0; p < P; ++p) new_hp[t * P + p] = cur_hp[t * P + p];
+      } else {
+        iters[t] = it;
+      }
+    }
+    // ---- E step (update_mixture with the new HPs) and the per-cluster marginal values for the monitoring
+    if (h2d(d_hp.p, new_hp.data(), (size_t)M * P * 8, c->st)) return fail(-2);
+    rc = dev_update_mixture(c, K, kd, d_hp.as<double>(), P, c->hpr_mean.as<double>(), c->hpr_cov.as<double>(),
+                            prop_mixture, pen_diag, new_mix.data());
+    if (rc) return fail(rc);
+    TaskObjArgs am = make_obj_args(c, kd, d_hp.as<double>(), P, TK_OBJ_MARG_MIX, 0, pen_diag, K, c->hpr_mean.as<double>(),
+                                   c->hpr_cov.as<double>(), d_tau.as<double>(), c->f_t.as<double>(), c->g_t.as<double>());
+    am.fk = d_fk.as<double>();
+    rc = launch_obj(c, am, (int)M, c->st);
+    if (rc) return fail(rc);
+    if (d2h(fk.data(), d_fk.p, (size_t)M * K * 8, c->st) || cudaStreamSynchronize(c->st) != cudaSuccess) return fail(-2);
+    for (int64_t t = 0; t < M; ++t) {
+      if (done[t]) continue;
+      // sum_logL_GP_clust with prop_mixture (likelihoods.R:378-396): sum_k [-tau_k logL_GP_k + tau_k log(pi_k / tau_k)]
+      long double acc = 0.0L;
+      for (int k = 0; k < K; ++k) {
+        const double tk = new_mix[t * K + k], pk = prop_mixture[k];
+        const double lf = (tk == 0.0 || pk == 0.0) ? 0.0 : log(pk / tk);
+        acc += (long double)(-(tk * fk[t * K + k]) + tk * lf);
+      }
+      const double nl = (double)acc;
+      double diff = nl - LL[t];
+      if (std::isnan(diff)) diff = -INFINITY;
+      for (int p = 0; p < P; ++p) cur_hp[t * P + p] = new_hp[t * P + p];
+      for (int k = 0; k < K; ++k) mix[t * K + k] = new_mix[t * K + k];
+      LL[t] = nl;
+      double eps = diff / fabs(nl);
+      if (std::isnan(eps)) eps = 1.0;
+      if (fabs(eps) < cv_threshold) { conv[t] = 1; done[t] = 1; }
+    }
+  }
+  cleanup();
+  for (size_t i = 0; i < cur_hp.size(); ++i) hp[i] = cur_hp[i];
+  for (size_t i = 0; i < mix.size(); ++i) mixture_out[i] = mix[i];
+  if (n_iter_out) for (int64_t t = 0; t < M; ++t) n_iter_out[t] = iters[t];
+  if (converged_out) for (int64_t t = 0; t < M; ++t) converged_out[t] = conv[t];
+  if (stats) { stats[0] = 0; stats[1] = tot_rounds; stats[2] = tot_evals; stats[3] = 0; }
+  return 0;
 }
 
 extern "C" int mb_ve_step(mb_context* c, int n_clusters, const mb_kernel* kern_k, const double* hp_k,

@@ -338,6 +338,18 @@ cudaError_t launch_lbfgsb_advance(LbfgsbState* st, int64_t m, int n, const doubl
   return cudaGetLastError();
 }
 
+// Problems whose skip flag is set never start: their state stays at x0 (what k_lbfgsb_export writes back) with no
+// evaluation counted.  Used by the batched train_gp_clust, where every new task runs its own EM loop and stops at its
+// own iteration (training.R:2098-2215).
+__global__ void k_lbfgsb_mask(LbfgsbState* st, int64_t m, const int32_t* skip) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < m && skip[t]) st[t].active = 0;
+}
+cudaError_t launch_lbfgsb_mask(LbfgsbState* st, int64_t m, const int32_t* skip, cudaStream_t s) {
+  k_lbfgsb_mask<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(st, m, skip);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_lbfgsb_export(const LbfgsbState* st, int64_t m, int n, double* x,
                                  int64_t x_stride, int* fail, int* nfgv, cudaStream_t s) {
   k_lbfgsb_export<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(st, m, n, x, x_stride, fail, nfgv);

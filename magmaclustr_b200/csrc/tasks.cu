@@ -113,6 +113,20 @@ __global__ void __launch_bounds__(256) k_task_objective(TaskObjArgs a) {
   load_task(s, a.db, row0, n);
   const int tid = threadIdx.x, nt = blockDim.x;
 
+  // TK_OBJ_MARG_MIX: the marginal value / gradient against each of the K cluster hyper-posteriors in turn, weighted by
+  // the task's mixture probabilities (likelihoods.R:349-398, gradients-likelihoods.R:192-227); every other mode: one pass.
+  const bool mixm = a.mode == TK_OBJ_MARG_MIX;
+  const int npass = mixm ? K : 1;
+  double f_tot = 0.0, g_tot[MB_MAX_HP];
+#pragma unroll
+  for (int p = 0; p < MB_MAX_HP; ++p) g_tot[p] = 0.0;
+  int retries_max = 0;
+  for (int kc = 0; kc < npass; ++kc) {
+  const double* hmean = a.hpst.mean + (mixm ? (size_t)kc * U : 0);
+  const double* hcov = a.hpst.cov ? a.hpst.cov + (mixm ? (size_t)kc * U * U : 0) : nullptr;
+  const double wk = mixm ? a.hpst.tau[t * K + kc] : 1.0;
+  const bool marg = a.mode == TK_OBJ_MARG || mixm;
+  __syncthreads();
   // gather S (post_cov block / c2) into C; r and c1 vectors
   const double* Sadd = nullptr;
   if (a.mode != TK_OBJ_MIX) {
@@ -128,7 +142,7 @@ __global__ void __launch_bounds__(256) k_task_objective(TaskObjArgs a) {
           v = v + tau * (mk[s.gi[i]] * mk[s.gi[j]] + ck[(size_t)s.gi[i] * U + s.gi[j]]);
         }
       } else {
-        v = a.hpst.cov ? a.hpst.cov[(size_t)s.gi[i] * U + s.gi[j]] : 0.0;   // NULL: post_cov = 0 (sum_logL_GP)
+        v = hcov ? hcov[(size_t)s.gi[i] * U + s.gi[j]] : 0.0;   // NULL: post_cov = 0 (sum_logL_GP)
       }
       s.C[i * ld + j] = v;
     }
@@ -140,21 +154,23 @@ __global__ void __launch_bounds__(256) k_task_objective(TaskObjArgs a) {
         s.c1[i] = c;
         s.rv[i] = s.yv[i];
       } else {
-        s.rv[i] = s.yv[i] - a.hpst.mean[s.gi[i]];
+        s.rv[i] = s.yv[i] - hmean[s.gi[i]];
       }
     }
     __syncthreads();
-    if (a.mode == TK_OBJ_MARG) Sadd = s.C;
+    if (marg) Sadd = s.C;
   }
 
   double ldchol;
   int retries = task_inverse(s, n, ld, D, a.kd, hp, Sadd, a.pen, &ldchol);
-  if (a.retries && tid == 0) a.retries[t] = retries;
+  if (retries > retries_max) retries_max = retries;
+  if (a.retries && tid == 0) a.retries[t] = retries < 0 ? retries : retries_max;
   if (retries < 0) {
     if (tid == 0) {
       if (a.mode == TK_OBJ_MIX) for (int k = 0; k < K; ++k) a.f[t * K + k] = NAN;
       else a.f[t] = NAN;
       if (a.want_grad) for (int p = 0; p < P; ++p) a.g[t * P + p] = NAN;
+      if (mixm && a.fk) for (int k = 0; k < K; ++k) a.fk[t * K + k] = NAN;
     }
     return;
   }
@@ -199,7 +215,7 @@ __global__ void __launch_bounds__(256) k_task_objective(TaskObjArgs a) {
       v[0] += s.rv[i] * s.al[i];
       if (a.mode == TK_OBJ_ELBO) v[2] += s.al[i] * s.c1[i];
     }
-    if (a.mode != TK_OBJ_MARG)
+    if (!marg)
       for (int e = tid; e < n * n; e += nt) {
         int i = e / n, j = e % n;
         v[1] += s.A[i * ld + j] * s.C[i * ld + j];
@@ -209,13 +225,19 @@ __global__ void __launch_bounds__(256) k_task_objective(TaskObjArgs a) {
       double f = 0.5 * (n * LOG_2PI - logdetA + v[0]);
       if (a.mode == TK_OBJ_MOD) f = f + 0.5 * v[1];
       if (a.mode == TK_OBJ_ELBO) f = f - v[2] + 0.5 * v[1];
-      a.f[t] = f;
+      if (mixm) {
+        if (a.fk) a.fk[t * K + kc] = f;
+        f_tot = f_tot + wk * f;
+        if (kc == npass - 1) a.f[t] = f_tot;
+      } else {
+        a.f[t] = f;
+      }
     }
   }
-  if (!a.want_grad) return;
+  if (!a.want_grad) { if (mixm) continue; return; }
 
   // common term W:  MOD  aa' + A S A - A ;  ELBO (a - 2b) a' + A c2 A - A ;  MARG aa' - A
-  if (a.mode != TK_OBJ_MARG) {
+  if (!marg) {
     blk_gemm_nn(s.B, s.C, s.A, n, ld);  // B = S A
     blk_gemm_nn(s.C, s.A, s.B, n, ld);  // C = A S A
   }
@@ -229,10 +251,10 @@ __global__ void __launch_bounds__(256) k_task_objective(TaskObjArgs a) {
     double lhs_i = s.al[i], lhs_j = s.al[j];
     if (a.mode == TK_OBJ_ELBO) { lhs_i -= 2 * s.be[i]; lhs_j -= 2 * s.be[j]; }
     double w = lhs_i * s.al[j] - s.A[i * ld + j];
-    if (a.mode != TK_OBJ_MARG) w += s.C[i * ld + j];
+    if (!marg) w += s.C[i * ld + j];
     if (i != j) {
       double w2 = lhs_j * s.al[i] - s.A[j * ld + i];
-      if (a.mode != TK_OBJ_MARG) w2 += s.C[j * ld + i];
+      if (!marg) w2 += s.C[j * ld + i];
       w += w2;
     }
     double dv[MB_MAX_HP];
@@ -245,8 +267,16 @@ __global__ void __launch_bounds__(256) k_task_objective(TaskObjArgs a) {
     for (int q = 0; q < 4; ++q) v[q] = (p0 + q < P) ? gacc[p0 + q] : 0.0;
     blk_reduce_sum<4>(v, s.red);
     if (tid == 0)
-      for (int q = 0; q < 4 && p0 + q < P; ++q) a.g[t * P + p0 + q] = -0.5 * v[q];
+      for (int q = 0; q < 4 && p0 + q < P; ++q) {
+        if (mixm) {
+          g_tot[p0 + q] = g_tot[p0 + q] + wk * (-0.5 * v[q]);
+          if (kc == npass - 1) a.g[t * P + p0 + q] = g_tot[p0 + q];
+        } else {
+          a.g[t * P + p0 + q] = -0.5 * v[q];
+        }
+      }
   }
+  }  // cluster passes
 }
 
 // ---------------------------------------------------------------------------------------

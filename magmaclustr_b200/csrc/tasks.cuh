@@ -11,7 +11,8 @@ enum {
   TK_OBJ_MOD = 0,    // logL_GP_mod / gr_GP_mod            likelihoods.R:155-174
   TK_OBJ_ELBO = 1,   // elbo_clust_multi_GP / gr_clust_..  elbos.R:18-55
   TK_OBJ_MARG = 2,   // logL_GP / gr_GP (K + S inverted)   likelihoods.R:73-86
-  TK_OBJ_MIX = 3     // update_mixture: K values of -logL_GP_mod per task
+  TK_OBJ_MIX = 3,    // update_mixture: K values of -logL_GP_mod per task
+  TK_OBJ_MARG_MIX = 4  // sum_logL_GP_clust / gr_sum_logL_GP_clust: sum_k tau_k logL_GP(.; mean_k, cov_k)   likelihoods.R:349-398
 };
 
 struct TaskData {          // resident dataset (device pointers)
@@ -52,6 +53,7 @@ struct TaskObjArgs {
   // here (L2 / HBM) and re-read by the gradient contraction instead of evaluating exp() a second time
   double* kcache;
   int64_t kcache_stride;
+  double* fk;                // TK_OBJ_MARG_MIX: optional n_tasks x K table of the per-cluster values logL_GP(.; k)
 };
 
 struct TaskInvArgs {       // E step / list_kern_to_inv

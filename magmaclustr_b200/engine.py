@@ -351,6 +351,18 @@ class Context:
         check(L.lib().mb_train_gp_tasks(self._h, C.byref(k), ptr(hp), int(cluster), float(pen_diag), ptr(stats)))
         return hp, stats
 
+    def train_gp_clust_tasks(self, k, hp, prop_mixture, pen_diag=1e-10, n_iter_max=25, cv_threshold=1e-3):
+        hp = f64(hp).copy()
+        prop = f64(prop_mixture)
+        K = prop.shape[0]
+        mix = np.zeros((self.n_tasks, K))
+        nit = np.zeros(self.n_tasks, dtype=np.int32)
+        cv = np.zeros(self.n_tasks, dtype=np.int32)
+        stats = np.zeros(4, dtype=np.int64)
+        check(L.lib().mb_train_gp_clust_tasks(self._h, C.byref(k), ptr(hp), ptr(prop), float(pen_diag), int(n_iter_max),
+                                              float(cv_threshold), ptr(mix), ptr(nit), ptr(cv), ptr(stats)))
+        return hp, mix, nit, cv, stats
+
     def pred_magma_tasks(self, k, hp, x_pred, pred_index, tau=None, pen_diag=1e-10, per_cluster=False, K=1):
         xp = f64(np.atleast_2d(np.asarray(x_pred, dtype=np.float64).T).T)
         pi = np.ascontiguousarray(pred_index, dtype=np.int32)

@@ -308,3 +308,57 @@ def pred_magmaclust(X_obs, y_obs, X_pred, kern, hp, hyperpost, proba, pen_diag=1
     for k, p in enumerate(preds):
         mixture_var = mixture_var + proba[k] * (p["Var"] + (p["Mean"] - mixture_mean) ** 2)
     return {"pred": preds, "Mean": mixture_mean, "Var": mixture_var, "keys": preds[0]["keys"], "X": preds[0]["X"]}
+
+
+def sum_logL_GP_clust(hp, X, y, mixture, mean_k, cov_k, kern, pen_diag, prop_mixture=None):
+    """likelihoods.R:349-398 for one task: mean_k / cov_k are the K hyper-posteriors at the task's inputs."""
+    terms = []
+    for k in range(len(mean_k)):
+        tau_k = mixture[k]
+        s = tau_k * M.logL_GP(hp, X, y, mean_k[k], kern, cov_k[k], pen_diag)
+        if prop_mixture is not None:
+            pi_k = prop_mixture[k]
+            log_frac = 0.0 if (tau_k == 0 or pi_k == 0) else math.log(pi_k / tau_k)
+            s = -s + tau_k * log_frac
+        terms.append(s)
+    return float(np.sum(np.array(terms, dtype=np.longdouble)))
+
+
+def gr_sum_logL_GP_clust(hp, X, y, mixture, mean_k, cov_k, kern, pen_diag):
+    """gradients-likelihoods.R:192-227."""
+    g = np.zeros(len(hp), dtype=np.longdouble)
+    for k in range(len(mean_k)):
+        g = g + mixture[k] * M.gr_GP(hp, X, y, mean_k[k], kern, cov_k[k], pen_diag)
+    return np.asarray(g, dtype=np.float64)
+
+
+def train_gp_clust(X, y, mean_k, cov_k, kern, ini_hp, prop_mixture, pen_diag=1e-10, n_iter_max=25, cv_threshold=1e-3):
+    """training.R:1923-2217 (EM loop :2098-2215) for one new task."""
+    hp = dict(ini_hp)
+    mixture = np.asarray(prop_mixture, dtype=np.float64).copy()
+    prop = np.asarray(prop_mixture, dtype=np.float64)
+    ll, cv, n_it, counts = -np.inf, False, 0, []
+    Kc = len(mean_k)
+    for it in range(1, n_iter_max + 1):
+        new_hp, res = M._optim(hp, lambda h: sum_logL_GP_clust(h, X, y, mixture, mean_k, cov_k, kern, pen_diag),
+                               lambda h: gr_sum_logL_GP_clust(h, X, y, mixture, mean_k, cov_k, kern, pen_diag))
+        if any(not np.isfinite(v) for v in new_hp.values()):
+            break
+        counts.append(res["counts"])
+        n_it = it
+        L = np.array([-M.logL_GP_mod(new_hp, X, y, mean_k[k], kern, cov_k[k], pen_diag) for k in range(Kc)])
+        w = prop * np.exp(L - L.max())
+        w = w / w.sum()
+        new_mixture = np.array([r_round(v, 5) for v in w])
+        new_ll = sum_logL_GP_clust(new_hp, X, y, new_mixture, mean_k, cov_k, kern, pen_diag, prop)
+        diff = new_ll - ll
+        if np.isnan(diff):
+            diff = -np.inf
+        hp, mixture, ll = new_hp, new_mixture, new_ll
+        eps = diff / abs(ll)
+        if np.isnan(eps):
+            eps = 1.0
+        if abs(eps) < cv_threshold:
+            cv = True
+            break
+    return {"hp": hp, "mixture": mixture, "n_iter": n_it, "converged": cv, "logL": ll, "counts": counts}

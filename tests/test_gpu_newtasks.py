@@ -154,3 +154,40 @@ def test_pred_magmaclust_tasks(ctx):
         np.testing.assert_allclose(mean[t], o["Mean"], rtol=1e-8, atol=1e-8)
         np.testing.assert_allclose(var[t], o["Var"], rtol=1e-7, atol=1e-9)
     assert np.all(var >= 0) and np.all(r == 0)
+
+
+def test_train_gp_clust_tasks(ctx):
+    """train_gp_clust of several new tasks in one call: every task runs its own EM loop (M step L-BFGS-B on
+    sum_logL_GP_clust, E step update_mixture, monitoring) and stops at its own iteration -- same iteration counts,
+    convergence flags and mixtures as the oracle's stand-alone loop, HPs to 1e-6."""
+    KC = 3
+    case = make_case(12, 10, 4, shared=True, K=KC)
+    upload(ctx, case)
+    rng = np.random.default_rng(4)
+    lab = rng.integers(0, KC, size=12)
+    mix = np.zeros((12, KC))
+    mix[np.arange(12), lab] = 1.0
+    hp_k = np.array([[1.0 + 0.3 * k, -1.5 - 0.2 * k] for k in range(KC)])
+    new_prep, new_odb, hp_new, names = _new_tasks(78, [5, 10, 3, 8, 10, 2])
+    prep = case["prep"]
+    prep.set_grid(new_prep.X)
+    ctx.hyperpost_keep(True)
+    pm, pc = ctx.hyperposterior_clust(KC, case["k0"], hp_k, case["ki"], case["hpi"], prep.grid_X, prep.grid_index,
+                                      np.zeros((KC, 1)), mix)
+    ctx.hyperpost_keep(False)
+    gi = prep.index_of(new_prep.keys)
+    ctx.upload_dataset(new_prep.offs, new_prep.X, new_prep.y, gi, prep.grid_X)
+    prop = mix.mean(axis=0)
+    hp_fit, mixture, nit, cv, stats = ctx.train_gp_clust_tasks(case["ki"], hp_new, prop)
+    its = []
+    for t, i in enumerate(new_prep.ids):
+        _, X, y = new_odb.tasks[i]
+        idx = gi[new_prep.offs[t]:new_prep.offs[t + 1]]
+        o = OC.train_gp_clust(X, y, [pm[k][idx] for k in range(KC)], [pc[k][np.ix_(idx, idx)] for k in range(KC)], "SE",
+                              dict(zip(names, hp_new[t])), prop)
+        its.append(o["n_iter"])
+        assert nit[t] == o["n_iter"] and bool(cv[t]) == o["converged"], (t, nit[t], o["n_iter"], cv[t], o["converged"])
+        np.testing.assert_allclose(mixture[t], o["mixture"], atol=2e-5)
+        np.testing.assert_allclose(hp_fit[t], [o["hp"][n] for n in names], rtol=1e-6, atol=1e-7)
+    assert stats[2] > 0
+    print("EM iterations per task", its)
