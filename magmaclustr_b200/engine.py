@@ -363,7 +363,7 @@ class Context:
                                               float(cv_threshold), ptr(mix), ptr(nit), ptr(cv), ptr(stats)))
         return hp, mix, nit, cv, stats
 
-    def pred_magma_tasks(self, k, hp, x_pred, pred_index, tau=None, pen_diag=1e-10, per_cluster=False, K=1):
+    def pred_magma_tasks(self, k, hp, x_pred, pred_index, tau=None, pen_diag=1e-10, per_cluster=False, K=1, strict=True):
         xp = f64(np.atleast_2d(np.asarray(x_pred, dtype=np.float64).T).T)
         pi = np.ascontiguousarray(pred_index, dtype=np.int32)
         m, g = self.n_tasks, xp.shape[0]
@@ -371,9 +371,11 @@ class Context:
         mk = np.zeros((m, K, g)) if per_cluster else None
         vk = np.zeros((m, K, g)) if per_cluster else None
         r = np.zeros((m, K), dtype=np.int32)
-        check(L.lib().mb_pred_magma_tasks(self._h, C.byref(k), ptr(f64(hp)), ptr(f64(tau)) if tau is not None else None,
-                                          g, ptr(xp), ptr(pi), float(pen_diag), ptr(mean), ptr(var),
-                                          ptr(mk) if per_cluster else None, ptr(vk) if per_cluster else None, ptr(r)))
+        rc = L.lib().mb_pred_magma_tasks(self._h, C.byref(k), ptr(f64(hp)), ptr(f64(tau)) if tau is not None else None,
+                                         g, ptr(xp), ptr(pi), float(pen_diag), ptr(mean), ptr(var),
+                                         ptr(mk) if per_cluster else None, ptr(vk) if per_cluster else None, ptr(r))
+        if rc != 1 or strict:    # status 1: some task's matrix never factored -- its rows are NaN and r[t, k] = -1
+            check(rc)
         return mean, var, mk, vk, r
 
     # ---- MagmaClust ------------------------------------------------------------------------
