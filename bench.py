@@ -183,7 +183,7 @@ def main():
     import torch
     from magmaclustr_b200 import _lib as L
     from magmaclustr_b200.engine import Context
-    from magmaclustr_b200.parallel import shard_tasks, make_allreduce
+    from magmaclustr_b200.parallel import shard_tasks, make_allreduce, init_library_nccl
 
     torch.cuda.set_device(local_rank)
     dist = None
@@ -206,7 +206,10 @@ def main():
     gX_h, _k4 = pinned(prep.grid_X)
     hpi_loc = np.ascontiguousarray(hpi[lo:hi_])
     if world > 1:
-        ctx.set_allreduce(make_allreduce(dist), rank, world)
+        if os.environ.get("MB_ALLREDUCE", "nccl") == "hook":
+            ctx.set_allreduce(make_allreduce(dist), rank, world)      # torch.distributed does the all-reduce
+        else:
+            init_library_nccl(ctx, dist, rank, world)                 # the library's own NCCL communicator
     ctx.upload_dataset(offs, X_h, y_h, gi_h, gX_h)
     m0 = np.zeros(ctx.U)
     ctx.set_state(k0, hp0, ki, hpi_loc, m0)

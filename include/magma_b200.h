@@ -71,6 +71,13 @@ int64_t mb_launch_count(mb_context* ctx);
  * must return 0 and leave the reduced values in place. */
 typedef int (*mb_allreduce_fn)(void* user, void* dev_ptr, int64_t count);
 int mb_set_allreduce(mb_context* ctx, mb_allreduce_fn fn, void* user, int rank, int world);
+/* NCCL owned by the library (the E step's union-grid sums, the shared-HP objective and the monitoring
+ * scalar are summed over the ranks).  Rank 0 calls mb_nccl_unique_id (128 bytes) and the host program distributes the id
+ * by whatever channel it has (MPI, a file, torch.distributed ...); every rank then calls mb_nccl_init with its own
+ * context.  The all-reduces are enqueued on the library's streams (ncclAllReduce, ncclDouble, ncclSum) -- no host round
+ * trip.  libnccl.so.2 is resolved with dlopen, so single-GPU users need no NCCL at all. */
+int mb_nccl_unique_id(char* id_out, int bytes);
+int mb_nccl_init(mb_context* ctx, const char* id, int bytes, int rank, int world);
 
 /* ---- the five legacy builders: /root/reference/src/code.cpp, src/init.c:17-24 ----------
  * m1 is n1 x d, m2 is n2 x d, out is n1 x n2, all column-major (R numeric matrices). */

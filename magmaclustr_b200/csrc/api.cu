@@ -12,6 +12,9 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is resolved with dlopen at mb_nccl_init (no link-time dependency)
+
 #include "common.cuh"
 #include "lbfgsb.h"
 #include "tasks.cuh"
@@ -217,7 +220,8 @@ struct mb_context {
   int64_t prof_launches = 0, prof_evals = 0;
   // tasks with more than TK_MAXN points: multi-stream pipelines of the large-matrix kernels (bigtasks.cu)
   BigTaskPool* big = nullptr;
-  // multi-GPU hook
+  // multi-GPU: NCCL communicator owned by the context (mb_nccl_init), or a caller-supplied hook
+  ncclComm_t nccl = nullptr;
   mb_allreduce_fn ar = nullptr;
   void* ar_user = nullptr;
   int rank = 0, world = 1;
@@ -270,8 +274,69 @@ static int prof_collect(mb_context* c) {
   return 0;
 }
 
+// NCCL entry points, resolved once from libnccl.so.2 (the copy already mapped into the process when the host program
+// uses one, e.g. torch's; the system library otherwise).
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    api.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.h) api.h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (api.h) {
+      api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.h, "ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.h, "ncclCommInitRank");
+      api.AllReduce = (decltype(api.AllReduce))dlsym(api.h, "ncclAllReduce");
+      api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.h, "ncclCommDestroy");
+      api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.h, "ncclGetErrorString");
+      if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) api.h = nullptr;
+    }
+  }
+  return api.h ? &api : nullptr;
+}
+
+extern "C" int mb_nccl_unique_id(char* id_out, int bytes) {
+  if (!id_out || bytes < (int)sizeof(ncclUniqueId)) MB_FAIL(-1, "id buffer must hold 128 bytes");
+  NcclApi* n = nccl_api();
+  if (!n) MB_FAIL(-5, "libnccl.so.2 not found");
+  ncclUniqueId id;
+  if (n->GetUniqueId(&id) != ncclSuccess) MB_FAIL(-5, "ncclGetUniqueId failed");
+  memcpy(id_out, &id, sizeof(id));
+  return 0;
+}
+
+extern "C" int mb_nccl_init(mb_context* c, const char* id, int bytes, int rank, int world) {
+  if (!c || !id || bytes < (int)sizeof(ncclUniqueId) || world < 1 || rank < 0 || rank >= world) MB_FAIL(-1, "bad argument");
+  NcclApi* n = nccl_api();
+  if (!n) MB_FAIL(-5, "libnccl.so.2 not found");
+  CU(cudaSetDevice(c->device));
+  if (c->nccl) { n->CommDestroy(c->nccl); c->nccl = nullptr; }
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof(uid));
+  ncclResult_t r = n->CommInitRank(&c->nccl, world, uid, rank);
+  if (r != ncclSuccess) { c->nccl = nullptr; MB_FAIL(-5, n->GetErrorString ? n->GetErrorString(r) : "ncclCommInitRank failed"); }
+  c->rank = rank; c->world = world;
+  return 0;
+}
+
+// In-place sum over the ranks of `count` doubles at `dev`: on the context's own communicator the all-reduce is
+// enqueued on `s` like any kernel (no host synchronisation); the caller-supplied hook needs the data complete first.
 static int ctx_allreduce(mb_context* c, void* dev, int64_t count, cudaStream_t s) {
-  if (c->world <= 1 || !c->ar) return 0;
+  if (c->world <= 1) return 0;
+  if (c->nccl) {
+    ncclResult_t r = nccl_api()->AllReduce(dev, dev, (size_t)count, ncclDouble, ncclSum, c->nccl, s);
+    if (r != ncclSuccess) MB_FAIL(-5, "ncclAllReduce failed");
+    return 0;
+  }
+  if (!c->ar) return 0;
   CU(cudaStreamSynchronize(s));
   if (c->ar(c->ar_user, dev, count) != 0) MB_FAIL(-5, "allreduce hook failed");
   return 0;
@@ -321,6 +386,7 @@ extern "C" int mb_destroy(mb_context* c) {
   c->st_hp_i.release();
   c->hpr_mean.release();
   c->hpr_cov.release();
+  if (c->nccl && nccl_api()) nccl_api()->CommDestroy(c->nccl);
   for (auto& ev : c->prof_ev) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);

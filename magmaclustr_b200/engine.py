@@ -35,6 +35,17 @@ class Context:
     def launches(self):
         return int(L.lib().mb_launch_count(self._h))
 
+    @staticmethod
+    def nccl_unique_id():
+        """128-byte NCCL id created by the library on the calling rank (rank 0 by convention)."""
+        buf = C.create_string_buffer(128)
+        check(L.lib().mb_nccl_unique_id(buf, 128))
+        return buf.raw
+
+    def nccl_init(self, uid, rank, world):
+        """Join the library-owned NCCL communicator: all-reduces then run on the library's streams."""
+        check(L.lib().mb_nccl_init(self._h, uid, len(uid), int(rank), int(world)))
+
     def set_allreduce(self, fn, rank, world):
         """fn(dev_ptr:int, count:int) -> None performs an in-place sum all-reduce."""
         def _cb(user, dev_ptr, count):

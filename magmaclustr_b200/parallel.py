@@ -34,3 +34,11 @@ def make_allreduce(dist):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         torch.cuda.synchronize()
     return hook
+
+
+def init_library_nccl(ctx, dist, rank, world):
+    """The library's own NCCL communicator (mb_nccl_init): rank 0 creates the id, torch.distributed only carries the
+    128 bytes to the other ranks."""
+    box = [ctx.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx.nccl_init(box[0], rank, world)
