@@ -299,6 +299,14 @@ int mb_logL_GP_tasks(mb_context*, const mb_kernel* kern, const double* hp, int h
  * maxit = 25) of logL_GP / gr_GP from hp[t, ] (n_tasks x n_hp, overwritten; a task whose result is not finite keeps
  * its initial values, :277-284).  stats as mb_m_step; mb_last_task_status gives convergence codes / counts. */
 int mb_train_gp_tasks(mb_context*, const mb_kernel* kern, double* hp, int cluster, double pen_diag, int64_t* stats);
+/* train_shared_gp (/root/reference/R/training.R:352-446), the default HP initialisation through precondition_hp
+ * (R/preconditioning.R:24-39): one HP vector shared by all resident tasks, L-BFGS-B (factr = 1e13, maxit, 100 in the
+ * reference) on sum_logL_GP (R/likelihoods.R:113-129) with optim's central-difference gradient (ndeps = 1e-3).
+ * hp: n_hp values in/out; mean: the scalar prior mean.  stats[0] = optimiser evaluations (each 1 + 2 n_hp launches over
+ * all tasks), stats[1] = optim's convergence code, stats[2] = task objective evaluations, stats[3] = 1 if the result
+ * was not finite (hp is then left at its initial values).  Sharded datasets: the sums are all-reduced. */
+int mb_train_shared_gp(mb_context*, const mb_kernel* kern, double* hp, double mean, double pen_diag, int maxit,
+                       int64_t* stats);
 /* train_gp_clust (/root/reference/R/training.R:1923-2217) for every resident task at once against the K resident cluster
  * hyper-posteriors: per task the reference's EM loop (M step optim(L-BFGS-B) of sum_logL_GP_clust / gr_sum_logL_GP_clust
  * (R/likelihoods.R:349-398, R/gradients-likelihoods.R:192-227), E step update_mixture, monitoring with prop_mixture),

@@ -95,6 +95,7 @@ _SIGS = {
     "mb_hyperpost_set": [_vp, C.c_int, C.c_int32, _dp, _dp],
     "mb_logL_GP_tasks": [_vp, _kp, _dp, C.c_int, C.c_int, C.c_double, _dp, _dp, _ip],
     "mb_train_gp_tasks": [_vp, _kp, _dp, C.c_int, C.c_double, _lp],
+    "mb_train_shared_gp": [_vp, _kp, _dp, C.c_double, C.c_double, C.c_int, _lp],
     "mb_train_gp_clust_tasks": [_vp, _kp, _dp, _dp, C.c_double, C.c_int, C.c_double, _dp, _ip, _ip, _lp],
     "mb_pred_magma_tasks": [_vp, _kp, _dp, _dp, C.c_int32, _dp, _ip, C.c_double, _dp, _dp, _dp, _dp, _ip],
     "mb_bench_hbm": [_vp, C.c_int, _kp, C.c_int, _dp, _dp],

@@ -1177,6 +1177,49 @@ extern "C" int mb_logL_GP_tasks(mb_context* c, const mb_kernel* kern, const doub
   return 0;
 }
 
+// train_shared_gp (/root/reference/R/training.R:352-446; the default initialisation through precondition_hp,
+// R/preconditioning.R:24-39): ONE HP vector shared by all resident tasks, optim(par, fn = sum_logL_GP, method = "L-BFGS-B",
+// factr = 1e13, maxit = 100) with NO analytic gradient -- optim's central differences (R src/library/stats/src/optim.c
+// fmingr: ndeps = 1e-3, df_i = (fn(x + eps e_i) - fn(x - eps e_i)) / (2 eps)), i.e. 1 + 2 P objective evaluations per
+// optimiser evaluation, each ONE launch over all tasks.  sum_logL_GP's terms are logL_GP with post_cov = 0 and a constant
+// mean (likelihoods.R:113-129), which is logL_GP_mod with S = 0: the DMMA kernel of the M step evaluates them.
+extern "C" int mb_train_shared_gp(mb_context* c, const mb_kernel* kern, double* hp, double mean, double pen_diag,
+                                  int maxit, int64_t* stats) {
+  MB_TRY(need_db(c, true));
+  if (!kern || !hp || maxit < 1) MB_FAIL(-1, "bad argument");
+  MB_TRY(ensure_em_buffers(c, 1));
+  const int P = kern->n_hp;
+  DevKern kd = make_devkern(kern);
+  CU(cudaMemsetAsync(c->pc.p, 0, (size_t)c->U * c->U * 8, c->st));
+  LAUNCH(c, launch_fill(c->U, mean, c->pm.as<double>(), c->st));
+  TaskObjArgs a = make_obj_args(c, kd, nullptr, 0, TK_OBJ_MOD, 0, pen_diag, 1, c->pm.as<double>(), c->pc.as<double>(),
+                                nullptr, c->f_t.as<double>(), c->g_t.as<double>());
+  LbfgsbState s;
+  lb_init(&s, P, hp, 1e13, 0.0, maxit);
+  const double ndeps = 1e-3;
+  int64_t n_fn = 0;
+  while (s.active) {
+    double f, g[MB_MAX_HP], x[MB_MAX_HP], v1, v2;
+    for (int p = 0; p < P; ++p) x[p] = s.x[p];
+    MB_TRY(shared_obj_eval(c, a, x, P, 0, &f, nullptr));
+    for (int p = 0; p < P; ++p) {
+      x[p] = s.x[p] + ndeps;
+      MB_TRY(shared_obj_eval(c, a, x, P, 0, &v1, nullptr));
+      x[p] = s.x[p] - ndeps;
+      MB_TRY(shared_obj_eval(c, a, x, P, 0, &v2, nullptr));
+      g[p] = (v1 - v2) / (2 * ndeps);
+      x[p] = s.x[p];
+    }
+    n_fn += 1 + 2 * P;
+    lb_advance(&s, f, g);
+  }
+  bool bad = false;
+  for (int p = 0; p < P; ++p) if (!std::isfinite(s.x[p])) bad = true;
+  if (!bad) for (int p = 0; p < P; ++p) hp[p] = s.x[p];     // training.R:437-443: NA -> the initial values are returned
+  if (stats) { stats[0] = s.nfgv; stats[1] = s.fail; stats[2] = n_fn * c->db.n_tasks; stats[3] = bad; }
+  return 0;
+}
+
 extern "C" int mb_train_gp_tasks(mb_context* c, const mb_kernel* kern, double* hp, int cluster, double pen_diag,
                                  int64_t* stats) {
   MB_TRY(need_hyperpost(c, cluster, false));

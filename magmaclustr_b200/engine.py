@@ -362,6 +362,12 @@ class Context:
         check(L.lib().mb_train_gp_tasks(self._h, C.byref(k), ptr(hp), int(cluster), float(pen_diag), ptr(stats)))
         return hp, stats
 
+    def train_shared_gp(self, k, hp, mean=0.0, pen_diag=1e-10, maxit=100):
+        hp = f64(hp).copy()
+        stats = np.zeros(4, dtype=np.int64)
+        check(L.lib().mb_train_shared_gp(self._h, C.byref(k), ptr(hp), float(mean), float(pen_diag), int(maxit), ptr(stats)))
+        return hp, stats
+
     def train_gp_clust_tasks(self, k, hp, prop_mixture, pen_diag=1e-10, n_iter_max=25, cv_threshold=1e-3):
         hp = f64(hp).copy()
         prop = f64(prop_mixture)

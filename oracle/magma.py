@@ -290,6 +290,44 @@ def train_gp(X, y, mean, kern, ini_hp, post_cov, pen_diag=1e-10, return_info=Fal
     return (hp, res) if return_info else hp
 
 
+def sum_logL_GP(hp, db, mean, kern, pen_diag):
+    """likelihoods.R:113-129: sapply over the tasks %>% sum() (long double accumulation)."""
+    vals = [logL_GP(hp, db.tasks[i][1], db.tasks[i][2], mean, kern, 0.0, pen_diag) for i in db.ids]
+    return float(np.sum(np.array(vals, dtype=np.longdouble)))
+
+
+def train_shared_gp(db, mean, kern, ini_hp, pen_diag=1e-10, maxit=100, return_info=False):
+    """training.R:352-446: optim(par, fn = sum_logL_GP, method = "L-BFGS-B", factr = 1e13, maxit = 100) WITHOUT gr --
+    optim's own central differences (R src/library/stats/src/optim.c, fmingr: ndeps = 1e-3)."""
+    from .lbfgsb import optim_lbfgsb
+    names = list(ini_hp)
+    ndeps = 1e-3
+    n_fn = [0]
+
+    def fn(x):
+        n_fn[0] += 1
+        return sum_logL_GP(dict(zip(names, x)), db, mean, kern, pen_diag)
+
+    def fg(x):
+        f = fn(x)
+        g = []
+        for i in range(len(x)):
+            xp = list(x)
+            xp[i] = x[i] + ndeps
+            v1 = fn(xp)
+            xp[i] = x[i] - ndeps
+            v2 = fn(xp)
+            g.append((v1 - v2) / (2 * ndeps))
+        return f, g
+
+    res = optim_lbfgsb([ini_hp[k] for k in names], fg, factr=1e13, maxit=maxit)
+    hp = dict(zip(names, res["par"]))
+    if any(not np.isfinite(v) for v in hp.values()):
+        hp = dict(ini_hp)
+    res["fn_evals"] = n_fn[0]
+    return (hp, res) if return_info else hp
+
+
 def hyperposterior(db, hp_0, hp_i, kern_0, kern_i, prior_mean, grid_X, pen_diag=1e-10):
     """prediction.R:467-727: E step re-evaluated on data U grid."""
     if grid_X is None:

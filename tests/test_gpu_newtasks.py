@@ -191,3 +191,22 @@ def test_train_gp_clust_tasks(ctx):
         np.testing.assert_allclose(hp_fit[t], [o["hp"][n] for n in names], rtol=1e-6, atol=1e-7)
     assert stats[2] > 0
     print("EM iterations per task", its)
+
+
+def test_train_shared_gp(ctx):
+    """train_shared_gp / precondition_hp (training.R:352-446): one shared HP vector, L-BFGS-B with optim's central
+    differences on sum_logL_GP.  The finite-difference gradient divides the objective's rounding noise by 2e-3, so the
+    trajectories may part by an evaluation; both optima must be equally good and the HPs agree to 1e-4."""
+    case = make_case(8, 10, 31, shared=True)
+    upload(ctx, case)
+    ki, names = case["ki"], case["names_i"]
+    hp0 = case["hpi"][0]
+    hp_fit, stats = ctx.train_shared_gp(ki, hp0, mean=0.0, maxit=100)
+    ohp, res = OM.train_shared_gp(case["odb"], 0.0, "SE", dict(zip(names, hp0)), 1e-10, 100, return_info=True)
+    print("gpu", hp_fit, stats, "oracle", ohp, res["counts"], res["convergence"], res["value"])
+    f_gpu = OM.sum_logL_GP(dict(zip(names, hp_fit)), case["odb"], 0.0, "SE", 1e-10)
+    f_ini = OM.sum_logL_GP(dict(zip(names, hp0)), case["odb"], 0.0, "SE", 1e-10)
+    assert f_gpu < f_ini and abs(f_gpu - res["value"]) <= 1e-6 * abs(res["value"])
+    np.testing.assert_allclose(hp_fit, [ohp[n] for n in names], rtol=1e-4, atol=1e-5)
+    assert abs(int(stats[0]) - res["counts"]) <= 2 and stats[1] == res["convergence"]
+    assert stats[2] == stats[0] * (1 + 2 * len(names)) * 8
