@@ -38,6 +38,21 @@ METRIC = "train_magma EM steps/sec at M=10k,N=64"
 FLOPS_PER_EVAL = 5.0  # x N^3: chol+inverse N^3, S A and A (S A) 4 N^3; log-det read off the Cholesky diagonal
 
 
+def simu_db_c4(m, n):
+    from magmaclustr_b200.simulate import simu_db
+    return simu_db(M=m, N=n, common_input=True, seed=4096, pool=np.linspace(-1.0, 1.0, n))
+
+
+def Prepared4(*a):
+    from magmaclustr_b200.dataprep import Prepared
+    return Prepared(*a)
+
+
+def ini_hp4(*a):
+    from magmaclustr_b200.simulate import ini_hp
+    return ini_hp(*a)
+
+
 def make_inputs(m_tasks=M_TASKS):
     from magmaclustr_b200.dataprep import Prepared
     from magmaclustr_b200.simulate import simu_db, ini_hp
@@ -172,6 +187,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fit", action="store_true")
+    ap.add_argument("--no-c4", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -325,6 +341,28 @@ def main():
             ms_d = ctx.bench_dense(what, n_big, reps=3)
             bc.setdefault("dense_4096", {})[key] = {"ms": ms_d, "tflops": flops / ms_d / 1e9,
                                                     "frac_of_dgemm": flops / ms_d / 1e9 / peak if peak else None}
+        if not args.no_c4:
+            # BASELINE config 4 shape (common grid, N = U = 4096): one EM step over 8 of the 256 tasks -- the large
+            # factorisations batched over the library's streams, their trailing updates on FP64 DMMA
+            try:
+                m4, n4 = 8, 4096
+                df4, _ = simu_db_c4(m4, n4)
+                prep4 = Prepared4(df4.ID.values, df4.Input.values, df4.Output.values)
+                hp04 = ini_hp4("SE", ["0"], True, False, 6).drop(columns="ID").iloc[0].to_numpy(dtype=np.float64)
+                hpi4 = ini_hp4("SE", prep4.ids, False, True, 106).drop(columns="ID").to_numpy(dtype=np.float64)
+                ctx4 = Context(local_rank)
+                ctx4.upload_dataset(prep4.offs, prep4.X, prep4.y, prep4.grid_index, prep4.grid_X)
+                ctx4.set_state(k0, hp04, ki, hpi4, np.zeros(ctx4.U))
+                ctx4.em_step_resident(k0, ki, restart=True)          # warm-up: allocations
+                ctx4.timer_start()
+                ll4, st4 = ctx4.em_step_resident(k0, ki, restart=True)
+                ms4 = ctx4.timer_stop_ms()
+                tf4 = int(st4[2]) * FLOPS_PER_EVAL * float(n4) ** 3 / ms4 / 1e9
+                bc["c4_em_step_8_tasks_x_4096"] = {"ms": ms4, "task_evals": int(st4[2]), "tflops_5n3": tf4,
+                                                   "frac_of_dgemm": tf4 / peak if peak else None, "logL": ll4}
+                ctx4.close()
+            except Exception as e:      # the headline line must survive a failure of this side measurement
+                bc["c4_em_step_8_tasks_x_4096"] = {"error": str(e)[:200]}
         line["batched_chol"] = bc
         # HBM-bound kernels of the path: stand-alone covariance build and the E step's reduction,
         # device-only, against the measured copy bandwidth of MEASURED_PEAKS.json

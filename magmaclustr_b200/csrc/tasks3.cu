@@ -534,10 +534,10 @@ __device__ inline void load_task3(const Sm3& s, const TaskData& db, int64_t row0
 }
 
 // S(r, c): gathered post_cov block / corr2 of the ELBO (elbos.R:44-53)
-__device__ __forceinline__ double gather_S3(const TaskObjArgs& a, int64_t task, const int* gi, int r, int c, int n) {
+__device__ __forceinline__ double gather_S3(const TaskObjArgs& a, int mode, int64_t task, const int* gi, int r, int c, int n) {
   if (r >= n || c >= n) return 0.0;
   const int U = a.hpst.U;
-  if (a.mode == TK_OBJ_ELBO) {
+  if (mode == TK_OBJ_ELBO) {
     double v = 0.0;
     for (int k = 0; k < a.hpst.K; ++k) {
       const double* mk = a.hpst.mean + (size_t)k * U;
@@ -551,8 +551,11 @@ __device__ __forceinline__ double gather_S3(const TaskObjArgs& a, int64_t task, 
 
 extern __shared__ double4 task3_smem_raw[];
 
-template <int KS, int N8C, bool D1>
+// MODE_T >= 0: the objective mode as a compile-time constant (the M step's TK_OBJ_MOD is instantiated that way: no
+// mode branches in the gather / product loops, the ELBO and mixture code is not in the binary); -1: mode at run time.
+template <int KS, int N8C, bool D1, int MODE_T>
 __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_objective3(const __grid_constant__ TaskObjArgs a) {
+  const int mode = MODE_T >= 0 ? MODE_T : a.mode;
   const int64_t task = a.active ? a.active[blockIdx.x] : blockIdx.x;
   if (a.lb && !a.lb[task].active) return;
   const int64_t row0 = a.db.offs[task];
@@ -574,10 +577,10 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_objecti
   for (int i = tid; i < np; i += T3_THREADS) {
     double r = 0.0, c = 0.0;
     if (i < n) {
-      if (a.mode == TK_OBJ_ELBO) {
+      if (mode == TK_OBJ_ELBO) {
         for (int k = 0; k < K; ++k) c = c + a.hpst.tau[task * K + k] * a.hpst.mean[(size_t)k * U + s.gi[i]];
         r = s.yv[i];
-      } else if (a.mode != TK_OBJ_MIX) {
+      } else if (mode != TK_OBJ_MIX) {
         r = s.yv[i] - a.hpst.mean[s.gi[i]];
       }
     }
@@ -590,7 +593,7 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_objecti
   if (a.retries && tid == 0) a.retries[task] = retries;
   if (retries < 0) {
     if (tid == 0) {
-      if (a.mode == TK_OBJ_MIX) for (int k = 0; k < K; ++k) a.f[task * K + k] = NAN;
+      if (mode == TK_OBJ_MIX) for (int k = 0; k < K; ++k) a.f[task * K + k] = NAN;
       else a.f[task] = NAN;
       if (a.want_grad) for (int p = 0; p < P; ++p) a.g[task * P + p] = NAN;
     }
@@ -606,7 +609,7 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_objecti
     logdetA = blk_lu_logabsdet(s.T2, n, n, s.done);
   }
 
-  if (a.mode == TK_OBJ_MIX) {
+  if (mode == TK_OBJ_MIX) {
     // update_mixture: K values of logL_GP_mod with the same inverse (vem-magmaclust.R:344-381)
     double* V = s.T2;
     double* O = s.T2 + (size_t)MB_MAX_CLUSTERS * np;
@@ -640,7 +643,7 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_objecti
     return;
   }
 
-  if (a.mode == TK_OBJ_ELBO) gemv3<N8C, 2>(s, n8, s.vin, s.vout, L);
+  if (mode == TK_OBJ_ELBO) gemv3<N8C, 2>(s, n8, s.vin, s.vout, L);
   else gemv3<N8C, 1>(s, n8, s.vin, s.vout, L);
   T3_MARK(5);
 
@@ -654,8 +657,8 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_objecti
     for (int k = 0; k < N8C; ++k) {
       sa[2 * k] = 0.0; sa[2 * k + 1] = 0.0;
       if (k < n8) {
-        sa[2 * k] = gather_S3(a, task, s.gi, 8 * i + L.g, 8 * k + L.t, n);
-        sa[2 * k + 1] = gather_S3(a, task, s.gi, 8 * i + L.g, 8 * k + L.t + 4, n);
+        sa[2 * k] = gather_S3(a, mode, task, s.gi, 8 * i + L.g, 8 * k + L.t, n);
+        sa[2 * k + 1] = gather_S3(a, mode, task, s.gi, 8 * i + L.g, 8 * k + L.t + 4, n);
         double a0, a1;
         row.aop(k, a0, a1);
         tr += sa[2 * k] * a0 + sa[2 * k + 1] * a1;
@@ -689,14 +692,14 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_objecti
     double v[3] = {0.0, tr, 0.0};
     for (int i = tid; i < n; i += T3_THREADS) {
       v[0] += rv[i] * al[i];
-      if (a.mode == TK_OBJ_ELBO) v[2] += al[i] * c1v[i];
+      if (mode == TK_OBJ_ELBO) v[2] += al[i] * c1v[i];
     }
     T3_MARK(6);
     red3<3>(v, s.red);   // also orders the B writes before the reads below
     if (tid == 0) {
       double f = 0.5 * (n * LOG_2PI - logdetA + v[0]);
-      if (a.mode == TK_OBJ_MOD) f = f + 0.5 * v[1];
-      if (a.mode == TK_OBJ_ELBO) f = f - v[2] + 0.5 * v[1];
+      if (mode == TK_OBJ_MOD) f = f + 0.5 * v[1];
+      if (mode == TK_OBJ_ELBO) f = f - v[2] + 0.5 * v[1];
       a.f[task] = f;
     }
   }
@@ -748,7 +751,7 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_objecti
             const double tij = h ? (qq ? e1 : e0) : (qq ? c1 : c0);
             const double arc = qq ? av.y : av.x;
             double lr = al[r], lc = al[c];
-            if (a.mode == TK_OBJ_ELBO) { lr -= 2 * be[r]; lc -= 2 * be[c]; }
+            if (mode == TK_OBJ_ELBO) { lr -= 2 * be[r]; lc -= 2 * be[c]; }
             double w;
             if (r == c) w = lr * al[r] + tij - arc;
             else w = (lr * al[c] + lc * al[r]) + 2.0 * (tij - arc);
@@ -829,13 +832,19 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_inverse
 // ---- launchers --------------------------------------------------------------------------------------
 static inline bool is_se(const DevKern& kd) { return kd.n_terms == 1 && kd.types[0] == MB_KERN_SE; }
 
+template <int KS, int N8C, bool D1, int MODE_T>
+static cudaError_t launch_obj3_m(const TaskObjArgs& a, int n_launch, cudaStream_t st) {
+  const size_t smem = t3_smem_bytes<N8C>(a.db.D);
+  cudaError_t e = cudaFuncSetAttribute(k_task_objective3<KS, N8C, D1, MODE_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_task_objective3<KS, N8C, D1, MODE_T><<<n_launch, T3_THREADS, smem, st>>>(a);
+  return cudaGetLastError();
+}
 template <int KS, int N8C, bool D1>
 static cudaError_t launch_obj3_t(const TaskObjArgs& a, int n_launch, cudaStream_t st) {
-  const size_t smem = t3_smem_bytes<N8C>(a.db.D);
-  cudaError_t e = cudaFuncSetAttribute(k_task_objective3<KS, N8C, D1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  k_task_objective3<KS, N8C, D1><<<n_launch, T3_THREADS, smem, st>>>(a);
-  return cudaGetLastError();
+  // the M step / monitoring objective of train_magma on the SE fast path gets its own instantiation
+  if (KS == KS_SE && D1 && a.mode == TK_OBJ_MOD) return launch_obj3_m<KS, N8C, D1, (KS == KS_SE && D1) ? TK_OBJ_MOD : -1>(a, n_launch, st);
+  return launch_obj3_m<KS, N8C, D1, -1>(a, n_launch, st);
 }
 
 cudaError_t launch_task_objective3(TaskObjArgs a, int n_launch, cudaStream_t st) {
