@@ -557,9 +557,16 @@ template <int KS, int N8C, bool D1, int MODE_T>
 __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_objective3(const __grid_constant__ TaskObjArgs a) {
   const int mode = MODE_T >= 0 ? MODE_T : a.mode;
   const int64_t task = a.active ? a.active[blockIdx.x] : blockIdx.x;
-  if (a.lb && !a.lb[task].active) return;
+  // every load the prologue needs is issued before the first one is waited for: the optimiser state's `active` flag and
+  // HPs, the task's row range (three dependent L2 round trips otherwise), and the HP exponentials are evaluated while the
+  // table rows are on their way
+  const double* hp_src = a.lb ? a.lb[task].x : a.hp + task * a.hp_stride;
+  double hp_pre[3] = {0.0, 0.0, 0.0};
+  if (KS == KS_SE) { hp_pre[0] = hp_src[0]; hp_pre[1] = hp_src[1]; if (a.kd.has_noise) hp_pre[2] = hp_src[2]; }
+  const int is_active = a.lb ? a.lb[task].active : 1;
   const int64_t row0 = a.db.offs[task];
   const int n = (int)(a.db.offs[task + 1] - row0);
+  if (!is_active) return;
   const int D = a.db.D, P = a.kd.n_hp, K = a.hpst.K, U = a.hpst.U;
   const int n8 = t3_n8(n), np = 8 * n8, ntri = t3_ntri(n8);
   const Sm3 s = carve3<N8C>((double*)task3_smem_raw, D);
@@ -570,9 +577,9 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_objecti
   double* al = s.vout;
   double* be = s.vout + np;
   T3_MARK_DECL;
-  load_task3<N8C>(s, a.db, row0, n, np);
   Cov<KS, D1> cov;
-  cov.init(a.kd, a.lb ? a.lb[task].x : a.hp + task * a.hp_stride, s.xs, D);
+  cov.init(a.kd, KS == KS_SE ? hp_pre : hp_src, s.xs, D);
+  load_task3<N8C>(s, a.db, row0, n, np);
   T3_MARK(0);
   for (int i = tid; i < np; i += T3_THREADS) {
     double r = 0.0, c = 0.0;
