@@ -33,7 +33,7 @@ M_TASKS, N_POINTS = 10000, 64
 DATA_SEED, HP0_SEED, HPI_SEED = 2024, 6, 106
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-grid launch of the dominant kernel (10 000
 # evaluations), from the ncu --set full capture summarised in profiles/ (None until captured)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 144334080
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 143665920
 METRIC = "train_magma EM steps/sec at M=10k,N=64"
 FLOPS_PER_EVAL = 5.0  # x N^3: chol+inverse N^3, S A and A (S A) 4 N^3; log-det read off the Cholesky diagonal
 
@@ -318,7 +318,7 @@ def main():
         "e2e": {"value": args.steps / (e2e_total * 1e-3), "unit": "EM steps/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "k_task_objective3<SE,8,D1>", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "tensor", "kernel": "k_task_objective3<SE,8,D1,MOD>", "achieved": achieved, "peak": peak,
                      "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
                      "algorithmic_flops_per_eval": FLOPS_PER_EVAL * N_POINTS ** 3,
                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (no FP64 figure in MEASURED_PEAKS.json)",

@@ -818,11 +818,27 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_inverse
       for (int k = 0; k < K; ++k) {
         const double tau = a.tau ? a.tau[task * K + k] : 1.0;
         double* pk = pinv + (size_t)k * U * U;
-        for (int e = tid; e < n * n; e += T3_THREADS) {
-          const int i = e / n, j = e - i * n;
-          const size_t c = (size_t)s.gi[i] * U + s.gi[j];
-          const double v = bad ? NAN : symA_at<N8C>(s.T1, i, j);
-          pk[c] = pk[c] + (a.tau ? tau * v : v);
+        // read-modify-write of the CTA's own accumulator.  The grid positions of one task are distinct, so the targets
+        // of one task never alias: eight independent loads are issued before the first store (the compiler has to assume
+        // aliasing and would chain 32 L2 round trips per thread otherwise).  Same additions, same order per element.
+        for (int e0 = tid; e0 < n * n; e0 += 8 * T3_THREADS) {
+          size_t c[8];
+          double v[8], old[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int e = e0 + q * T3_THREADS;
+            c[q] = 0; v[q] = 0.0; old[q] = 0.0;
+            if (e < n * n) {
+              const int i = e / n, j = e - i * n;
+              c[q] = (size_t)s.gi[i] * U + s.gi[j];
+              const double x = bad ? NAN : symA_at<N8C>(s.T1, i, j);
+              v[q] = a.tau ? tau * x : x;
+              old[q] = pk[c[q]];
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (e0 + q * T3_THREADS < n * n) pk[c[q]] = old[q] + v[q];
         }
         double* wk = pw + (size_t)k * U;
         for (int i = tid; i < n; i += T3_THREADS) {
