@@ -1,8 +1,8 @@
 """BASELINE config 5 end to end at full size: hyperposterior_clust re-evaluated on a 2-D 100 x 100 grid (U = 10 000,
 K clusters, kernel "RQ + PERIO"), then pred_magmaclust for 1000 new tasks on all 10 000 grid points in ONE call against the
 device-resident hyper-posterior (mb_hyperpost_keep + mb_pred_magma_tasks).  Wall-clock with host buffers in and out.
---check: pulls the hyper-posterior back once and compares two new tasks on a subset of grid points with the oracle.
-usage: bench_c5.py [--tasks 1000] [--k 3] [--grid 100] [--check]"""
+The same pipeline is compared with the oracle on a sample of tasks / grid points in tests/test_gpu_fullsize.py.
+usage: bench_c5.py [--tasks 1000] [--k 3] [--grid 100]"""
 import argparse, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -17,7 +17,6 @@ ap.add_argument("--train-tasks", type=int, default=200)
 ap.add_argument("--k", type=int, default=3)
 ap.add_argument("--grid", type=int, default=100)
 ap.add_argument("--n-obs", type=int, default=20)
-ap.add_argument("--check", action="store_true")
 args = ap.parse_args()
 KC, G1 = args.k, args.grid
 rng = np.random.default_rng(5)
@@ -105,19 +104,4 @@ out["tasks_whose_matrix_never_factored"] = int((~ok_t).sum())
 out["finite"] = bool(np.isfinite(mean[ok_t]).all() and np.isfinite(var[ok_t]).all())
 out["var_min"] = float(var[ok_t].min())
 out["hp_fit_abs_max"] = float(np.abs(hp_new).max())
-if args.check:
-    from oracle import magmaclust as OC
-    ctx.upload_dataset(train.offs, train.X, train.y, train.grid_index, train.grid_X)
-    pm, pc = ctx.hyperposterior_clust(KC, kk, hp_k, ki, hp_i_tr, train.grid_X, train.grid_index, np.zeros((KC, 1)), mix)
-    hyp = {"keys": [k.decode() for k in train.grid_keys], "mean": list(pm), "cov": list(pc)}
-    sub = np.sort(rng.choice(G, size=60, replace=False))
-    worst_m, worst_v = 0.0, 0.0
-    for t in [int(v) for v in np.flatnonzero(ok_t)[[0, ok_t.sum() // 2, -1]]]:
-        sl = slice(new.offs[t], new.offs[t + 1])
-        o = OC.pred_magmaclust(new.X[sl], new.y[sl], gp[op][sub], KERN, dict(zip(names_i, hp_new[t])), hyp, tau[t])
-        oo = np.argsort(reference_keys(gp[op][sub]), kind="stable")      # the oracle returns its rows in key order
-        worst_m = max(worst_m, float(np.max(np.abs(mean[t][sub][oo] - o["Mean"]) / np.maximum(1.0, np.abs(o["Mean"])))))
-        worst_v = max(worst_v, float(np.max(np.abs(var[t][sub][oo] - o["Var"]) / np.maximum(1e-3, np.abs(o["Var"])))))
-    out["check_max_rel_mean"] = worst_m
-    out["check_max_rel_var"] = worst_v
 print(json.dumps(out))

@@ -1,4 +1,4 @@
-"""Committed golden fixtures (tests/golden/, made by scripts/make_golden.py in the build container).
+"""Committed golden fixtures (tests/golden/, made by tests/tools/make_golden.py in the build container).
 
 Inputs are the reference's own golden datasets (tests/testthat/fixtures/simu_data_reference.rds) and its
 fixed 5-point test dataset; outputs were produced by the oracle (R cannot run here, so for e_step, m_step,

@@ -302,7 +302,7 @@ def test_train_magma_config1(ctx, seed):
 
     The mean process has cond(K_0) ~ 1e12, so every implementation (LAPACK included) carries ~1e-5
     relative noise in hp_0's objective and in the hyper-posterior (test_mean_process_objective_sensitivity,
-    scripts/diag_config1.py); the EM loop amplifies it and stops on a 1e-3 threshold.  The oracle is
+    tests/tools/diag_config1.py); the EM loop amplifies it and stops on a 1e-3 threshold.  The oracle is
     therefore run as a small ENSEMBLE (hp_0 perturbed by 1e-5 relative): the GPU's EM step count must be
     one the ensemble produces -- for seeds 1, 6, 8 the ensemble is unanimous, i.e. the count is exact --
     and its log-likelihood sequence must lie within the ensemble's spread (x4) around the oracle's.

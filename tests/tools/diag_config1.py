@@ -1,8 +1,8 @@
 """Where do the GPU and oracle EM trajectories of config 1 (seed 17) part?  Per EM iteration, from the
 ORACLE's current HPs: e_step both ways, then m_step both ways from the oracle's hyper-posterior."""
 import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 from helpers import make_case, upload, relerr
 from magmaclustr_b200.engine import Context

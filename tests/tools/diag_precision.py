@@ -2,8 +2,8 @@
 (mpmath, 40 digits) evaluation of the same E step?  cond(K_0) ~ 1e12 makes both inexact; this tells
 whether the CUDA path is as accurate as LAPACK or noisier."""
 import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 import mpmath as mp
 from helpers import make_case, upload, relerr
