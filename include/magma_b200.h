@@ -331,6 +331,25 @@ int mb_pred_magma_tasks(mb_context*, const mb_kernel* kern, const double* hp, co
  * (/root/reference/R/em-magma.R:39-46).  bytes_out[0] = algorithmic bytes per repetition. */
 int mb_bench_hbm(mb_context*, int what, const mb_kernel* kern_i, int reps, double* ms_out, double* bytes_out);
 
+/* ---- host data path (no GPU involved): what train_magma / train_magmaclust / pred_* do to `data` before any arithmetic
+ * (/root/reference/R/training.R:690-720, R/prediction.R:534-567,937-976, R/em-magma.R:27-30), as an R-free routine.
+ * mb_r_signif = signif(x, digits) (R nmath/fprec.c); mb_r_as_character = as.character(<double>) (15 significant digits,
+ * fixed unless scientific is shorter); mb_reference_key = the `Reference` string of one input row
+ * (paste(signif(row, digits), collapse = ":")).
+ * mb_prepare_rows: X is n_rows x d row-major (Input, covariates), ids the ID strings, y the outputs (may be NULL);
+ * grid_extra (n_extra x d, may be NULL) are additional grid inputs (prediction grid / new-task inputs) to include in the
+ * union grid.  Outputs (caller-allocated): perm[n_rows] = original row of every output row (rows ordered by ID string then
+ * Reference string, byte-wise like dplyr::arrange); X_out / y_out the rounded, permuted table; offs_out[n_tasks + 1]
+ * (capacity n_rows + 1); grid_index_out[n_rows]; grid_X_out (capacity (n_rows + n_extra) x d) the union grid in
+ * Reference order.  Returns 3 when a task has two rows on the same grid point (the reference's stop(), training.R:703-714). */
+double mb_r_signif(double x, int digits);
+int mb_r_as_character(double x, char* out, int cap);
+int mb_reference_key(const double* row, int d, int digits, char* out, int cap);
+int mb_prepare_rows(int64_t n_rows, int d, const double* X, const double* y, const char* const* ids, int digits,
+                    const double* grid_extra, int64_t n_extra, int64_t* perm, double* X_out, double* y_out,
+                    int64_t* n_tasks_out, int64_t* offs_out, int32_t* grid_index_out, int32_t* n_grid_out,
+                    double* grid_X_out);
+
 /* ---- optimiser, exposed for tests: optim(method="L-BFGS-B") on a built-in test function
  * (0 = Rosenbrock n=2), run by the same state machine the M step uses (host build). */
 int mb_lbfgsb_selftest(int which, double* x, int n, double factr, int maxit, double* fval,

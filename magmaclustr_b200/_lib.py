@@ -98,6 +98,11 @@ _SIGS = {
     "mb_train_shared_gp": [_vp, _kp, _dp, C.c_double, C.c_double, C.c_int, _lp],
     "mb_train_gp_clust_tasks": [_vp, _kp, _dp, _dp, C.c_double, C.c_int, C.c_double, _dp, _ip, _ip, _lp],
     "mb_pred_magma_tasks": [_vp, _kp, _dp, _dp, C.c_int32, _dp, _ip, C.c_double, _dp, _dp, _dp, _dp, _ip],
+    "mb_r_signif": [C.c_double, C.c_int],
+    "mb_r_as_character": [C.c_double, C.c_char_p, C.c_int],
+    "mb_reference_key": [_dp, C.c_int, C.c_int, C.c_char_p, C.c_int],
+    "mb_prepare_rows": [C.c_int64, C.c_int, _dp, _dp, C.POINTER(C.c_char_p), C.c_int, _dp, C.c_int64, _lp, _dp, _dp, _lp, _lp,
+                        _ip, _ip, _dp],
     "mb_bench_hbm": [_vp, C.c_int, _kp, C.c_int, _dp, _dp],
     "mb_lbfgsb_selftest": [C.c_int, _dp, C.c_int, C.c_double, C.c_int, _dp, _ip, _ip],
 }
@@ -115,7 +120,7 @@ def lib():
         for name, sig in _SIGS.items():
             fn = getattr(l, name)
             fn.argtypes = sig
-            fn.restype = C.c_int64 if name == "mb_launch_count" else C.c_int
+            fn.restype = C.c_int64 if name == "mb_launch_count" else (C.c_double if name == "mb_r_signif" else C.c_int)
         l.mb_last_error.restype = C.c_char_p
         l.mb_kernel_hp_name.argtypes = [_kp, C.c_int]
         l.mb_kernel_hp_name.restype = C.c_char_p

@@ -135,3 +135,32 @@ class Prepared:
         if not np.all(self.grid_keys[pos] == keys):
             raise KeyError("some inputs are not on the grid")
         return pos.astype(np.int32)
+
+
+def prepare_rows_native(ids, X, y=None, grid_extra=None, digits=6):
+    """The same preparation done by the library's compiled host routine (mb_prepare_rows, csrc/hostprep.cu): what an R
+    shim would call instead of the tidyverse pipeline of training.R:690-720.  Returns a dict with the fields of `Prepared`
+    (X, y, offs, grid_index, grid_X, perm).  Rows with missing values must already be dropped (tidyr::drop_na)."""
+    import ctypes as C
+    from . import _lib as L
+    X = np.ascontiguousarray(np.atleast_2d(np.asarray(X, dtype=np.float64).T).T)
+    n, d = X.shape
+    yv = None if y is None else np.ascontiguousarray(y, dtype=np.float64)
+    idb = [str(i).encode("utf-8") for i in ids]
+    arr = (C.c_char_p * n)(*idb)
+    ge = None if grid_extra is None else np.ascontiguousarray(np.atleast_2d(np.asarray(grid_extra, dtype=np.float64).T).T)
+    ne = 0 if ge is None else ge.shape[0]
+    perm = np.zeros(n, dtype=np.int64)
+    Xo = np.zeros((n, d))
+    yo = np.zeros(n)
+    nt = C.c_int64(0)
+    offs = np.zeros(n + 1, dtype=np.int64)
+    gi = np.zeros(n, dtype=np.int32)
+    ng = C.c_int32(0)
+    gX = np.zeros((n + ne, d))
+    L.check(L.lib().mb_prepare_rows(n, d, L.ptr(X), L.ptr(yv) if yv is not None else None, arr, int(digits),
+                                    L.ptr(ge) if ge is not None else None, ne, L.ptr(perm), L.ptr(Xo),
+                                    L.ptr(yo) if yv is not None else None, C.byref(nt), L.ptr(offs), L.ptr(gi), C.byref(ng),
+                                    L.ptr(gX)))
+    return {"X": Xo, "y": yo if yv is not None else None, "offs": offs[:nt.value + 1].copy(), "grid_index": gi,
+            "grid_X": gX[:ng.value].copy(), "perm": perm}

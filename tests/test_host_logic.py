@@ -180,3 +180,68 @@ def test_sharded_e_step_sums_with_gloo_world2(tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+# ---- compiled host data path (csrc/hostprep.cu): bit-exact with the Python preparation and the oracle ------------------
+def test_native_number_formatting_matches_r_rules():
+    import ctypes as C
+    lib = L.lib()
+    cases = {1e-4: "1e-04", 0.001: "0.001", 1e5: "1e+05", 123457.0: "123457", 100000.0: "1e+05",
+             -0.22: "-0.22", 0.3: "0.3", 10.0: "10", -1.0: "-1", 0.1 + 0.2: "0.3", 2.5e-7: "2.5e-07",
+             0.0: "0", 1234567.891: "1234567.891", 1 / 3: "0.333333333333333"}
+    buf = C.create_string_buffer(64)
+    for v, s in cases.items():
+        L.check(lib.mb_r_as_character(v, buf, 64))
+        assert buf.value.decode() == s
+    rng = np.random.default_rng(12)
+    xs = np.concatenate([rng.normal(size=300) * 10.0 ** rng.integers(-8, 9, size=300), np.round(rng.uniform(-5, 5, 200), 2),
+                         [1234567.891, 1 / 3, -0.0123456789, 123456.7, 0.999999499, 5e-324, 0.0, 1e22, -1e-15]])
+    for v in xs:
+        r = lib.mb_r_signif(float(v), 6)
+        assert r == RF.r_signif(float(v))
+        L.check(lib.mb_r_as_character(r, buf, 64))
+        assert buf.value.decode() == RF.r_as_character(r), v
+    row = np.array([0.1 + 0.2, -1234567.0, 2.5e-7])
+    L.check(lib.mb_reference_key(L.ptr(row), 3, 6, buf, 64))
+    assert buf.value.decode() == RF.reference_key(row) == "0.3:-1234570:2.5e-07"
+
+
+def test_native_prepare_rows_matches_python_and_oracle():
+    rng = np.random.default_rng(8)
+    for d in (1, 2):
+        sizes = rng.integers(1, 9, size=13)
+        ids, X = [], []
+        pool = np.round(np.arange(-1, 1.001, 0.01), 2)
+        for t, n in enumerate(sizes):
+            ids += [str(t + 1)] * int(n)                      # "1", "10", "11", ... sort as strings
+            pts = rng.choice(len(pool), size=(int(n),), replace=False)
+            cols = [pool[pts]] + [np.round(rng.uniform(0, 10, int(n)), 3) for _ in range(d - 1)]
+            X.append(np.column_stack(cols))
+        X = np.vstack(X)
+        y = rng.normal(size=len(X))
+        shuffle = rng.permutation(len(X))                     # the table need not arrive sorted
+        ids = [ids[i] for i in shuffle]
+        X, y = X[shuffle], y[shuffle]
+        extra = np.column_stack([np.round(np.linspace(-1, 1, 7), 3)] + [np.full(7, 1.5)] * (d - 1))
+        nat = DP.prepare_rows_native(ids, X, y, grid_extra=extra)
+        py = DP.Prepared(ids, X, y)
+        py.set_grid(extra)
+        np.testing.assert_array_equal(nat["offs"], py.offs)
+        np.testing.assert_array_equal(nat["X"], py.X)
+        np.testing.assert_array_equal(nat["y"], py.y)
+        np.testing.assert_array_equal(nat["grid_index"], py.grid_index)       # index mapping: exact
+        np.testing.assert_array_equal(nat["grid_X"], py.grid_X)
+        # and against the oracle's Dataset (training.R:690-720 restated independently)
+        odb = OM.Dataset(ids, X, y)
+        keys, Xg, index = odb.extend_grid(extra)
+        np.testing.assert_array_equal(nat["grid_X"], Xg)
+        for t, i in enumerate(odb.ids):
+            np.testing.assert_array_equal(nat["grid_index"][nat["offs"][t]:nat["offs"][t + 1]], index[i])
+
+
+def test_native_prepare_rows_rejects_duplicates():
+    ids = ["a", "a", "b"]
+    X = np.array([[0.5], [0.5000001], [0.5]])       # equal after signif(6): two Outputs of "a" on one grid point
+    with pytest.raises(L.MagmaError) as e:
+        DP.prepare_rows_native(ids, X, np.zeros(3))
+    assert e.value.args[0] == 3 or "several Outputs" in str(e.value)
