@@ -210,3 +210,35 @@ def test_train_shared_gp(ctx):
     np.testing.assert_allclose(hp_fit, [ohp[n] for n in names], rtol=1e-4, atol=1e-5)
     assert abs(int(stats[0]) - res["counts"]) <= 2 and stats[1] == res["convergence"]
     assert stats[2] == stats[0] * (1 + 2 * len(names)) * 8
+
+
+@pytest.mark.parametrize("kern", ["RQ + PERIO", "SE * LIN", "PERIO"])
+def test_new_task_path_compound_kernels(ctx, kern):
+    """The new-task entry points with the generic kernel grammar (kernel-to-matrices.R:163-340): marginal value and
+    gradient per task, and the batched prediction, against the oracle on the library's own hyper-posterior."""
+    case, prep, new_prep, new_odb, _, _, Xp, pm, pc, gi = _magma_hyperpost(ctx, seed=33)
+    k = L.parse_kernel(kern, True)
+    names = L.hp_names(k)
+    rng = np.random.default_rng(3)
+    hp = rng.uniform(0.2, 1.2, size=(new_prep.n_tasks, len(names)))
+    hp[:, names.index("noise")] = rng.uniform(-3.0, -1.0, size=new_prep.n_tasks)
+    f, g, r = ctx.logL_GP_tasks(k, hp)
+    for t, i in enumerate(new_prep.ids):
+        _, X, y = new_odb.tasks[i]
+        idx = gi[new_prep.offs[t]:new_prep.offs[t + 1]]
+        hpd = dict(zip(names, hp[t]))
+        of = OM.logL_GP(hpd, X, y, pm[idx], kern, pc[np.ix_(idx, idx)], 1e-10)
+        og = OM.gr_GP(hpd, X, y, pm[idx], kern, pc[np.ix_(idx, idx)], 1e-10)
+        assert abs(f[t] - of) <= 1e-9 * max(1.0, abs(of)), (kern, t, f[t], of)
+        np.testing.assert_allclose(g[t], og, rtol=1e-7, atol=1e-8, err_msg="%s task %d" % (kern, t))
+    from magmaclustr_b200.dataprep import reference_keys, r_signif
+    Xp_r = r_signif(Xp)
+    kp = reference_keys(Xp_r)
+    op = np.argsort(kp, kind="stable")
+    mean, var, _, _, r = ctx.pred_magma_tasks(k, hp, Xp_r[op], prep.index_of(kp[op]))
+    hyp = {"keys": [q.decode() for q in prep.grid_keys], "mean": pm, "cov": pc}
+    for t, i in enumerate(new_prep.ids):
+        _, X, y = new_odb.tasks[i]
+        o = OM.pred_magma(X, y, Xp, kern, dict(zip(names, hp[t])), hyp)
+        np.testing.assert_allclose(mean[t], o["Mean"], rtol=1e-8, atol=1e-8)
+        np.testing.assert_allclose(var[t], o["Var"], rtol=1e-7, atol=1e-9)
