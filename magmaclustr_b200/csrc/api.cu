@@ -210,7 +210,7 @@ struct mb_context {
   int hpr_K = 0, hpr_U = 0;
   bool hpr_keep = false, hpr_has_cov = false;
   // timing / profiling
-  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_single = nullptr;
   cudaEvent_t ev_ring[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_cp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool prof_on = false;
@@ -390,6 +390,7 @@ extern "C" int mb_destroy(mb_context* c) {
   for (auto& ev : c->prof_ev) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+  if (c->ev_single) cudaEventDestroy(c->ev_single);
   for (int i = 0; i < 8; ++i) if (c->ev_ring[i]) cudaEventDestroy(c->ev_ring[i]);
   for (int i = 0; i < 8; ++i) if (c->ev_cp[i]) cudaEventDestroy(c->ev_cp[i]);
   c->ws0.release();
@@ -970,8 +971,18 @@ static int optimise(mb_context* c, std::vector<SingleProblem>& singles, bool tas
     if (!c->ev_cp[i]) CU(cudaEventCreateWithFlags(&c->ev_cp[i], cudaEventDisableTiming));
   }
   if (!c->st3) CU(cudaStreamCreateWithFlags(&c->st3, cudaStreamNonBlocking));
+  // Event-driven host loop: neither the task rounds nor the single (mean / cluster process) problem ever block the other.
+  // The single problem's evaluation is enqueued on st2 and polled; a blocking wait there (~225 us per evaluation of the
+  // 201-point problem) would pace the task rounds at one per evaluation, which starves the task stream as soon as a round
+  // is shorter than that (tail rounds, and every round once the tasks are sharded over 4-8 GPUs).
+  if (!c->ev_single) CU(cudaEventCreateWithFlags(&c->ev_single, cudaEventDisableTiming));
+  int read = 0;                 // rounds whose active count has been read
+  bool single_inflight = false;
+  double* hres = c->h_pin + 32;
+  int* hinfo = c->h_pin_i + 8;
   while (tasks_active || cur < singles.size()) {
-    if (tasks_active) {
+    bool progressed = false;
+    if (tasks_active && enq - read <= LB_LAG) {
       if (enq >= 4095) MB_FAIL(2, "L-BFGS-B lock-step did not terminate");
       MB_TRY(launch_obj(c, a, (int)M, c->st, true));
       LAUNCH(c, launch_lbfgsb_advance(c->lb.as<LbfgsbState>(), M, P_i, a.f, a.g, c->counters.as<int>() + enq, c->st));
@@ -982,21 +993,51 @@ static int optimise(mb_context* c, std::vector<SingleProblem>& singles, bool tas
       MB_TRY(d2h(c->h_pin_i + 64 + (enq % RING), c->counters.as<int>() + enq, sizeof(int), c->st3));
       CU(cudaEventRecord(c->ev_cp[enq % RING], c->st3));
       enq++;
+      progressed = true;
     }
     if (cur < singles.size()) {
       SingleProblem& sp = singles[cur];
-      if (!sp.s.active) { cur++; }
-      else {
-        double f, g[MB_MAX_HP];
-        MB_TRY(run_single_eval(c, sp, pen, &f, g));
-        lb_advance(&sp.s, f, g);
-        if (!sp.s.active) cur++;
+      if (!single_inflight) {
+        if (!sp.s.active) { cur++; }
+        else if (dense_use_big(sp.n) || getenv("MB_SINGLE_BLOCKING")) {   // the large-matrix path synchronises inside (host jitter loop): blocking evaluation
+          double f, g[MB_MAX_HP];
+          MB_TRY(run_single_eval(c, sp, pen, &f, g));
+          lb_advance(&sp.s, f, g);
+          if (!sp.s.active) cur++;
+        } else {
+          MB_TRY(dense_obj_enqueue(c, c->ws0, sp.kd, sp.s.x, sp.X, sp.n, sp.D, sp.y, sp.mean, sp.S, pen, 1, c->st2, hres, hinfo));
+          CU(cudaEventRecord(c->ev_single, c->st2));
+          single_inflight = true;
+        }
+        progressed = true;
+      } else {
+        const cudaError_t q = tasks_active ? cudaEventQuery(c->ev_single) : cudaEventSynchronize(c->ev_single);
+        if (q == cudaSuccess) {
+          sp.evals++;
+          double g[MB_MAX_HP];
+          const double f = (hinfo[0] < 0) ? NAN : hres[0];
+          for (int p = 0; p < sp.kd.n_hp; ++p) g[p] = hres[1 + p];
+          lb_advance(&sp.s, f, g);
+          if (!sp.s.active) cur++;
+          single_inflight = false;
+          progressed = true;
+        } else if (q != cudaErrorNotReady) {
+          mb_set_error(__FILE__, __LINE__, cudaGetErrorString(q));
+          return -2;
+        }
       }
     }
-    if (tasks_active && enq > LB_LAG) {
-      const int r = enq - 1 - LB_LAG;
-      CU(cudaEventSynchronize(c->ev_cp[r % RING]));
-      if (c->h_pin_i[64 + (r % RING)] == 0) { tasks_active = false; rounds = r + 1; }
+    if (tasks_active && read < enq) {
+      // with nothing else to do the host may as well block on the oldest outstanding count
+      const bool idle = !progressed && !(cur < singles.size());
+      const cudaError_t q = idle ? cudaEventSynchronize(c->ev_cp[read % RING]) : cudaEventQuery(c->ev_cp[read % RING]);
+      if (q == cudaSuccess) {
+        if (c->h_pin_i[64 + (read % RING)] == 0) { tasks_active = false; rounds = read + 1; }
+        read++;
+      } else if (q != cudaErrorNotReady) {
+        mb_set_error(__FILE__, __LINE__, cudaGetErrorString(q));
+        return -2;
+      }
     }
   }
   if (tasks_on) {
