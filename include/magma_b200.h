@@ -270,7 +270,9 @@ int mb_matmul(mb_context*, int transa, int transb, int m, int n, int k, const do
               const double* B, int ldb, double* C, int ldc);
 /* Device-only timing of the large-matrix kernels (batched-Cholesky FP64 TFLOP/s of BASELINE.json's metric)
  * on an n-point SE + noise covariance: what = 0 product (2 n^3 flops), 1 chol() (n^3 / 3), 2 chol2inv(chol())
- * (n^3).  ms_out[0] = mean milliseconds per repetition, CUDA events on the library's stream. */
+ * (n^3), 3 the single-CTA shared-memory chol2inv(chol()) of the union grid (n <= 224; ms_out[1..6] then receive the
+ * cycles of its phases: load, Cholesky, log-det, triangular inverse, X X', store).  ms_out (8 doubles): ms_out[0] = mean
+ * milliseconds per repetition, CUDA events on the library's stream. */
 int mb_bench_dense(mb_context*, int what, int n, int reps, double* ms_out);
 /* Same for the batched per-task path on the resident dataset (after mb_set_state): every task's
  * chol2inv(chol(K_i + jitter)) in one persistent launch, nothing written.  flops_out[0] = sum_i N_i^3. */

@@ -1731,7 +1731,7 @@ extern "C" int mb_bench_dense(mb_context* c, int what, int n, int reps, double* 
   mb_kernel k;
   MB_TRY(mb_kernel_parse("SE", 1, &k));
   DevKern kd = make_devkern(&k);
-  const double hp[3] = {0.3, -5.0, -3.0};
+  const double hp[3] = {0.3, what == 3 ? -2.0 : -5.0, -3.0};
   LAUNCH(c, launch_dense_cov(kd, hp, dx.as<double>(), n, dx.as<double>(), n, 1, -1, 1, ws.Kmat.as<double>(), n, 1, c->st));
   const int64_t ldw = ((int64_t)n + 7) / 8 * 8;
   cudaEvent_t e0, e1;
@@ -1742,6 +1742,10 @@ extern "C" int mb_bench_dense(mb_context* c, int what, int n, int reps, double* 
     if (what == 0) {
       LAUNCH(c, launch_big_gemm_plain(n, n, n, ws.Kmat.as<double>(), 1, n, ws.Kmat.as<double>(), n, 1, ws.T.as<double>(), n,
                                       1.0, nullptr, 0.0, c->st));
+    } else if (what == 3) {   // the single-CTA shared-memory kernel of the union grid (n <= 224)
+      if (!dense_sm_fits(n)) MB_FAIL(-1, "what = 3 needs n <= 224");
+      LAUNCH(c, launch_dense_cholinv_sm(ws.Kmat.as<double>(), n, ws.A.as<double>(), n, 1e-10, 0, ws.info.as<int>(),
+                                        ws.res.as<double>() + 16, c->st));
     } else {
       CU(launch_big_cholinv_attempt(ws.Kmat.as<double>(), n, ws.Ap.as<double>(), ws.Bp.as<double>(), ldw, ws.A.as<double>(),
                                     n, 1e-10, 0, what == 1 ? 1 : 0, ws.info.as<int>() + 4, ws.info.as<int>(),
@@ -1756,8 +1760,13 @@ extern "C" int mb_bench_dense(mb_context* c, int what, int n, int reps, double* 
   cudaEventDestroy(e1);
   MB_TRY(d2h(c->h_pin_i, ws.info.p, sizeof(int), c->st));
   CU(cudaStreamSynchronize(c->st));
-  if (what != 0 && c->h_pin_i[0] != 0) MB_FAIL(1, "bench matrix did not factor");
+  if (what != 0 && what != 3 && c->h_pin_i[0] != 0) MB_FAIL(1, "bench matrix did not factor");
   ms_out[0] = ms / reps;
+  if (what == 3) {   // phase cycles of the last launch: load, Cholesky, log-det, triangular inverse, X X', store
+    MB_TRY(d2h(c->h_pin, ws.res.as<double>() + 16, 16 * sizeof(double), c->st));
+    CU(cudaStreamSynchronize(c->st));
+    for (int q = 0; q < 6; ++q) ms_out[1 + q] = c->h_pin[4 + q];
+  }
   return 0;
 }
 

@@ -32,28 +32,42 @@ __global__ void __launch_bounds__(DSM_THREADS, 1) k_dense_cholinv_sm(const doubl
   const Ln L;
   for (int i = threadIdx.x; i < n8; i += DSM_THREADS)
     for (int j = i; j < n8; ++j) s.tab[d3_tri(i, n8) + j - i] = (unsigned short)((i << 8) | j);
+  __syncthreads();
   int retries = 0;
   double total = 0.0;
+  long long tk0 = clock64(), tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0, tk5 = 0;   // phase marks (thread 0 reports them in out[4..9])
   for (;;) {
     total = 0.0;
     if (mode == 0) { double p = pen; for (int r = 0; r <= retries; ++r) { total += p; p = 10 * p; } }
-    for (int e = threadIdx.x; e < np * np; e += DSM_THREADS) {
-      const int i = e / np, j = e - i * np;
-      const int ti = i >> 3, tj = j >> 3;
-      if (ti > tj) continue;
-      double v = 0.0;
-      if (i < n && j < n) {
-        if (j >= i) {
-          v = src[(size_t)i * ld_src + j];
-          if (i == j && mode == 0) { double q = pen; for (int r = 0; r <= retries; ++r) { v += q; q = 10 * q; } }
+    // upper tiles only, one 8 x 8 tile per 64 consecutive threads (rows of 8 doubles = two 32-byte sectors), eight
+    // independent loads in flight per thread: the matrix comes from L2 and a dependent load costs ~700 cycles
+    for (int e0 = threadIdx.x; e0 < ntri * 64; e0 += 8 * DSM_THREADS) {
+      double v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int e = e0 + q * DSM_THREADS;
+        v[q] = 0.0;
+        if (e < ntri * 64) {
+          const int t = s.tab[e >> 6], i = 8 * (t >> 8) + ((e >> 3) & 7), j = 8 * (t & 255) + (e & 7);
+          if (i < n && j < n) { if (j >= i) v[q] = src[(size_t)i * ld_src + j]; }
+          else if (i == j) v[q] = 1.0;
         }
-      } else if (i == j) {
-        v = 1.0;
       }
-      s.T1[(size_t)(d3_tri(ti, n8) + tj - ti) * 64 + sw(i & 7, j & 7)] = v;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int e = e0 + q * DSM_THREADS;
+        if (e < ntri * 64) {
+          const int t = s.tab[e >> 6], i = 8 * (t >> 8) + ((e >> 3) & 7), j = 8 * (t & 255) + (e & 7);
+          double x = v[q];
+          if (i == j && i < n && mode == 0) { double p = pen; for (int r = 0; r <= retries; ++r) { x += p; p = 10 * p; } }
+          s.T1[(size_t)(e >> 6) * 64 + sw(i & 7, j & 7)] = x;
+        }
+      }
     }
     __syncthreads();
+    tk1 = clock64();
     const int f = d3_chol<NWS>(s, n8, L);
+    tk2 = clock64();
     if (f == 0) break;
     __syncthreads();
     if (mode == 1) { if (threadIdx.x == 0) { info[0] = f; out[0] = NAN; } return; }
@@ -76,15 +90,25 @@ __global__ void __launch_bounds__(DSM_THREADS, 1) k_dense_cholinv_sm(const doubl
     }
   }
   if (mode == 1) return;
+  tk3 = clock64();
   d3_trtri<NWS, 2>(s, n8, L);
+  tk4 = clock64();
   d3_lauum<NWS, 2>(s, n8, L);
-  for (int e = threadIdx.x; e < n * n; e += DSM_THREADS) {
-    const int r = e / n, c = e - r * n;
-    const int i = r >> 3, j = c >> 3;
-    inv[e] = (i <= j) ? s.T1[(size_t)(d3_tri(i, n8) + j - i) * 64 + sw(r & 7, c & 7)]
-                      : s.T1[(size_t)(d3_tri(j, n8) + i - j) * 64 + sw(c & 7, r & 7)];
+  tk5 = clock64();
+  // full symmetric matrix out: a warp writes 32 consecutive doubles of one row, rows are dealt to the warps
+  for (int r = L.warp; r < n; r += NWS) {
+    const int i = r >> 3;
+    for (int c = L.lane; c < n; c += 32) {
+      const int j = c >> 3;
+      inv[(size_t)r * n + c] = (i <= j) ? s.T1[(size_t)(d3_tri(i, n8) + j - i) * 64 + sw(r & 7, c & 7)]
+                                        : s.T1[(size_t)(d3_tri(j, n8) + i - j) * 64 + sw(c & 7, r & 7)];
+    }
   }
   (void)ntri;
+  if (threadIdx.x == 0) {
+    out[4] = (double)(tk1 - tk0); out[5] = (double)(tk2 - tk1); out[6] = (double)(tk3 - tk2); out[7] = (double)(tk4 - tk3);
+    out[8] = (double)(tk5 - tk4); out[9] = (double)(clock64() - tk5);
+  }
 }
 
 // ---- C = alpha A B + beta Cin on the FP64 tensor cores ------------------------------------------------

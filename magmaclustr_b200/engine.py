@@ -289,9 +289,9 @@ class Context:
 
     def bench_dense(self, what, n, reps=3):
         """Device-only milliseconds per call: what = 0 n^3 product, 1 Cholesky, 2 Cholesky + inverse."""
-        ms = np.zeros(1)
+        ms = np.zeros(8)
         check(L.lib().mb_bench_dense(self._h, int(what), int(n), int(reps), ptr(ms)))
-        return float(ms[0])
+        return (float(ms[0]), ms[1:7].copy()) if what == 3 else float(ms[0])
 
     def bench_task_inverse(self, ki, reps=5, pen_diag=1e-10):
         """(ms per launch, sum N_i^3) of the batched chol2inv(chol(K_i)) over the resident dataset."""
