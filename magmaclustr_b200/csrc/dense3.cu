@@ -113,9 +113,11 @@ __global__ void __launch_bounds__(DSM_THREADS, 1) k_dense_cholinv_sm(const doubl
 
 // ---- C = alpha A B + beta Cin on the FP64 tensor cores ------------------------------------------------
 // A(i,k) = A[i*ars + k*acs], B(k,j) = B[k*brs + j*bcs], C row-major (ldc).  CTA: 4 warps, 32 x 32 block,
-// K slabs of 16 staged in shared memory (leading dimensions 20 / 36: fragment loads conflict-free).
+// K slabs of 32 staged in shared memory (leading dimension 36: fragment loads conflict-free); the next slab is fetched
+// into registers while the current one is multiplied -- at the 201-point union grid the kernel is a chain of L2 round
+// trips (one per slab), so the slab is as deep as the register budget allows.
 #define GD_BM 32
-#define GD_BK 16
+#define GD_BK 32
 __global__ void __launch_bounds__(128) k_gemm_dmma(int m, int n, int kk, const double* __restrict__ A, int64_t ars,
                                                    int64_t acs, const double* __restrict__ B, int64_t brs, int64_t bcs,
                                                    double* C, int64_t ldc, double alpha, const double* Cin, double beta) {
@@ -125,12 +127,12 @@ __global__ void __launch_bounds__(128) k_gemm_dmma(int m, int n, int kk, const d
   const int wy = warp >> 1, wx = warp & 1;
   const int i0 = blockIdx.y * GD_BM, j0 = blockIdx.x * GD_BM;
   double acc[2][2][2] = {};
-  double pa[4], pb[4];
+  double pa[8], pb[8];
   auto fetch = [&](int k0) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 8; ++q) {
       const int e = tid + 128 * q;
-      const int ar = e >> 4, ac = e & 15;
+      const int ar = e >> 5, ac = e & 31;
       const int gi = i0 + ar, gk = k0 + ac;
       pa[q] = (gi < m && gk < kk) ? A[gi * ars + gk * acs] : 0.0;
       const int br = e >> 5, bc = e & 31;
@@ -141,9 +143,9 @@ __global__ void __launch_bounds__(128) k_gemm_dmma(int m, int n, int kk, const d
   fetch(0);
   for (int k0 = 0; k0 < kk; k0 += GD_BK) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 8; ++q) {
       const int e = tid + 128 * q;
-      As[e >> 4][e & 15] = pa[q];
+      As[e >> 5][e & 31] = pa[q];
       Bs[e >> 5][e & 31] = pb[q];
     }
     __syncthreads();
