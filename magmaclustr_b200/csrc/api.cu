@@ -1313,6 +1313,7 @@ extern "C" int mb_pred_magma_tasks(mb_context* c, const mb_kernel* kern, const d
   const size_t per_task = (size_t)K * ((size_t)nmax * nmax + nmax);
   // tasks are processed in chunks so that the Gamma^-1 table and the outputs stay bounded
   int64_t chunk = (int64_t)(((size_t)1 << 30) / (per_task * 8 + (size_t)n_pred * 8 * (2 + (pred_mean_k ? 2 * K : 0))));
+  if (const char* ec = getenv("MB_PRED_CHUNK")) { if (atoll(ec) >= 1) chunk = atoll(ec); }   // test hook: force several chunks
   if (chunk < 1) chunk = 1;
   if (chunk > M) chunk = M;
   if (chunk > 65535) chunk = 65535;

@@ -112,6 +112,14 @@ def test_pred_magma_tasks(ctx):
         np.testing.assert_allclose(mean[t], o["Mean"], rtol=1e-8, atol=1e-8)
         np.testing.assert_allclose(var[t], o["Var"], rtol=1e-7, atol=1e-9)
         assert r[t, 0] == 0
+    # the same call cut into chunks of two tasks (the library bounds its scratch table that way at large sizes)
+    import os
+    os.environ["MB_PRED_CHUNK"] = "2"
+    try:
+        mean2, var2, _, _, _ = ctx.pred_magma_tasks(case["ki"], hp_new, Xp_r[op], ip)
+    finally:
+        del os.environ["MB_PRED_CHUNK"]
+    assert np.array_equal(mean2, mean) and np.array_equal(var2, var)
 
 
 def test_pred_magmaclust_tasks(ctx):
