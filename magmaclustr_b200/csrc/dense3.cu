@@ -12,6 +12,12 @@
 // chol(post_cov) of logL_monitoring (R/likelihoods.R:303-307).
 #include "dense3.cuh"
 
+#include <stdlib.h>
+
+#include <map>
+
+#define DSM_SPLIT_N 128   /* smallest matrix for which the X X' product leaves the single CTA */
+
 size_t dense_sm_bytes(int n) {
   const int n8 = (n + 7) / 8, ntri = n8 * (n8 + 1) / 2;
   return ((size_t)ntri * 64 + (size_t)n8 * 64 + (size_t)n8 * 8 + 2 * NWS) * sizeof(double) +
@@ -26,7 +32,8 @@ extern __shared__ double4 dense3_smem_raw[];
 // mode 1: sum log diag chol(src), NO jitter; info[0] = 0 or failing pivot    likelihoods.R:303-307
 __global__ void __launch_bounds__(DSM_THREADS, 1) k_dense_cholinv_sm(const double* __restrict__ src, int ld_src,
                                                                      double* __restrict__ inv, int n, double pen,
-                                                                     int max_retry, int mode, int* info, double* out) {
+                                                                     int max_retry, int mode, int* info, double* out,
+                                                                     double* __restrict__ xt_out) {
   const int n8 = (n + 7) >> 3, np = 8 * n8, ntri = n8 * (n8 + 1) / 2;
   const SmD s = carve_d((double*)dense3_smem_raw, n8);
   const Ln L;
@@ -93,6 +100,16 @@ __global__ void __launch_bounds__(DSM_THREADS, 1) k_dense_cholinv_sm(const doubl
   tk3 = clock64();
   d3_trtri<NWS, 2>(s, n8, L);
   tk4 = clock64();
+  if (xt_out) {
+    // split path: X = R^-1 (packed upper tiles) goes to global memory and k_mid_lauum forms A = X X' on many SMs -- that
+    // product is ~9 k DMMAs, 36 k cycles of ONE SM's tensor pipe here, a few microseconds when it is spread out
+    for (int e = threadIdx.x; e < ntri * 64; e += DSM_THREADS) xt_out[e] = s.T1[e];
+    if (threadIdx.x == 0) {
+      out[4] = (double)(tk1 - tk0); out[5] = (double)(tk2 - tk1); out[6] = (double)(tk3 - tk2); out[7] = (double)(tk4 - tk3);
+      out[8] = 0.0; out[9] = (double)(clock64() - tk4);
+    }
+    return;
+  }
   d3_lauum<NWS, 2>(s, n8, L);
   tk5 = clock64();
   // full symmetric matrix out: a warp writes 32 consecutive doubles of one row, rows are dealt to the warps
@@ -108,6 +125,74 @@ __global__ void __launch_bounds__(DSM_THREADS, 1) k_dense_cholinv_sm(const doubl
   if (threadIdx.x == 0) {
     out[4] = (double)(tk1 - tk0); out[5] = (double)(tk2 - tk1); out[6] = (double)(tk3 - tk2); out[7] = (double)(tk4 - tk3);
     out[8] = (double)(tk5 - tk4); out[9] = (double)(clock64() - tk5);
+  }
+}
+
+// A = X X' from the packed upper tiles of X = R^-1 left in global memory by k_dense_cholinv_sm (split path): one warp per
+// upper tile (i, j), the same two accumulator chains over even / odd m and the same final c + e as d3_lauum, so every
+// entry is bit-identical to the single-CTA kernel's; the operand fragments of four m-steps are fetched from L2 before the
+// first product.  Writes the full symmetric n x n matrix (row-major), lower part mirrored from the upper one.
+#define ML_WARPS 4
+__global__ void __launch_bounds__(32 * ML_WARPS) k_mid_lauum(const double* __restrict__ xt, int n, double* __restrict__ inv,
+                                                             const int* __restrict__ info) {
+  if (info[0] < 0) return;   // the factorisation gave up: nothing to form
+  const int n8 = (n + 7) >> 3, ntri = n8 * (n8 + 1) / 2;
+  const Ln L;
+  const int idx = blockIdx.x * ML_WARPS + L.warp;
+  if (idx >= ntri) return;
+  int i = 0, rem = idx;
+  while (rem >= n8 - i) { rem -= n8 - i; ++i; }
+  const int j = i + rem;
+  const double* Ti = xt + (size_t)(d3_tri(i, n8) - i) * 64;   // tile (i, m) at Ti + m * 64
+  const double* Tj = xt + (size_t)(d3_tri(j, n8) - j) * 64;
+  double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+  int m = j;
+  for (; m + 3 < n8; m += 4) {
+    double a0, a1, b0, b1, p0, p1, q0, q1, r0, r1, s0, s1, t0, t1, u0, u1;
+    rf(Ti + (size_t)m * 64, L, a0, a1);
+    rf(Tj + (size_t)m * 64, L, b0, b1);
+    rf(Ti + (size_t)(m + 1) * 64, L, p0, p1);
+    rf(Tj + (size_t)(m + 1) * 64, L, q0, q1);
+    rf(Ti + (size_t)(m + 2) * 64, L, r0, r1);
+    rf(Tj + (size_t)(m + 2) * 64, L, s0, s1);
+    rf(Ti + (size_t)(m + 3) * 64, L, t0, t1);
+    rf(Tj + (size_t)(m + 3) * 64, L, u0, u1);
+    dmma884(c0, c1, a0, b0);
+    dmma884(e0, e1, p0, q0);
+    dmma884(c0, c1, a1, b1);
+    dmma884(e0, e1, p1, q1);
+    dmma884(c0, c1, r0, s0);
+    dmma884(e0, e1, t0, u0);
+    dmma884(c0, c1, r1, s1);
+    dmma884(e0, e1, t1, u1);
+  }
+  for (; m + 1 < n8; m += 2) {
+    double a0, a1, b0, b1, p0, p1, q0, q1;
+    rf(Ti + (size_t)m * 64, L, a0, a1);
+    rf(Tj + (size_t)m * 64, L, b0, b1);
+    rf(Ti + (size_t)(m + 1) * 64, L, p0, p1);
+    rf(Tj + (size_t)(m + 1) * 64, L, q0, q1);
+    dmma884(c0, c1, a0, b0);
+    dmma884(e0, e1, p0, q0);
+    dmma884(c0, c1, a1, b1);
+    dmma884(e0, e1, p1, q1);
+  }
+  if (m < n8) {
+    double a0, a1, b0, b1;
+    rf(Ti + (size_t)m * 64, L, a0, a1);
+    rf(Tj + (size_t)m * 64, L, b0, b1);
+    dmma884(c0, c1, a0, b0);
+    dmma884(c0, c1, a1, b1);
+  }
+  const double v[2] = {c0 + e0, c1 + e1};
+  const int r = 8 * i + L.g;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int c = 8 * j + 2 * L.t + q;
+    if (r < n && c < n && (i != j || c >= r)) {
+      inv[(size_t)r * n + c] = v[q];
+      if (c != r) inv[(size_t)c * n + r] = v[q];
+    }
   }
 }
 
@@ -232,7 +317,25 @@ cudaError_t launch_dense_cholinv_sm(const double* src, int ld_src, double* inv, 
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  k_dense_cholinv_sm<<<1, DSM_THREADS, smem, st>>>(src, ld_src, inv, n, pen, 40, mode, info, out);
+  // mode 0 at n >= DSM_SPLIT_N: the kernel stops after X = R^-1 and a multi-CTA kernel forms X X' (k_mid_lauum); the packed
+  // X lives in a scratch buffer per stream (calls on different streams may overlap)
+  double* xt = nullptr;
+  if (mode == 0 && n >= DSM_SPLIT_N && !getenv("MB_DENSE_NOSPLIT")) {
+    static std::map<cudaStream_t, double*> scratch;
+    auto it = scratch.find(st);
+    if (it == scratch.end()) {
+      double* p = nullptr;
+      const size_t cap = (size_t)(DSM_MAX_N8 * (DSM_MAX_N8 + 1) / 2) * 64 * sizeof(double);
+      if (cudaMalloc(&p, cap) != cudaSuccess) { cudaGetLastError(); p = nullptr; }
+      it = scratch.emplace(st, p).first;
+    }
+    xt = it->second;
+  }
+  k_dense_cholinv_sm<<<1, DSM_THREADS, smem, st>>>(src, ld_src, inv, n, pen, 40, mode, info, out, xt);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || !xt) return e;
+  const int n8 = (n + 7) / 8, ntri = n8 * (n8 + 1) / 2;
+  k_mid_lauum<<<(ntri + ML_WARPS - 1) / ML_WARPS, 32 * ML_WARPS, 0, st>>>(xt, n, inv, info);
   return cudaGetLastError();
 }
 

@@ -362,3 +362,27 @@ def test_logdet_modes_agree_on_tasks(mode):
     env = dict(os.environ, MB_LOGDET=mode)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_chol_inv_jitter_split_product_is_bit_identical(ctx):
+    """Union-grid sizes (n >= 128): the X X' product of chol2inv runs in a separate multi-CTA kernel; every entry must equal
+    the single-CTA kernel's (same accumulation order), the result is exactly symmetric and matches LAPACK."""
+    import os
+    rng = np.random.default_rng(9)
+    for n in (128, 150, 201, 224):
+        a = rng.normal(size=(n, n))
+        spd = a @ a.T + n * np.eye(n)
+        inv, retries, _ = ctx.chol_inv_jitter(spd, 1e-10)
+        os.environ["MB_DENSE_NOSPLIT"] = "1"
+        try:
+            inv1, retries1, _ = ctx.chol_inv_jitter(spd, 1e-10)
+        finally:
+            del os.environ["MB_DENSE_NOSPLIT"]
+        assert retries == retries1 == 0
+        assert np.array_equal(inv, inv1), n
+        assert np.array_equal(inv, inv.T)
+        np.testing.assert_allclose(inv, OK.chol_inv_jitter(spd, 1e-10), rtol=1e-10, atol=1e-14)
+    # a matrix that never factors: the product kernel must not run on garbage (status reported, no crash)
+    bad = np.full((130, 130), np.nan)
+    with pytest.raises(L.MagmaError):
+        ctx.chol_inv_jitter(bad, 1e-10)
