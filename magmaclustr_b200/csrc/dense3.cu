@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include <map>
+#include <utility>
 
 #define DSM_SPLIT_N 128   /* smallest matrix for which the X X' product leaves the single CTA */
 
@@ -321,13 +322,16 @@ cudaError_t launch_dense_cholinv_sm(const double* src, int ld_src, double* inv, 
   // X lives in a scratch buffer per stream (calls on different streams may overlap)
   double* xt = nullptr;
   if (mode == 0 && n >= DSM_SPLIT_N && !getenv("MB_DENSE_NOSPLIT")) {
-    static std::map<cudaStream_t, double*> scratch;
-    auto it = scratch.find(st);
+    static std::map<std::pair<int, cudaStream_t>, double*> scratch;   // (device, stream): one host thread drives a context
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const std::pair<int, cudaStream_t> key(dev, st);
+    auto it = scratch.find(key);
     if (it == scratch.end()) {
       double* p = nullptr;
       const size_t cap = (size_t)(DSM_MAX_N8 * (DSM_MAX_N8 + 1) / 2) * 64 * sizeof(double);
       if (cudaMalloc(&p, cap) != cudaSuccess) { cudaGetLastError(); p = nullptr; }
-      it = scratch.emplace(st, p).first;
+      it = scratch.emplace(key, p).first;
     }
     xt = it->second;
   }
