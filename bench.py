@@ -209,7 +209,7 @@ def main():
     df, prep, hp0, hpi = make_inputs()
     k0, ki = L.parse_kernel("SE", False), L.parse_kernel("SE", True)
     ctx = Context(local_rank)
-    lo, hi_ = shard_tasks(prep.offs, rank, world)
+    lo, hi_ = shard_tasks(prep.offs, rank, world, len(prep.grid_X))
     offs = (prep.offs[lo:hi_ + 1] - prep.offs[lo]).astype(np.int64)
     r0, r1 = int(prep.offs[lo]), int(prep.offs[hi_])
     # pinned host copies of the step's inputs (e2e path)
@@ -226,6 +226,7 @@ def main():
             ctx.set_allreduce(make_allreduce(dist), rank, world)      # torch.distributed does the all-reduce
         else:
             init_library_nccl(ctx, dist, rank, world)                 # the library's own NCCL communicator
+        ctx.set_shard(lo, len(prep.offs) - 1)                         # leaf-aligned shard: results independent of the GPU count
     ctx.upload_dataset(offs, X_h, y_h, gi_h, gX_h)
     m0 = np.zeros(ctx.U)
     ctx.set_state(k0, hp0, ki, hpi_loc, m0)

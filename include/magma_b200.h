@@ -78,6 +78,16 @@ int mb_set_allreduce(mb_context* ctx, mb_allreduce_fn fn, void* user, int rank, 
  * trip.  libnccl.so.2 is resolved with dlopen, so single-GPU users need no NCCL at all. */
 int mb_nccl_unique_id(char* id_out, int bytes);
 int mb_nccl_init(mb_context* ctx, const char* id, int bytes, int rank, int world);
+/* Sharding that keeps the results independent of the number of GPUs.  The reference adds the tasks one after the other
+ * (R/em-magma.R:39-46, R/likelihoods.R:253-312); the library cuts the GLOBAL task list (ID order, training.R:699-701) into
+ * mb_estep_leaves(M, U) contiguous LEAVES -- a power of two fixed by the task count M and the union-grid size U alone -- sums
+ * the tasks of a leaf in task order and the leaves in a fixed binary tree.  A rank must hold whole leaves:
+ * mb_shard_range gives rank `rank` of `world` its task range [first, last), and mb_set_shard tells a context which range
+ * of the global list its resident dataset is (call it before the first E step; a single-GPU run needs neither).  With
+ * that, post_mean / post_cov / log-likelihoods / EM step counts are bit-identical on 1, 2, 4, 8 GPUs. */
+int mb_estep_leaves(int64_t n_tasks_global, int32_t n_grid);
+int mb_shard_range(int64_t n_tasks_global, int32_t n_grid, int rank, int world, int64_t* first, int64_t* last);
+int mb_set_shard(mb_context* ctx, int64_t first_task_global, int64_t n_tasks_global);
 
 /* ---- the five legacy builders: /root/reference/src/code.cpp, src/init.c:17-24 ----------
  * m1 is n1 x d, m2 is n2 x d, out is n1 x n2, all column-major (R numeric matrices). */

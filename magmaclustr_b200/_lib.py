@@ -91,6 +91,9 @@ _SIGS = {
     "mb_bench_task_inverse": [_vp, _kp, C.c_double, C.c_int, _dp, _dp],
     "mb_nccl_unique_id": [C.c_char_p, C.c_int],
     "mb_nccl_init": [_vp, C.c_char_p, C.c_int, C.c_int, C.c_int],
+    "mb_estep_leaves": [C.c_int64, C.c_int32],
+    "mb_shard_range": [C.c_int64, C.c_int32, C.c_int, C.c_int, _lp, _lp],
+    "mb_set_shard": [_vp, C.c_int64, C.c_int64],
     "mb_hyperpost_keep": [_vp, C.c_int],
     "mb_hyperpost_set": [_vp, C.c_int, C.c_int32, _dp, _dp],
     "mb_logL_GP_tasks": [_vp, _kp, _dp, C.c_int, C.c_int, C.c_double, _dp, _dp, _ip],

@@ -22,64 +22,34 @@
 
 // ---- launchers defined in the other translation units ------------------------------------
 cudaError_t launch_task_objective(TaskObjArgs a, int n_launch, cudaStream_t st);
-cudaError_t launch_task_inverse(TaskInvArgs a, int n_ctas, cudaStream_t st);
 cudaError_t launch_task_cov(TaskData db, DevKern kd, const double* hp, int64_t hp_stride,
                             int deriv, double* out, const int64_t* out_offs, cudaStream_t st);
-int task_max_ctas_per_sm(int nmax, int D);
 cudaError_t launch_task_cov_sym(TaskData db, DevKern kd, const double* hp, int64_t hp_stride, int deriv, double* out,
                                 const int64_t* out_offs, int sm_count, cudaStream_t st);
 cudaError_t launch_task_pred(TaskPredArgs a, int n_launch_tasks, cudaStream_t st);
-cudaError_t launch_task_objective2(TaskObjArgs a, int n_launch, cudaStream_t st);
-cudaError_t launch_task_inverse2(TaskInvArgs a, int n_ctas, cudaStream_t st);
-int task2_max_ctas_per_sm(int nmax, int D);
-
 cudaError_t launch_task_objective3(TaskObjArgs a, int n_launch, cudaStream_t st);
 cudaError_t launch_task_inverse3(TaskInvArgs a, int n_ctas, cudaStream_t st);
 int task3_max_ctas_per_sm(int nmax, int D);
 
-// kernel generation switch: v3 (default) = 4-warp CTAs on packed swizzled tiles, DMMA; MB_TASK_KERNEL=v2
-// selects the 8-warp DMMA version, v1 the first scalar shared-memory version (both kept as
-// independent cross-checks of v3)
 struct BigTaskPool;
 void big_pool_destroy(BigTaskPool* p);
 int big_tasks_objective(BigTaskPool** pp, const TaskObjArgs& a, const int64_t* h_offs, cudaStream_t st, int64_t* launches);
-int big_tasks_slots(BigTaskPool** pp, int nmax, int64_t n_tasks);
 int big_tasks_inverse(BigTaskPool** pp, const TaskInvArgs& a, const int64_t* h_offs, const int64_t* h_inv_offs,
-                      cudaStream_t st, int64_t* launches);
+                      const int64_t* h_leaf_offs, cudaStream_t st, int64_t* launches);
 
-static int task_kernel_version() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MB_TASK_KERNEL");
-    v = 3;
-    if (e && e[0] == 'v' && (e[1] == '1' || e[1] == '2')) v = e[1] - '0';
-  }
-  return v;
-}
+// marginal-likelihood modes (new tasks, small N_obs) run the scalar shared-memory kernel of tasks.cu; everything else the
+// DMMA kernels of tasks3.cu
 static cudaError_t launch_task_objective_any(TaskObjArgs a, int n_launch, cudaStream_t st) {
-  const int v = task_kernel_version();
-  if (a.mode == TK_OBJ_MARG || a.mode == TK_OBJ_MARG_MIX || v == 1) return launch_task_objective(a, n_launch, st);
-  return v == 2 ? launch_task_objective2(a, n_launch, st) : launch_task_objective3(a, n_launch, st);
+  if (a.mode == TK_OBJ_MARG || a.mode == TK_OBJ_MARG_MIX) return launch_task_objective(a, n_launch, st);
+  return launch_task_objective3(a, n_launch, st);
 }
-static cudaError_t launch_task_inverse_any(TaskInvArgs a, int n_ctas, cudaStream_t st) {
-  const int v = task_kernel_version();
-  return v == 1 ? launch_task_inverse(a, n_ctas, st) : (v == 2 ? launch_task_inverse2(a, n_ctas, st) : launch_task_inverse3(a, n_ctas, st));
-}
-static int task_ctas_per_sm_any(int nmax, int D) {
-  const int v = task_kernel_version();
-  return v == 1 ? task_max_ctas_per_sm(nmax, D) : (v == 2 ? task2_max_ctas_per_sm(nmax, D) : task3_max_ctas_per_sm(nmax, D));
-}
+static cudaError_t launch_task_inverse_any(TaskInvArgs a, int n_ctas, cudaStream_t st) { return launch_task_inverse3(a, n_ctas, st); }
+static int task_ctas_per_sm_any(int nmax, int D) { return task3_max_ctas_per_sm(nmax, D); }
 cudaError_t launch_dense_cov(const DevKern& kd, const double* hp_host, const double* x1, int n1,
                              const double* x2, int n2, int D, int deriv, int with_noise,
                              double* out, int64_t rs, int64_t cs, cudaStream_t st);
 cudaError_t launch_legacy_builder(int which, const double* m1, int n1, const double* m2, int n2,
                                   int d, double par, double* out, cudaStream_t st);
-cudaError_t launch_dense_cholinv(const double* src, int ld_src, double* A, double* B, double* Xd,
-                                 double* inv, int n, double pen, int* info, double* out,
-                                 cudaStream_t st);
-cudaError_t launch_dense_chol_logdiag(const double* src, double* W, double* Xd, int n, int* info,
-                                      double* out, cudaStream_t st);
-size_t dense_xd_doubles(int n);
 bool dense_sm_fits(int n);
 cudaError_t launch_dense_cholinv_sm(const double* src, int ld_src, double* inv, int n, double pen, int mode,
                                     int* info, double* out, cudaStream_t st);
@@ -89,20 +59,16 @@ cudaError_t launch_gemm_dmma(int m, int n, int k, const double* A, int64_t ars, 
 cudaError_t launch_resid_gemv(int n, const double* A, const double* y, const double* mean, double* r, double* al,
                               cudaStream_t st);
 // chol_inv_jitter of a device matrix: shared-memory-resident kernel when it fits (U <= 224), else the
-// multi-CTA blocked path of dense_big.cu.  MB_DENSE_KERNEL=v2 forces the single-CTA L2-resident kernel of
-// dense.cu (cross-check only: slow).
+// multi-CTA blocked path of dense_big.cu (MB_DENSE_KERNEL=big forces the latter: used by the tests to cross-check)
 static int dense_env() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MB_DENSE_KERNEL"); v = (e && e[0] == 'v' && e[1] == '2') ? 0 : ((e && e[0] == 'b') ? 2 : 1); }
+  if (v < 0) { const char* e = getenv("MB_DENSE_KERNEL"); v = (e && e[0] == 'b') ? 2 : 1; }
   return v;
 }
 static bool dense_use_sm(int n) { return dense_env() == 1 && dense_sm_fits(n); }
-static bool dense_use_big(int n) { return dense_env() == 2 || (dense_env() == 1 && !dense_sm_fits(n)); }
+static bool dense_use_big(int n) { return !dense_use_sm(n); }
 cudaError_t launch_dense_lu_logdet(const double* src, double* W, int n, int* done, double* out,
                                    cudaStream_t st);
-cudaError_t launch_gemm(int m, int n, int k, const double* A, int64_t ars, int64_t acs,
-                        const double* B, int64_t brs, int64_t bcs, double* C, int64_t ldc,
-                        double alpha, const double* Cin, double beta, cudaStream_t st);
 cudaError_t launch_gemv(int m, int n, const double* A, int64_t ld, const double* x,
                         const double* y0, double* y, cudaStream_t st);
 int dense_obj_nparts(int n);
@@ -111,9 +77,10 @@ cudaError_t launch_dense_obj(const DevKern& kd, const double* hp_host, const dou
                              const double* al, const double* r, const double* logdet,
                              int from_chol, int want_grad, double* part, double* res,
                              cudaStream_t st);
-cudaError_t launch_reduce_partials(int64_t count, int nparts, const double* base,
-                                   const double* part, int64_t part_stride, double* out,
-                                   cudaStream_t st);
+cudaError_t launch_reduce_tree(int64_t count, int nparts, const double* base, const double* part, int64_t part_stride,
+                               double* out, cudaStream_t st);
+cudaError_t launch_leaf_sums(const double* v, int P, const int64_t* leaf_offs, int n_leaves, double* out, cudaStream_t st);
+cudaError_t launch_retry_stats(const int32_t* retries, int64_t n, int* out2, cudaStream_t st);
 cudaError_t launch_sum_sequential(const double* v, int64_t n, int64_t stride, double* out,
                                   cudaStream_t st);
 cudaError_t launch_colsum_sequential(const double* v, int64_t n, int P, double* out,
@@ -160,7 +127,7 @@ struct DBuf {
 };
 
 struct DenseWs {   // workspace of one dense n x n problem
-  DBuf Kmat, A, B, T, S, Ap, Bp, Xd, vecs, part, res, info, done;
+  DBuf Kmat, A, B, T, S, Ap, Bp, vecs, part, res, info, done;
   int n = 0;
   double* r() { return vecs.as<double>(); }
   double* al() { return vecs.as<double>() + n; }
@@ -170,15 +137,14 @@ struct DenseWs {   // workspace of one dense n x n problem
     size_t m = (size_t)nn * nn * sizeof(double);
     if (Kmat.ensure(m) || A.ensure(m) || B.ensure(m) || T.ensure(m) || S.ensure(m)) return -3;
     const size_t npad = (size_t)((nn + 7) / 8) * 8;
-    if (Ap.ensure(npad * npad * sizeof(double)) || Bp.ensure(npad * npad * sizeof(double)) ||
-        Xd.ensure(dense_xd_doubles(nn) * sizeof(double))) return -3;
+    if (Ap.ensure(npad * npad * sizeof(double)) || Bp.ensure(npad * npad * sizeof(double))) return -3;
     if (vecs.ensure(4 * (size_t)nn * sizeof(double))) return -3;
     if (part.ensure((size_t)dense_obj_nparts(nn) * (1 + MB_MAX_HP) * sizeof(double))) return -3;
     if (res.ensure(32 * sizeof(double)) || info.ensure(8 * sizeof(int))) return -3;
     if (done.ensure((size_t)nn * sizeof(int))) return -3;
     return 0;
   }
-  void release() { Kmat.release(); A.release(); B.release(); T.release(); S.release(); Ap.release(); Bp.release(); Xd.release(); vecs.release();
+  void release() { Kmat.release(); A.release(); B.release(); T.release(); S.release(); Ap.release(); Bp.release(); vecs.release();
                    part.release(); res.release(); info.release(); done.release(); }
 };
 
@@ -197,8 +163,8 @@ struct mb_context {
   std::vector<int64_t> h_offs;
   // workspaces
   DenseWs ws0, ws1;                 // ws0: mean/cluster process on st2 ; ws1: generic on st
-  DBuf hp_i, hp_k, f_t, g_t, retries, lb, counters, part_inv, part_w, sums, pm, pc, m0, tau,
-      inv0, post_inv, weighted, fails, nfgv, scratch, kcache;
+  DBuf hp_i, hp_k, f_t, g_t, retries, lb, counters, sums, pm, pc, m0, tau,
+      inv0, post_inv, fails, nfgv, scratch, kcache;
   double* h_pin = nullptr;          // pinned host scratch (256 doubles)
   int* h_pin_i = nullptr;           // pinned host ints (1024)
   // resident EM state (mb_set_state): pristine + working HP tables
@@ -225,6 +191,13 @@ struct mb_context {
   mb_allreduce_fn ar = nullptr;
   void* ar_user = nullptr;
   int rank = 0, world = 1;
+  // this rank's slice of the GLOBAL task list (mb_set_shard; the whole list when never set) and the leaves it owns
+  int64_t g_first = 0, g_total = 0;
+  bool shard_set = false;
+  int lv_NL = 0, lv_l0 = 0, lv_n = 0, lv_U = -1;
+  int64_t lv_first = -1, lv_total = -1, lv_ntasks = -1;
+  std::vector<int64_t> lv_offs;
+  DBuf d_lv_offs, tickets, leafbuf, slotbuf, leafsum;
 };
 
 #define CU(call) MB_CUDA_OK(call)
@@ -235,7 +208,7 @@ static int launch_obj(mb_context* c, const TaskObjArgs& a, int n_launch, cudaStr
                       bool profiled = false) {
   if (a.db.nmax > TK_MAXN) return big_tasks_objective(&c->big, a, c->h_offs.data(), st, &c->launches);
   TaskObjArgs a2 = a;
-  if (a.want_grad && task_kernel_version() == 3) {
+  if (a.want_grad && a.mode != TK_OBJ_MARG && a.mode != TK_OBJ_MARG_MIX) {
     const int n8 = (a.db.nmax + 7) / 8;
     a2.kcache_stride = (int64_t)(a.db.nmax <= 64 ? 36 : 78) * 64;   // packed upper tiles of the 8 / 12-tile layouts
     (void)n8;
@@ -336,9 +309,146 @@ static int ctx_allreduce(mb_context* c, void* dev, int64_t count, cudaStream_t s
     if (r != ncclSuccess) MB_FAIL(-5, "ncclAllReduce failed");
     return 0;
   }
-  if (!c->ar) return 0;
+  if (!c->ar) MB_FAIL(-5, "world > 1 but neither mb_nccl_init nor an mb_set_allreduce hook is configured");
   CU(cudaStreamSynchronize(s));
   if (c->ar(c->ar_user, dev, count) != 0) MB_FAIL(-5, "allreduce hook failed");
+  return 0;
+}
+
+// ================================================================================================
+// Leaves: the fixed partition of the GLOBAL task list behind every sum over tasks.
+// The reference adds the tasks sequentially (em-magma.R:39-46, likelihoods.R:253-312).  Here a sum over tasks is
+//   (1) a sequential (E step) or compensated (scalars) sum over the tasks of each LEAF, in task order,
+//   (2) a fixed binary tree over the NL leaves (dense.cu:k_reduce_tree).
+// NL and the leaf boundaries depend on the global task count and the grid size only, and every rank owns whole leaves, so
+// the result has the same bits on 1, 2, 4, 8 ... GPUs (and for any SM count / launch geometry).  Across ranks the leaf (or
+// subtree) sums are exchanged with an all-reduce of a zero-padded slot buffer -- x + 0 is exact, so this is a gather whatever
+// order the collective adds in -- and every rank finishes the same tree.
+// ================================================================================================
+static int leaf_count(int64_t g_total, int U) {
+  const int64_t per = ((int64_t)U * U + U) * 8;
+  int64_t cap = per > 0 ? ((int64_t)1 << 30) / per : 128;
+  if (cap < 1) cap = 1;
+  int64_t m = 128;
+  if (g_total < m) m = g_total;
+  if (cap < m) m = cap;
+  int nl = 1;
+  while ((int64_t)nl * 2 <= m) nl *= 2;
+  return nl;
+}
+static int64_t leaf_start(int64_t l, int nl, int64_t g_total) { return (l * g_total + nl - 1) / nl; }
+
+extern "C" int mb_estep_leaves(int64_t n_tasks_global, int32_t n_grid) {
+  if (n_tasks_global < 1 || n_grid < 0) return -1;
+  return leaf_count(n_tasks_global, n_grid);
+}
+
+extern "C" int mb_shard_range(int64_t n_tasks_global, int32_t n_grid, int rank, int world, int64_t* first, int64_t* last) {
+  if (n_tasks_global < 1 || world < 1 || rank < 0 || rank >= world || !first || !last) MB_FAIL(-1, "bad argument");
+  const int nl = leaf_count(n_tasks_global, n_grid);
+  if (nl < world) MB_FAIL(-1, "more ranks than E-step leaves: use fewer GPUs for this dataset");
+  *first = leaf_start((int64_t)rank * nl / world, nl, n_tasks_global);
+  *last = leaf_start((int64_t)(rank + 1) * nl / world, nl, n_tasks_global);
+  return 0;
+}
+
+extern "C" int mb_set_shard(mb_context* c, int64_t first_task_global, int64_t n_tasks_global) {
+  if (!c) MB_FAIL(-1, "null ctx");
+  if (first_task_global < 0 || n_tasks_global < 1 || first_task_global >= n_tasks_global) MB_FAIL(-1, "bad shard");
+  c->g_first = first_task_global; c->g_total = n_tasks_global; c->shard_set = true;
+  c->lv_U = -1;
+  return 0;
+}
+
+// leaves of the resident tasks for a grid of U points (cached)
+static int ctx_leaves(mb_context* c, int U) {
+  const int64_t M = c->db.n_tasks;
+  const int64_t first = c->shard_set ? c->g_first : 0, total = c->shard_set ? c->g_total : M;
+  if (c->world > 1 && !c->shard_set) MB_FAIL(-1, "world > 1: call mb_set_shard (global position of this rank's tasks) first");
+  if (first + M > total) MB_FAIL(-1, "mb_set_shard: the resident tasks run past the global task count");
+  if (c->world == 1 && M != total) MB_FAIL(-1, "mb_set_shard: a partial shard needs world > 1 (mb_nccl_init / mb_set_allreduce)");
+  if (c->lv_U == U && c->lv_first == first && c->lv_total == total && c->lv_ntasks == M) return 0;
+  const int nl = leaf_count(total, U);
+  int l0 = -1, l1 = -1;
+  for (int l = 0; l <= nl; ++l) {
+    const int64_t s = leaf_start(l, nl, total);
+    if (s == first && l0 < 0) l0 = l;
+    if (s == first + M) l1 = l;
+  }
+  if (l0 < 0 || l1 <= l0) MB_FAIL(-1, "shard boundaries must coincide with E-step leaf boundaries (mb_shard_range)");
+  if (c->world > 1 && (c->world & (c->world - 1)) == 0 && nl % c->world == 0 &&
+      (l0 != c->rank * (nl / c->world) || l1 - l0 != nl / c->world))
+    MB_FAIL(-1, "with a power-of-two world every rank must hold the shard mb_shard_range gives it");
+  c->lv_offs.resize(l1 - l0 + 1);
+  for (int l = l0; l <= l1; ++l) c->lv_offs[l - l0] = leaf_start(l, nl, total) - first;
+  MB_TRY(c->d_lv_offs.ensure(c->lv_offs.size() * 8));
+  CU(cudaMemcpyAsync(c->d_lv_offs.p, c->lv_offs.data(), c->lv_offs.size() * 8, cudaMemcpyHostToDevice, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  c->lv_NL = nl; c->lv_l0 = l0; c->lv_n = l1 - l0; c->lv_U = U;
+  c->lv_first = first; c->lv_total = total; c->lv_ntasks = M;
+  return 0;
+}
+
+// out[0..count) = base + (fixed tree over ALL leaves of the global task list) of the per-leaf vectors vals[l * stride ..],
+// l < lv_n local leaves.  Needs ctx_leaves().  Everything is enqueued on s (the hook path synchronises inside).
+static int leaf_reduce(mb_context* c, const double* vals, int64_t stride, int64_t count, const double* base, double* out,
+                       cudaStream_t s) {
+  if (c->world <= 1) {
+    LAUNCH(c, launch_reduce_tree(count, c->lv_n, base, vals, stride, out, s));
+    return 0;
+  }
+  const bool subtree = (c->world & (c->world - 1)) == 0 && c->lv_NL % c->world == 0;
+  const int slots = subtree ? c->world : c->lv_NL;
+  MB_TRY(c->slotbuf.ensure((size_t)slots * count * 8));
+  double* sb = c->slotbuf.as<double>();
+  CU(cudaMemsetAsync(sb, 0, (size_t)slots * count * 8, s));
+  if (subtree) {
+    LAUNCH(c, launch_reduce_tree(count, c->lv_n, nullptr, vals, stride, sb + (size_t)c->rank * count, s));
+  } else {
+    CU(cudaMemcpy2DAsync(sb + (size_t)c->lv_l0 * count, count * 8, vals, stride * 8, count * 8, c->lv_n,
+                         cudaMemcpyDeviceToDevice, s));
+  }
+  MB_TRY(ctx_allreduce(c, sb, (int64_t)slots * count, s));
+  LAUNCH(c, launch_reduce_tree(count, slots, base, sb, count, out, s));
+  return 0;
+}
+
+// out[0..P) = sum over ALL tasks (every rank) of the columns of the row-major table v (local tasks x P), device pointers
+static int leaf_sum_columns(mb_context* c, const double* v, int P, double* out, cudaStream_t s) {
+  MB_TRY(ctx_leaves(c, c->U));
+  MB_TRY(c->leafsum.ensure((size_t)c->lv_n * P * 8));
+  LAUNCH(c, launch_leaf_sums(v, P, c->d_lv_offs.as<int64_t>(), c->lv_n, c->leafsum.as<double>(), s));
+  return leaf_reduce(c, c->leafsum.as<double>(), P, P, nullptr, out, s);
+}
+
+// same for a host table: out_host[0..P) = column sums over the tasks of ALL ranks (vem-magmaclust.R:265-266, elbos.R:253)
+static int leaf_sum_columns_host(mb_context* c, const double* tab, int P, double* out_host) {
+  const size_t bytes = (size_t)c->db.n_tasks * P * 8;
+  MB_TRY(c->scratch.ensure(bytes + 64 * 8));
+  double* d_tab = c->scratch.as<double>();
+  double* d_out = d_tab + (size_t)c->db.n_tasks * P;
+  CU(cudaMemcpyAsync(d_tab, tab, bytes, cudaMemcpyHostToDevice, c->st));
+  MB_TRY(leaf_sum_columns(c, d_tab, P, d_out, c->st));
+  CU(cudaMemcpyAsync(out_host, d_out, (size_t)P * 8, cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+// Collective agreement on a status: every rank passes its own return code, all get a non-zero code when any rank failed,
+// so nobody is left waiting in the next all-reduce.
+static int ctx_agree(mb_context* c, int local_rc, cudaStream_t s) {
+  if (c->world <= 1) return local_rc;
+  if (c->sums.ensure(64 * 8)) return -3;
+  const double flag = local_rc ? 1.0 : 0.0;
+  if (cudaMemcpyAsync(c->sums.as<double>() + 32, &flag, 8, cudaMemcpyHostToDevice, s) != cudaSuccess) return -2;
+  if (cudaStreamSynchronize(s) != cudaSuccess) return -2;
+  int rc = ctx_allreduce(c, c->sums.as<double>() + 32, 1, s);
+  if (rc) return rc;
+  double tot = 0.0;
+  if (cudaMemcpyAsync(&tot, c->sums.as<double>() + 32, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess) return -2;
+  if (cudaStreamSynchronize(s) != cudaSuccess) return -2;
+  if (local_rc) return local_rc;
+  if (tot != 0.0) MB_FAIL(3, "another rank reported a failure in this step");
   return 0;
 }
 
@@ -378,9 +488,9 @@ extern "C" int mb_destroy(mb_context* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   DBuf* bufs[] = {&c->d_offs, &c->d_X, &c->d_y, &c->d_gidx, &c->d_gridX, &c->hp_i, &c->hp_k, &c->f_t,
-                  &c->g_t, &c->retries, &c->lb, &c->counters, &c->part_inv, &c->part_w, &c->sums,
-                  &c->pm, &c->pc, &c->m0, &c->tau, &c->inv0, &c->post_inv, &c->weighted, &c->fails,
-                  &c->nfgv, &c->scratch, &c->kcache};
+                  &c->g_t, &c->retries, &c->lb, &c->counters, &c->sums,
+                  &c->pm, &c->pc, &c->m0, &c->tau, &c->inv0, &c->post_inv, &c->fails,
+                  &c->nfgv, &c->scratch, &c->kcache, &c->d_lv_offs, &c->tickets, &c->leafbuf, &c->slotbuf, &c->leafsum};
   for (DBuf* b : bufs) b->release();
   c->st_hp_i0.release();
   c->st_hp_i.release();
@@ -556,11 +666,8 @@ static int dev_cholinv(mb_context* c, DenseWs& ws, const double* src, int n, dou
                        cudaStream_t s, int* retries, double* jitter, double* sumlogdiag) {
   if (dense_use_sm(n))
     LAUNCH(c, launch_dense_cholinv_sm(src, n, ws.A.as<double>(), n, pen, 0, ws.info.as<int>(), ws.res.as<double>() + 16, s));
-  else if (dense_use_big(n))
-    MB_TRY(big_cholinv_sync(c, ws, src, n, pen, 0, ws.A.as<double>(), ws.info.as<int>(), ws.res.as<double>() + 16, s));
   else
-    LAUNCH(c, launch_dense_cholinv(src, n, ws.Ap.as<double>(), ws.Bp.as<double>(), ws.Xd.as<double>(),
-                                   ws.A.as<double>(), n, pen, ws.info.as<int>(), ws.res.as<double>() + 16, s));
+    MB_TRY(big_cholinv_sync(c, ws, src, n, pen, 0, ws.A.as<double>(), ws.info.as<int>(), ws.res.as<double>() + 16, s));
   MB_TRY(d2h(c->h_pin_i, ws.info.p, sizeof(int), s));
   MB_TRY(d2h(c->h_pin + 200, ws.res.as<double>() + 16, 2 * sizeof(double), s));
   CU(cudaStreamSynchronize(s));
@@ -715,7 +822,7 @@ extern "C" int mb_list_kern_to_mat(mb_context* c, const mb_kernel* k, int64_t n_
     a.retries = b_ret.as<int32_t>();
     if (nmax > TK_MAXN) {
       a.U = 0;
-      int brc = big_tasks_inverse(&c->big, a, offs, out_offs, c->st, &c->launches);
+      int brc = big_tasks_inverse(&c->big, a, offs, out_offs, nullptr, c->st, &c->launches);
       if (brc != 0) { cleanup(); return brc; }
       e = cudaSuccess;
     } else {
@@ -757,13 +864,9 @@ static int dense_obj_enqueue(mb_context* c, DenseWs& ws, const DevKern& kd, cons
   if (dense_use_sm(n))
     LAUNCH(c, launch_dense_cholinv_sm(ws.Kmat.as<double>(), n, ws.A.as<double>(), n, pen, 0, ws.info.as<int>(),
                                       ws.res.as<double>() + 16, s));
-  else if (dense_use_big(n))
+  else
     MB_TRY(big_cholinv_sync(c, ws, ws.Kmat.as<double>(), n, pen, 0, ws.A.as<double>(), ws.info.as<int>(),
                             ws.res.as<double>() + 16, s));
-  else
-    LAUNCH(c, launch_dense_cholinv(ws.Kmat.as<double>(), n, ws.Ap.as<double>(), ws.Bp.as<double>(),
-                                   ws.Xd.as<double>(), ws.A.as<double>(), n, pen, ws.info.as<int>(),
-                                   ws.res.as<double>() + 16, s));
   const double* logdet;
   if (c->logdet_chol) {
     logdet = ws.res.as<double>() + 17;
@@ -801,7 +904,6 @@ static int dev_e_step(mb_context* c, int K, const mb_kernel* kern_k, const doubl
   MB_TRY(c->ws1.ensure(U));
   MB_TRY(c->inv0.ensure(K * UU * 8));
   MB_TRY(c->post_inv.ensure(K * UU * 8));
-  MB_TRY(c->weighted.ensure((size_t)K * U * 8));
   MB_TRY(c->retries.ensure(c->db.n_tasks * 4));
   int max_r0 = 0, max_rp = 0;
   // inverse prior covariances on st2 (independent of the task work on st)
@@ -814,67 +916,64 @@ static int dev_e_step(mb_context* c, int K, const mb_kernel* kern_k, const doubl
     if (r > max_r0) max_r0 = r;
     CU(cudaMemcpyAsync(c->inv0.as<double>() + k * UU, c->ws1.A.p, UU * 8, cudaMemcpyDeviceToDevice, c->st2));
   }
-  // task inverses + deterministic partial sums
+  // task inverses, added leaf by leaf in task order (estep3.cu); one accumulator [K x U x U | K x U] per local leaf
   const bool big = c->db.nmax > TK_MAXN;
-  int G;
-  if (big) {
-    G = big_tasks_slots(&c->big, c->db.nmax, c->db.n_tasks);
-    if (G < 1) return G < 0 ? G : -2;
-  } else {
-    G = c->sm_count * task_ctas_per_sm_any(c->db.nmax, c->db.D);
-    if (G > c->db.n_tasks) G = (int)c->db.n_tasks;
-    const size_t cap = (size_t)2 << 30;
-    while (G > 1 && (size_t)G * K * UU * 8 > cap) G = (G + 1) / 2;
-  }
-  MB_TRY(c->part_inv.ensure((size_t)G * K * UU * 8));
-  MB_TRY(c->part_w.ensure((size_t)G * K * U * 8));
-  CU(cudaMemsetAsync(c->part_inv.p, 0, (size_t)G * K * UU * 8, c->st));
-  CU(cudaMemsetAsync(c->part_w.p, 0, (size_t)G * K * U * 8, c->st));
+  MB_TRY(ctx_leaves(c, U));
+  const int nl = c->lv_n;
+  const int64_t pstride = (int64_t)K * (UU + U);
+  MB_TRY(c->leafbuf.ensure((size_t)nl * pstride * 8));
+  MB_TRY(c->tickets.ensure((size_t)nl * sizeof(int)));
+  CU(cudaMemsetAsync(c->leafbuf.p, 0, (size_t)nl * pstride * 8, c->st));
+  CU(cudaMemsetAsync(c->tickets.p, 0, (size_t)nl * sizeof(int), c->st));
   TaskInvArgs a;
   memset(&a, 0, sizeof(a));
   a.db = c->db;
   if (gidx_override) a.db.gidx = gidx_override;
   a.kd = kdi; a.hp = hp_i_dev; a.hp_stride = hp_stride; a.pen = pen; a.K = K; a.tau = tau_dev; a.U = U;
-  a.part_inv = c->part_inv.as<double>(); a.part_w = c->part_w.as<double>();
+  a.part_inv = c->leafbuf.as<double>(); a.part_w = c->leafbuf.as<double>() + K * UU; a.part_stride = pstride;
+  a.leaf_offs = c->d_lv_offs.as<int64_t>(); a.n_leaves = nl; a.tickets = c->tickets.as<int>();
   a.retries = c->retries.as<int32_t>();
-  if (big) MB_TRY(big_tasks_inverse(&c->big, a, c->h_offs.data(), nullptr, c->st, &c->launches));
-  else LAUNCH(c, launch_task_inverse_any(a, G, c->st));
-  CU(cudaStreamSynchronize(c->st2));
-  // post_inv_k = inv_k (+) sum_i tau_ik inv_i ; weighted_k = inv_k m_k (+) sum_i tau_ik inv_i y_i
-  if (c->world > 1) {
-    LAUNCH(c, launch_reduce_partials(K * UU, G, nullptr, c->part_inv.as<double>(), K * UU, c->post_inv.as<double>(), c->st));
-    LAUNCH(c, launch_reduce_partials((int64_t)K * U, G, nullptr, c->part_w.as<double>(), (int64_t)K * U, c->weighted.as<double>(), c->st));
-    MB_TRY(ctx_allreduce(c, c->post_inv.p, K * UU, c->st));
-    MB_TRY(ctx_allreduce(c, c->weighted.p, (int64_t)K * U, c->st));
-    LAUNCH(c, launch_axpby(K * UU, 1.0, c->inv0.as<double>(), 1.0, c->post_inv.as<double>(), c->post_inv.as<double>(), c->st));
-    for (int k = 0; k < K; ++k)
-      LAUNCH(c, launch_gemv(U, U, c->inv0.as<double>() + k * UU, U, m_k_dev + (size_t)k * U,
-                            c->weighted.as<double>() + (size_t)k * U, c->weighted.as<double>() + (size_t)k * U, c->st));
+  if (big) {
+    MB_TRY(big_tasks_inverse(&c->big, a, c->h_offs.data(), nullptr, c->lv_offs.data(), c->st, &c->launches));
   } else {
-    LAUNCH(c, launch_reduce_partials(K * UU, G, c->inv0.as<double>(), c->part_inv.as<double>(), K * UU, c->post_inv.as<double>(), c->st));
-    // weighted: start from inv_k m_k, then the partials in order
-    MB_TRY(c->sums.ensure((size_t)K * U * 8 + 256));
-    for (int k = 0; k < K; ++k)
-      LAUNCH(c, launch_gemv(U, U, c->inv0.as<double>() + k * UU, U, m_k_dev + (size_t)k * U, nullptr,
-                            c->sums.as<double>() + (size_t)k * U, c->st));
-    LAUNCH(c, launch_reduce_partials((int64_t)K * U, G, c->sums.as<double>(), c->part_w.as<double>(), (int64_t)K * U, c->weighted.as<double>(), c->st));
+    // the CTAs of a leaf wait for each other: the whole grid has to be resident at once
+    const int cap = c->sm_count * task_ctas_per_sm_any(c->db.nmax, c->db.D);
+    int64_t longest = 1;
+    for (int l = 0; l < nl; ++l) if (c->lv_offs[l + 1] - c->lv_offs[l] > longest) longest = c->lv_offs[l + 1] - c->lv_offs[l];
+    int per = cap / nl;
+    if (per < 1) per = 1;          // more leaves than resident CTAs: one CTA per leaf never waits
+    if (per > longest) per = (int)longest;
+    a.ctas_per_leaf = per;
+    LAUNCH(c, launch_task_inverse_any(a, nl * per, c->st));
   }
+  CU(cudaStreamSynchronize(c->st2));
+  // [post_inv_k | weighted_k] = [inv_k | inv_k m_k] + tree over the leaves of all ranks
+  MB_TRY(c->sums.ensure((size_t)pstride * 8 + 256));
+  double* base = c->sums.as<double>();
+  CU(cudaMemcpyAsync(base, c->inv0.p, K * UU * 8, cudaMemcpyDeviceToDevice, c->st));
+  for (int k = 0; k < K; ++k)
+    LAUNCH(c, launch_gemv(U, U, c->inv0.as<double>() + k * UU, U, m_k_dev + (size_t)k * U, nullptr, base + K * UU + (size_t)k * U, c->st));
+  MB_TRY(c->post_inv.ensure((size_t)pstride * 8));
+  MB_TRY(leaf_reduce(c, c->leafbuf.as<double>(), pstride, pstride, base, c->post_inv.as<double>(), c->st));
+  double* weighted = c->post_inv.as<double>() + K * UU;
   for (int k = 0; k < K; ++k) {
     int r = 0;
     int rc = dev_cholinv(c, c->ws1, c->post_inv.as<double>() + k * UU, U, pen, c->st, &r, nullptr, nullptr);
     if (rc != 0) return rc;
     if (r > max_rp) max_rp = r;
     CU(cudaMemcpyAsync(post_cov + k * UU, c->ws1.A.p, UU * 8, cudaMemcpyDeviceToDevice, c->st));
-    LAUNCH(c, launch_gemv(U, U, post_cov + k * UU, U, c->weighted.as<double>() + (size_t)k * U, nullptr,
+    LAUNCH(c, launch_gemv(U, U, post_cov + k * UU, U, weighted + (size_t)k * U, nullptr,
                           post_mean + (size_t)k * U, c->st));
   }
-  // task retry statistics
-  std::vector<int32_t> hr(c->db.n_tasks);
-  MB_TRY(d2h(hr.data(), c->retries.p, c->db.n_tasks * 4, c->st));
+  // task retry statistics: the largest count and the "never factored" flag are reduced on the device
+  LAUNCH(c, launch_retry_stats(c->retries.as<int32_t>(), c->db.n_tasks, c->tickets.as<int>(), c->st));
+  MB_TRY(d2h(c->h_pin_i + 16, c->tickets.p, 2 * sizeof(int), c->st));
   CU(cudaStreamSynchronize(c->st));
-  int max_rt = 0;
-  for (int32_t v : hr) { if (v < 0) MB_FAIL(1, "chol_inv_jitter: no positive-definite jitter found for a task"); if (v > max_rt) max_rt = v; }
-  if (info3) { info3[0] = max_r0; info3[1] = max_rp; info3[2] = max_rt; }
+  int rc_tasks = 0;
+  if (c->h_pin_i[17] != 0) { mb_set_error(__FILE__, __LINE__, "chol_inv_jitter: no positive-definite jitter found for a task"); rc_tasks = 1; }
+  rc_tasks = ctx_agree(c, rc_tasks, c->st);
+  if (rc_tasks) return rc_tasks;
+  if (info3) { info3[0] = max_r0; info3[1] = max_rp; info3[2] = c->h_pin_i[16]; }
   return 0;
 }
 
@@ -882,12 +981,9 @@ static int dev_e_step(mb_context* c, int K, const mb_kernel* kern_k, const doubl
 static cudaError_t launch_chol_logdiag_any(mb_context* c, DenseWs& ws, const double* src, int n, int* info,
                                            double* out, cudaStream_t s) {
   if (dense_use_sm(n)) return launch_dense_cholinv_sm(src, n, nullptr, n, 0.0, 1, info, out, s);
-  if (dense_use_big(n)) {
-    const int64_t ldw = ((int64_t)n + 7) / 8 * 8;
-    return launch_big_cholinv_attempt(src, n, ws.Ap.as<double>(), ws.Bp.as<double>(), ldw, nullptr, n, 0.0, 0, 1,
-                                      ws.info.as<int>() + 4, info, out, s, &c->launches);
-  }
-  return launch_dense_chol_logdiag(src, ws.Ap.as<double>(), ws.Xd.as<double>(), n, info, out, s);
+  const int64_t ldw = ((int64_t)n + 7) / 8 * 8;
+  return launch_big_cholinv_attempt(src, n, ws.Ap.as<double>(), ws.Bp.as<double>(), ldw, nullptr, n, 0.0, 0, 1,
+                                    ws.info.as<int>() + 4, info, out, s, &c->launches);
 }
 
 static TaskObjArgs make_obj_args(mb_context* c, const DevKern& kd, const double* hp_dev, int64_t stride,
@@ -911,9 +1007,8 @@ static int shared_obj_eval(mb_context* c, TaskObjArgs a, const double* hp_host, 
   a.hp = c->hp_i.as<double>(); a.hp_stride = 0; a.want_grad = want_grad;
   MB_TRY(launch_obj(c, a, (int)c->db.n_tasks, c->st));
   MB_TRY(c->sums.ensure(64 * 8));
-  LAUNCH(c, launch_sum_sequential(a.f, c->db.n_tasks, 1, c->sums.as<double>(), c->st));
-  if (want_grad) LAUNCH(c, launch_colsum_sequential(a.g, c->db.n_tasks, P, c->sums.as<double>() + 1, c->st));
-  MB_TRY(ctx_allreduce(c, c->sums.p, 1 + (want_grad ? P : 0), c->st));
+  MB_TRY(leaf_sum_columns(c, a.f, 1, c->sums.as<double>(), c->st));
+  if (want_grad) MB_TRY(leaf_sum_columns(c, a.g, P, c->sums.as<double>() + 1, c->st));
   MB_TRY(d2h(c->h_pin, c->sums.p, (1 + P) * 8, c->st));
   CU(cudaStreamSynchronize(c->st));
   *f_out = c->h_pin[0];
@@ -1464,8 +1559,7 @@ static int dev_logL_monitoring(mb_context* c, const mb_kernel* kern_0, const dou
                                 c->f_t.as<double>(), c->g_t.as<double>());
   MB_TRY(launch_obj(c, a, (int)c->db.n_tasks, c->st));
   MB_TRY(c->sums.ensure(64 * 8));
-  LAUNCH(c, launch_sum_sequential(a.f, c->db.n_tasks, 1, c->sums.as<double>(), c->st));
-  MB_TRY(ctx_allreduce(c, c->sums.p, 1, c->st));
+  MB_TRY(leaf_sum_columns(c, a.f, 1, c->sums.as<double>(), c->st));
   // det term: chol(post_cov) without jitter (likelihoods.R:303-307)
   LAUNCH(c, launch_chol_logdiag_any(c, c->ws1, pc_dev, c->U, c->ws1.info.as<int>(), c->sums.as<double>() + 8, c->st));
   MB_TRY(d2h(c->h_pin, c->sums.p, 16 * 8, c->st));
@@ -1589,6 +1683,18 @@ extern "C" int mb_train_magma(mb_context* c, const mb_kernel* kern_0, double* hp
     bool bad = false;
     for (int p = 0; p < P0; ++p) if (isnan(h0[p])) bad = true;
     for (double v : htab) if (isnan(v)) { bad = true; break; }
+    // every rank takes the same branch: a NaN anywhere stops the fit everywhere (the ranks meet again in the next all-reduce)
+    if (c->world > 1) {
+      MB_TRY(c->sums.ensure(64 * 8));
+      const double flag = bad ? 1.0 : 0.0;
+      double tot = 0.0;
+      CU(cudaMemcpyAsync(c->sums.as<double>() + 33, &flag, 8, cudaMemcpyHostToDevice, c->st));
+      CU(cudaStreamSynchronize(c->st));
+      MB_TRY(ctx_allreduce(c, c->sums.as<double>() + 33, 1, c->st));
+      CU(cudaMemcpyAsync(&tot, c->sums.as<double>() + 33, 8, cudaMemcpyDeviceToHost, c->st));
+      CU(cudaStreamSynchronize(c->st));
+      bad = tot != 0.0;
+    }
     if (bad) break;
     double diff = new_ll - ll;
     if (isnan(diff)) diff = -INFINITY;
@@ -1810,7 +1916,7 @@ extern "C" int mb_bench_task_inverse(mb_context* c, const mb_kernel* kern_i, dou
 
 // Device-only timing of the HBM-bound kernels of the path on the resident dataset:
 //   what = 0  list_kern_to_cov: every task's covariance matrix written to HBM (bytes = 8 sum n_i^2 + table reads)
-//   what = 1  the E step's deterministic reduction of the per-CTA partial precision sums (bytes = 8 (G + 2) U^2)
+//   what = 1  the E step's fixed-tree reduction of the per-leaf precision sums (bytes = 8 (leaves + 2) U^2)
 // ms_out[0] = mean ms per repetition, bytes_out[0] = algorithmic bytes per repetition.
 extern "C" int mb_bench_hbm(mb_context* c, int what, const mb_kernel* kern_i, int reps, double* ms_out, double* bytes_out) {
   MB_TRY(need_db(c, what == 1));
@@ -1838,16 +1944,16 @@ extern "C" int mb_bench_hbm(mb_context* c, int what, const mb_kernel* kern_i, in
     bytes_out[0] = 8.0 * (double)total + 8.0 * (double)c->h_offs[M] * c->db.D + 8.0 * (double)M * kern_i->n_hp;
   } else if (what == 1) {
     const size_t UU = (size_t)c->U * c->U;
-    int G = c->sm_count * task_ctas_per_sm_any(c->db.nmax > TK_MAXN ? TK_MAXN : c->db.nmax, c->db.D);
-    if (G > c->db.n_tasks) G = (int)c->db.n_tasks;
-    MB_TRY(c->part_inv.ensure((size_t)G * UU * 8));
+    MB_TRY(ctx_leaves(c, c->U));
+    const int G = c->lv_n;
+    MB_TRY(c->leafbuf.ensure((size_t)G * UU * 8));
     MB_TRY(c->inv0.ensure(UU * 8));
     MB_TRY(c->post_inv.ensure(UU * 8));
-    CU(cudaMemsetAsync(c->part_inv.p, 0, (size_t)G * UU * 8, c->st));
+    CU(cudaMemsetAsync(c->leafbuf.p, 0, (size_t)G * UU * 8, c->st));
     CU(cudaMemsetAsync(c->inv0.p, 0, UU * 8, c->st));
     for (int it = -1; it < reps; ++it) {
       if (it == 0) CU(cudaEventRecord(e0, c->st));
-      LAUNCH(c, launch_reduce_partials(UU, G, c->inv0.as<double>(), c->part_inv.as<double>(), UU, c->post_inv.as<double>(), c->st));
+      LAUNCH(c, launch_reduce_tree(UU, G, c->inv0.as<double>(), c->leafbuf.as<double>(), UU, c->post_inv.as<double>(), c->st));
     }
     bytes_out[0] = 8.0 * (double)UU * (G + 2);
   } else {
@@ -2245,11 +2351,12 @@ extern "C" int mb_vm_step(mb_context* c, int n_clusters, const mb_kernel* kern_k
     for (int u = 0; u < U; ++u) m_k[(size_t)k * U + u] = mu;
   }
   MB_TRY(h2d(c->m0.p, m_k, (size_t)K * U * 8, c->st));
-  // pi_k = colMeans(tau) (:265-266)
-  for (int k = 0; k < K; ++k) {
-    long double s = 0.0L;
-    for (int64_t t = 0; t < M; ++t) s += tau[t * K + k];
-    prop_mixture[k] = (double)(s / M);
+  // pi_k = colMeans(tau) (:265-266) over the tasks of every rank
+  {
+    double colsum[MB_MAX_CLUSTERS];
+    MB_TRY(leaf_sum_columns_host(c, tau, K, colsum));
+    const double m_all = (double)(c->shard_set ? c->g_total : M);
+    for (int k = 0; k < K; ++k) prop_mixture[k] = colsum[k] / m_all;
   }
   MB_TRY(c->hp_k.ensure((size_t)M * Pi * 8));
   MB_TRY(h2d(c->hp_k.p, hp_i, (size_t)M * Pi * 8, c->st));
@@ -2335,11 +2442,21 @@ extern "C" int mb_elbo_monitoring(mb_context* c, int n_clusters, const mb_kernel
                                 c->pc.as<double>(), c->tau.as<double>(), c->f_t.as<double>(), c->g_t.as<double>());
   MB_TRY(launch_obj(c, a, (int)M, c->st));
   MB_TRY(c->sums.ensure(64 * 8));
-  LAUNCH(c, launch_sum_sequential(a.f, M, 1, c->sums.as<double>(), c->st));
-  MB_TRY(ctx_allreduce(c, c->sums.p, 1, c->st));
+  MB_TRY(leaf_sum_columns(c, a.f, 1, c->sums.as<double>(), c->st));
   MB_TRY(d2h(c->h_pin, c->sums.p, 8, c->st));
   CU(cudaStreamSynchronize(c->st));
   const double sum_ll_i = c->h_pin[0];
+  // sum_i tau_ik log(pi_k / tau_ik) over the tasks of every rank (elbos.R:249-256)
+  double sum_tau_k[MB_MAX_CLUSTERS];
+  {
+    std::vector<double> terms((size_t)M * K);
+    for (int64_t t = 0; t < M; ++t)
+      for (int k = 0; k < K; ++k) {
+        const double tk = tau[t * K + k], pi_k = prop_mixture[k];
+        terms[t * K + k] = (tk == 0.0 || pi_k == 0.0) ? 0.0 : tk * log(pi_k / tk);
+      }
+    MB_TRY(leaf_sum_columns_host(c, terms.data(), K, sum_tau_k));
+  }
   // cluster terms (elbos.R:209-219, 237-268)
   double sum_ll_k = 0.0, sum_corr = 0.0;
   double* hres = c->h_pin + 32;
@@ -2356,14 +2473,7 @@ extern "C" int mb_elbo_monitoring(mb_context* c, int n_clusters, const mb_kernel
     MB_TRY(d2h(c->h_pin_i, c->ws1.info.p, sizeof(int), c->st));
     CU(cudaStreamSynchronize(c->st));
     if (c->h_pin_i[0] != 0) MB_FAIL(1, "chol(cov_k) failed in elbo_monitoring_VEM (no jitter is applied there)");
-    double sum_tau = 0.0;
-    const double pi_k = prop_mixture[k];
-    for (int64_t t = 0; t < M; ++t) {
-      double tk = tau[t * K + k];
-      double lf = (tk == 0.0 || pi_k == 0.0) ? 0.0 : log(pi_k / tk);
-      sum_tau = sum_tau + tk * lf;
-    }
-    sum_corr += sum_tau + c->h_pin[8];
+    sum_corr += sum_tau_k[k] + c->h_pin[8];
   }
   *elbo = -sum_ll_k - sum_ll_i + sum_corr;
   return 0;

@@ -24,7 +24,7 @@
 
 struct BigSlot {
   cudaStream_t st = nullptr;
-  cudaEvent_t ev = nullptr;
+  cudaEvent_t ev = nullptr, ev_sc = nullptr;   // ev_sc: this slot's last E-step scatter
   double *W = nullptr, *Y = nullptr, *A = nullptr, *Bm = nullptr, *Sg = nullptr, *vec = nullptr, *gpart = nullptr,
          *spart = nullptr, *out = nullptr;
   int *fail = nullptr, *info = nullptr;
@@ -45,6 +45,7 @@ static void slot_free(BigSlot& s) {
   cudaFree(s.W); cudaFree(s.Y); cudaFree(s.A); cudaFree(s.Bm); cudaFree(s.Sg); cudaFree(s.vec); cudaFree(s.gpart);
   cudaFree(s.spart); cudaFree(s.out); cudaFree(s.fail); cudaFree(s.info);
   if (s.ev) cudaEventDestroy(s.ev);
+  if (s.ev_sc) cudaEventDestroy(s.ev_sc);
   if (s.st) cudaStreamDestroy(s.st);
   s = BigSlot();
 }
@@ -86,6 +87,7 @@ static int pool_ensure(BigTaskPool** pp, int nmax, int64_t n_tasks, bool need_gr
   for (auto& s : p->slots) {
     BT_CU(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
     BT_CU(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+    BT_CU(cudaEventCreateWithFlags(&s.ev_sc, cudaEventDisableTiming));
     BT_CU(cudaMalloc(&s.W, mat));
     BT_CU(cudaMalloc(&s.Y, mat));
     BT_CU(cudaMalloc(&s.A, mat));
@@ -417,16 +419,12 @@ int big_tasks_objective(BigTaskPool** pp, const TaskObjArgs& a, const int64_t* h
   return 0;
 }
 
-// E step / list_kern_to_inv.  part_inv / part_w must hold one zero-initialised accumulator per slot
-// (big_tasks_slots()); they are reduced in slot order by the caller.
-int big_tasks_slots(BigTaskPool** pp, int nmax, int64_t n_tasks) {
-  int rc = pool_ensure(pp, nmax, n_tasks, false);
-  if (rc) return rc < 0 ? rc : -2;
-  return (int)(*pp)->slots.size();
-}
-
+// E step / list_kern_to_inv.  With accumulators (a.part_inv: one zero-initialised [K x U x U | K x U] block per leaf,
+// a.part_stride apart; h_leaf_offs = first task of every leaf) the factorisations of consecutive tasks overlap on the pool's
+// streams while their scatters are chained by events, so every leaf receives its tasks in task order (deterministic, and
+// the same order as the shared-memory kernel of estep3.cu).
 int big_tasks_inverse(BigTaskPool** pp, const TaskInvArgs& a, const int64_t* h_offs, const int64_t* h_inv_offs,
-                      cudaStream_t st, int64_t* launches) {
+                      const int64_t* h_leaf_offs, cudaStream_t st, int64_t* launches) {
   const int64_t M = a.db.n_tasks;
   int rc = pool_ensure(pp, a.db.nmax, M, false);
   if (rc) return rc;
@@ -435,7 +433,10 @@ int big_tasks_inverse(BigTaskPool** pp, const TaskInvArgs& a, const int64_t* h_o
   std::vector<int64_t> todo;
   for (int64_t t = 0; t < M; ++t) todo.push_back(t);
   std::vector<int> rr(M, 0);
-  const size_t UU = (size_t)a.U * a.U;
+  std::vector<int> leaf_of(M, 0);
+  if (a.part_inv && h_leaf_offs)
+    for (int l = 0; l < a.n_leaves; ++l)
+      for (int64_t t = h_leaf_offs[l]; t < h_leaf_offs[l + 1]; ++t) leaf_of[t] = l;
   while (!todo.empty()) {
     rc = join_in(p, st);
     if (rc) return rc;
@@ -457,8 +458,11 @@ int big_tasks_inverse(BigTaskPool** pp, const TaskInvArgs& a, const int64_t* h_o
         double* al = s.vec;
         k_bt_gemv<<<(n + 7) / 8, 256, 0, s.st>>>(s.A, p->ldw, n, a.db.y + row0, al, nullptr, nullptr, s.fail);
         dim3 g2((n + 31) / 32, (n + 31) / 32), b2(32, 8);
-        k_bt_scatter<<<g2, b2, 0, s.st>>>(s.A, p->ldw, n, gi, a.tau, task, a.K, a.U, a.part_inv + (size_t)si * a.K * UU, al,
-                                          a.part_w ? a.part_w + (size_t)si * a.K * a.U : nullptr, s.fail);
+        if (q > 0) BT_CU(cudaStreamWaitEvent(s.st, p->slots[(q - 1) % S].ev_sc, 0));   // scatters in task order
+        k_bt_scatter<<<g2, b2, 0, s.st>>>(s.A, p->ldw, n, gi, a.tau, task, a.K, a.U,
+                                          a.part_inv + (size_t)leaf_of[task] * a.part_stride, al,
+                                          a.part_w ? a.part_w + (size_t)leaf_of[task] * a.part_stride : nullptr, s.fail);
+        BT_CU(cudaEventRecord(s.ev_sc, s.st));
         *launches += 2;
       }
       k_bt_status<<<1, 1, 0, s.st>>>(s.fail, rr[task], task, p->d_status, a.retries);

@@ -57,81 +57,6 @@ __global__ void k_legacy_builder(int which, const double* m1, int n1, const doub
   }
 }
 
-// Padded copy of the upper triangle of src (+ cumulative jitter) into A (np x np, identity on
-// the padding), kernel-to-matrices.R:672-678.
-__device__ inline void dense_load_padded(const double* src, int ld_src, double* A, int n, int np,
-                                         double pen, int retries) {
-  for (int e = threadIdx.x; e < np * np; e += blockDim.x) {
-    int i = e / np, j = e - i * np;
-    double v = 0.0;
-    if (i < n && j < n) {
-      if (j >= i) {
-        v = src[(size_t)i * ld_src + j];
-        if (i == j && retries >= 0) {
-          double q = pen;
-          for (int r = 0; r <= retries; ++r) { v += q; q = 10 * q; }
-        }
-      }
-    } else if (i == j) {
-      v = 1.0;
-    }
-    A[e] = v;
-  }
-  __syncthreads();
-}
-
-// chol_inv_jitter of one matrix by a single CTA (32 warps) with the tile algorithms of
-// tiles.cuh on L2-resident buffers.  src: n x n (upper triangle read); A, B: np x np scratch
-// (np = n rounded up to 8); Xd: (np / 8) * XD_STRIDE doubles; inv: n x n result (full, exactly
-// symmetric).  info[0] = retries (-1: gave up), out[0] = total jitter, out[1] = sum log diag(R).
-__global__ void __launch_bounds__(512) k_dense_cholinv(const double* src, int ld_src, double* A,
-                                                        double* B, double* Xd, double* inv, int n,
-                                                        double pen, int max_retry, int* info,
-                                                        double* out) {
-  __shared__ double red[32];
-  __shared__ int flag;
-  const int np = ((n + 7) / 8) * 8, n8 = np / 8;
-  int retries = 0;
-  double total = 0.0;
-  for (;;) {
-    double p = pen;
-    total = 0.0;
-    for (int r = 0; r <= retries; ++r) { total += p; p = 10 * p; }
-    dense_load_padded(src, ld_src, A, n, np, pen, retries);
-    if (chol_tiles<NWD>(A, Xd, n8, np, &flag) == 0) break;
-    __syncthreads();
-    if (++retries > max_retry) {
-      if (threadIdx.x == 0) { info[0] = -1; out[0] = total; out[1] = NAN; }
-      return;
-    }
-  }
-  double v[1] = {0.0};
-  for (int j = threadIdx.x; j < n; j += blockDim.x) v[0] += log(A[(size_t)j * np + j]);
-  blk_reduce_sum<1>(v, red);
-  if (threadIdx.x == 0) { info[0] = retries; out[0] = total; out[1] = v[0]; }
-  trtri_tiles<NWD>(A, Xd, B, n8, np);
-  lauum_tiles<NWD>(B, A, n8, np);
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-    int i = e / n, j = e - i * n;
-    inv[e] = A[(size_t)i * np + j];
-  }
-}
-
-// sum log diag chol(src) with NO jitter (likelihoods.R:303-307); info[0] = 0 or failing pivot.
-__global__ void __launch_bounds__(512) k_dense_chol_logdiag(const double* src, double* W, double* Xd,
-                                                             int n, int* info, double* out) {
-  __shared__ double red[32];
-  __shared__ int flag;
-  const int np = ((n + 7) / 8) * 8, n8 = np / 8;
-  dense_load_padded(src, n, W, n, np, 0.0, -1);
-  int r = chol_tiles<NWD>(W, Xd, n8, np, &flag);
-  if (r != 0) { if (threadIdx.x == 0) { info[0] = r; out[0] = NAN; } return; }
-  double v[1] = {0.0};
-  for (int j = threadIdx.x; j < n; j += blockDim.x) v[0] += log(W[(size_t)j * np + j]);
-  blk_reduce_sum<1>(v, red);
-  if (threadIdx.x == 0) { info[0] = 0; out[0] = v[0]; }
-}
-
 // log|det src| through LU with partial pivoting (determinant(), likelihoods.R:37-41).
 __global__ void __launch_bounds__(1024) k_dense_lu_logdet(const double* src, double* W, int n,
                                                           int* done, double* out) {
@@ -139,56 +64,6 @@ __global__ void __launch_bounds__(1024) k_dense_lu_logdet(const double* src, dou
   __syncthreads();
   double ldet = blk_lu_logabsdet(W, n, n, done);
   if (threadIdx.x == 0) out[0] = ldet;
-}
-
-// C[i*ldc + j] = sum_k A(i,k) B(k,j), A(i,k) = A[i*ars + k*acs], B(k,j) = B[k*brs + j*bcs];
-// optional C = beta*Cin + alpha*acc with Cin(i,j) = Cin[i*ldc + j].
-#define GT 64
-#define GK 16
-__global__ void __launch_bounds__(256) k_gemm(int m, int n, int kk, const double* A, int64_t ars,
-                                              int64_t acs, const double* B, int64_t brs,
-                                              int64_t bcs, double* C, int64_t ldc, double alpha,
-                                              const double* Cin, double beta) {
-  __shared__ double As[GK][GT + 1];
-  __shared__ double Bs[GK][GT + 1];
-  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-  const int i0 = blockIdx.y * GT, j0 = blockIdx.x * GT;
-  double acc[4][4] = {};
-  for (int k0 = 0; k0 < kk; k0 += GK) {
-    for (int e = threadIdx.x; e < GT * GK; e += 256) {
-      int r = e / GK, c = e % GK;  // A tile: 64 rows x 16 k
-      int gi = i0 + r, gk = k0 + c;
-      As[c][r] = (gi < m && gk < kk) ? A[gi * ars + gk * acs] : 0.0;
-      int bk = e / GT, bj = e % GT;  // B tile: 16 k x 64 cols
-      int gk2 = k0 + bk, gj = j0 + bj;
-      Bs[bk][bj] = (gk2 < kk && gj < n) ? B[gk2 * brs + gj * bcs] : 0.0;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < GK; ++k) {
-      double av[4], bv[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) av[a] = As[k][ty * 4 + a];
-#pragma unroll
-      for (int b = 0; b < 4; ++b) bv[b] = Bs[k][tx * 4 + b];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] += av[a] * bv[b];
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      int gi = i0 + ty * 4 + a, gj = j0 + tx * 4 + b;
-      if (gi < m && gj < n) {
-        double v = alpha * acc[a][b];
-        if (Cin) v += beta * Cin[gi * ldc + gj];
-        C[gi * ldc + gj] = v;
-      }
-    }
 }
 
 // y[i] = sum_k A[i*ld + k] x[k] (+ y0[i]); one warp per row, fixed summation tree.
@@ -267,37 +142,32 @@ __global__ void k_dense_obj_final(int n, int P, int nparts, const double* part, 
   }
 }
 
-// ---- small utilities -------------------------------------------------------------------
-// out[e] = base[e] + sum_g part[g][e], g ascending (deterministic): post_inv = inv_0 (+) sum_i.
-// Two levels: the partials are cut into RP_SLICES contiguous slices; 32 x RP_SLICES threads per block sum "their"
-// slice of 32 consecutive elements in ascending g (unit-stride 256-byte reads per warp), then the first warp adds the
-// slice sums in slice order on top of base.  The summation tree is fixed by (nparts) alone -- deterministic and
-// independent of the launch geometry -- and keeps 8x more loads in flight than one thread per element.
-#define RP_SLICES 8
-__global__ void __launch_bounds__(32 * RP_SLICES) k_reduce_partials(int64_t count, int nparts, const double* __restrict__ base,
-                                                                    const double* __restrict__ part, int64_t part_stride,
-                                                                    double* __restrict__ out) {
-  __shared__ double sh[RP_SLICES][32];
-  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
-  const int per = (nparts + RP_SLICES - 1) / RP_SLICES;
-  const int g0 = sl * per, g1 = min(nparts, g0 + per);
-  for (int64_t e0 = (int64_t)blockIdx.x * 32; e0 < count; e0 += (int64_t)gridDim.x * 32) {
-    const int64_t e = e0 + lane;
-    double acc = 0.0;
-    if (e < count) {
-      const double* p = part + e;
-#pragma unroll 8
-      for (int g = g0; g < g1; ++g) acc += __ldcs(p + (size_t)g * part_stride);
-    }
-    sh[sl][lane] = acc;
-    __syncthreads();
-    if (sl == 0 && e < count) {
-      double r = base ? base[e] : 0.0;
-#pragma unroll
-      for (int q = 0; q < RP_SLICES; ++q) r += sh[q][lane];
-      out[e] = r;
-    }
-    __syncthreads();
+// Sum of n partial vectors (part + g * part_stride, g < n) in a FIXED BINARY TREE over g: node (level, i) = node(level - 1,
+// 2 i) + node(level - 1, 2 i + 1); a missing right child passes the left one through.  For n a power of two the sum over an
+// aligned block of 2^k partials is a subtree, so reducing blocks separately (one per GPU) and then the block sums gives the
+// same bits as one reduction over all partials: this is what makes the E step independent of the number of GPUs.
+// One thread per element, unit-stride loads across the warp; out = base + tree (base may be NULL).
+template <int LOG>
+__device__ __forceinline__ bool tree_sum(const double* __restrict__ p, int64_t stride, int g0, int n, double& out) {
+  if (g0 >= n) return false;
+  if (LOG == 0) { out = __ldcg(p + (size_t)g0 * stride); return true; }
+  double l, r;
+  tree_sum<(LOG > 0 ? LOG - 1 : 0)>(p, stride, g0, n, l);
+  const bool hr = tree_sum<(LOG > 0 ? LOG - 1 : 0)>(p, stride, g0 + (1 << (LOG > 0 ? LOG - 1 : 0)), n, r);
+  out = hr ? l + r : l;
+  return true;
+}
+#define RT_MAX_LOG 8   /* up to 256 partials */
+__global__ void __launch_bounds__(256) k_reduce_tree(int64_t count, int n, const double* __restrict__ base,
+                                                     const double* __restrict__ part, int64_t part_stride,
+                                                     double* __restrict__ out) {
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < count; e += (int64_t)gridDim.x * 256) {
+    double v = 0.0;
+    if (n <= 2) tree_sum<1>(part + e, part_stride, 0, n, v);
+    else if (n <= 8) tree_sum<3>(part + e, part_stride, 0, n, v);
+    else if (n <= 32) tree_sum<5>(part + e, part_stride, 0, n, v);
+    else tree_sum<RT_MAX_LOG>(part + e, part_stride, 0, n, v);
+    out[e] = base ? base[e] + v : v;
   }
 }
 
@@ -322,6 +192,23 @@ __global__ void __launch_bounds__(256) k_sum_compensated(const double* v, int64_
     double S = 0.0, C = 0.0, plain = 0.0;
     for (int w = 0; w < 256; ++w) { neumaier_add(S, C, sh[w]); C += sc[w]; plain += sh[w]; }
     out[blockIdx.x] = isfinite(plain) ? S + C : plain;   // Inf / NaN propagate like a plain sum
+  }
+}
+
+// per-leaf version: block (p, l) sums column p of the row-major table v (P columns) over the tasks of leaf l
+__global__ void __launch_bounds__(256) k_leaf_sum_compensated(const double* v, int P, const int64_t* leaf_offs, double* out) {
+  __shared__ double sh[256], sc[256];
+  const int p = blockIdx.x, l = blockIdx.y;
+  const int64_t t0 = leaf_offs[l], t1 = leaf_offs[l + 1];
+  double s = 0.0, c = 0.0;
+  for (int64_t t = t0 + threadIdx.x; t < t1; t += 256) neumaier_add(s, c, v[t * P + p]);
+  sh[threadIdx.x] = s;
+  sc[threadIdx.x] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double S = 0.0, C = 0.0, plain = 0.0;
+    for (int i = 0; i < 256; ++i) { neumaier_add(S, C, sh[i]); C += sc[i]; plain += sh[i]; }
+    out[(size_t)l * P + p] = isfinite(plain) ? S + C : plain;   // Inf / NaN propagate like a plain sum
   }
 }
 
@@ -396,32 +283,10 @@ cudaError_t launch_legacy_builder(int which, const double* m1, int n1, const dou
   return cudaGetLastError();
 }
 
-cudaError_t launch_dense_cholinv(const double* src, int ld_src, double* A, double* B, double* Xd,
-                                 double* inv, int n, double pen, int* info, double* out,
-                                 cudaStream_t st) {
-  k_dense_cholinv<<<1, 512, 0, st>>>(src, ld_src, A, B, Xd, inv, n, pen, 40, info, out);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_dense_chol_logdiag(const double* src, double* W, double* Xd, int n, int* info,
-                                      double* out, cudaStream_t st) {
-  k_dense_chol_logdiag<<<1, 512, 0, st>>>(src, W, Xd, n, info, out);
-  return cudaGetLastError();
-}
-
-size_t dense_xd_doubles(int n) { return (size_t)((n + 7) / 8) * XD_STRIDE; }
 
 cudaError_t launch_dense_lu_logdet(const double* src, double* W, int n, int* done, double* out,
                                    cudaStream_t st) {
   k_dense_lu_logdet<<<1, 1024, 0, st>>>(src, W, n, done, out);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_gemm(int m, int n, int k, const double* A, int64_t ars, int64_t acs,
-                        const double* B, int64_t brs, int64_t bcs, double* C, int64_t ldc,
-                        double alpha, const double* Cin, double beta, cudaStream_t st) {
-  dim3 grid((n + GT - 1) / GT, (m + GT - 1) / GT);
-  k_gemm<<<grid, 256, 0, st>>>(m, n, k, A, ars, acs, B, brs, bcs, C, ldc, alpha, Cin, beta);
   return cudaGetLastError();
 }
 
@@ -450,12 +315,37 @@ cudaError_t launch_dense_obj(const DevKern& kd, const double* hp_host, const dou
   return launch_dense_obj_final3(n, want_grad ? kd.n_hp : 0, nparts, part, r, al, logdet, from_chol, S != nullptr, res, st);
 }
 
-cudaError_t launch_reduce_partials(int64_t count, int nparts, const double* base,
-                                   const double* part, int64_t part_stride, double* out,
-                                   cudaStream_t st) {
-  int64_t blocks = (count + 31) / 32;
-  if (blocks > 148 * 64) blocks = 148 * 64;
-  k_reduce_partials<<<(unsigned)blocks, 32 * RP_SLICES, 0, st>>>(count, nparts, base, part, part_stride, out);
+// out2[0] = max(retries), out2[1] = 1 when some task never factored (retries < 0); out2 is reset here
+__global__ void k_retry_stats(const int32_t* retries, int64_t n, int* out2) {
+  int mx = 0, bad = 0;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int v = retries[t];
+    if (v < 0) bad = 1;
+    if (v > mx) mx = v;
+  }
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  bad = __reduce_max_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0) { if (mx > 0) atomicMax(out2, mx); if (bad) atomicMax(out2 + 1, 1); }
+}
+cudaError_t launch_retry_stats(const int32_t* retries, int64_t n, int* out2, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(out2, 0, 2 * sizeof(int), st);
+  if (e != cudaSuccess) return e;
+  k_retry_stats<<<grid_for(n, 256), 256, 0, st>>>(retries, n, out2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_tree(int64_t count, int nparts, const double* base, const double* part, int64_t part_stride,
+                               double* out, cudaStream_t st) {
+  if (nparts < 1 || nparts > (1 << RT_MAX_LOG)) return cudaErrorInvalidValue;
+  int64_t blocks = (count + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_reduce_tree<<<(unsigned)blocks, 256, 0, st>>>(count, nparts, base, part, part_stride, out);
+  return cudaGetLastError();
+}
+
+// out[l * P + p] = compensated sum over the tasks t of leaf l of v[t * P + p]
+cudaError_t launch_leaf_sums(const double* v, int P, const int64_t* leaf_offs, int n_leaves, double* out, cudaStream_t st) {
+  k_leaf_sum_compensated<<<dim3((unsigned)P, (unsigned)n_leaves), 256, 0, st>>>(v, P, leaf_offs, out);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,155 @@
+// estep3.cu -- E step / VE step over all tasks (em-magma.R:25-82, vem-magmaclust.R:32-150) and list_kern_to_inv
+// (kernel-to-matrices.R:586-652): every task's chol_inv_jitter(K_i) in shared memory (device code in tasks3.cuh), then
+//   post_inv_k (+)= tau_ik K_i^{-1}   and   weighted_k (+)= tau_ik K_i^{-1} y_i     scattered onto the union grid.
+//
+// The reference adds the tasks one after the other (em-magma.R:39-46).  Here the GLOBAL task list is cut into a fixed number
+// of LEAVES (contiguous task ranges, api.cu:leaf_count -- fixed by the number of tasks and the grid size alone, not by the
+// number of GPUs, SMs or CTAs); every leaf owns one accumulator and receives its tasks IN TASK ORDER: the CTAs that share a
+// leaf factorise their tasks concurrently and take turns at the accumulator through a ticket counter.  The leaf sums are then
+// added in a fixed binary tree (dense.cu:k_reduce_tree).  Results are therefore bit-identical whatever the launch geometry
+// and however the leaves are dealt to GPUs; there are no FP64 atomics.
+// With one accumulator per leaf (<= 128 x 323 KB at U = 201) the read-modify-write traffic stays in L2.
+#include "tasks3.cuh"
+
+extern __shared__ double4 task3_smem_raw[];
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int KS, int N8C, bool D1>
+__global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_inverse3(const __grid_constant__ TaskInvArgs a) {
+  const int D = a.db.D, K = a.K, U = a.U;
+  const Sm3 s = carve3<N8C>((double*)task3_smem_raw, D);
+  const Ln L;
+  const int tid = threadIdx.x;
+  // accumulating launches: CTA -> (leaf, lane within the leaf); the CTAs of a leaf deal its tasks round-robin.
+  // list_kern_to_inv launches (no accumulators): plain grid-stride walk.
+  int leaf = 0;
+  int64_t t_first, t_end, t_step, leaf_t0 = 0;
+  if (a.part_inv) {
+    leaf = blockIdx.x % a.n_leaves;
+    leaf_t0 = a.leaf_offs[leaf];
+    t_first = leaf_t0 + blockIdx.x / a.n_leaves;
+    t_end = a.leaf_offs[leaf + 1];
+    t_step = a.ctas_per_leaf;
+  } else {
+    t_first = blockIdx.x; t_end = a.db.n_tasks; t_step = gridDim.x;
+  }
+  double* pinv = a.part_inv ? a.part_inv + (size_t)leaf * a.part_stride : nullptr;
+  double* pw = a.part_inv ? a.part_w + (size_t)leaf * a.part_stride : nullptr;
+  for (int64_t task = t_first; task < t_end; task += t_step) {
+    const int64_t row0 = a.db.offs[task];
+    const int n = (int)(a.db.offs[task + 1] - row0);
+    const int n8 = t3_n8(n), np = 8 * n8;
+    load_task3<N8C>(s, a.db, row0, n, np);
+    Cov<KS, D1> cov;
+    cov.init(a.kd, a.hp + task * a.hp_stride, s.xs, D);
+    double sumlog;
+    T3_MARK_DECL;
+    const int retries = task_inverse3<N8C>(s, n, n8, cov, a.pen, &sumlog, L, nullptr T3_MARK_PASS);
+    if (a.retries && tid == 0) a.retries[task] = retries;
+    const bool bad = retries < 0;
+    if (a.inv_out) {
+      double* o = a.inv_out + a.inv_offs[task];
+      for (int e = tid; e < n * n; e += T3_THREADS) o[e] = bad ? NAN : symA_at<N8C>(s.T1, e % n, e / n);
+    }
+    if (pinv) {
+      double* al = s.vout;
+      gemv3<N8C, 1>(s, n8, s.yv, al, L);
+      // ---- ordered section: wait for the previous task of this leaf
+      const int ticket = (int)(task - leaf_t0);
+      if (tid == 0) {
+        while (ld_acquire_gpu(a.tickets + leaf) != ticket) __nanosleep(100);
+      }
+      __syncthreads();
+      for (int k = 0; k < K; ++k) {
+        const double tau = a.tau ? a.tau[task * K + k] : 1.0;
+        double* pk = pinv + (size_t)k * U * U;
+        // read-modify-write of the leaf's accumulator in L2 (ld.cg / st.cg: other SMs wrote it before).  The grid positions
+        // of one task are distinct, so the targets of one task never alias: eight independent loads are in flight before
+        // the first store.
+        for (int e0 = tid; e0 < n * n; e0 += 8 * T3_THREADS) {
+          size_t c[8];
+          double v[8], old[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int e = e0 + q * T3_THREADS;
+            c[q] = 0; v[q] = 0.0; old[q] = 0.0;
+            if (e < n * n) {
+              const int i = e / n, j = e - i * n;
+              c[q] = (size_t)s.gi[i] * U + s.gi[j];
+              const double x = bad ? NAN : symA_at<N8C>(s.T1, i, j);
+              v[q] = a.tau ? tau * x : x;
+              old[q] = __ldcg(pk + c[q]);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (e0 + q * T3_THREADS < n * n) __stcg(pk + c[q], old[q] + v[q]);
+        }
+        double* wk = pw + (size_t)k * U;
+        for (int i = tid; i < n; i += T3_THREADS) {
+          const double v = bad ? NAN : al[i];
+          __stcg(wk + s.gi[i], __ldcg(wk + s.gi[i]) + (a.tau ? tau * v : v));
+        }
+      }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) st_release_gpu(a.tickets + leaf, ticket + 1);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- launchers --------------------------------------------------------------------------------------
+static inline bool is_se(const DevKern& kd) { return kd.n_terms == 1 && kd.types[0] == MB_KERN_SE; }
+
+template <int KS, int N8C, bool D1>
+static cudaError_t launch_inv3_t(const TaskInvArgs& a, int n_ctas, cudaStream_t st) {
+  const size_t smem = t3_smem_bytes<N8C>(a.db.D);
+  cudaError_t e = cudaFuncSetAttribute(k_task_inverse3<KS, N8C, D1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_task_inverse3<KS, N8C, D1><<<n_ctas, T3_THREADS, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+// n_ctas: with accumulators (a.part_inv) it must equal a.n_leaves * a.ctas_per_leaf and, when ctas_per_leaf > 1, fit the
+// device at once (the CTAs of a leaf wait for each other): see task3_max_ctas_per_sm().
+cudaError_t launch_task_inverse3(TaskInvArgs a, int n_ctas, cudaStream_t st) {
+  const bool small = a.db.nmax <= 64, d1 = a.db.D == 1;
+  if (is_se(a.kd)) {
+    if (d1) return small ? launch_inv3_t<KS_SE, 8, true>(a, n_ctas, st) : launch_inv3_t<KS_SE, 12, true>(a, n_ctas, st);
+    return small ? launch_inv3_t<KS_SE, 8, false>(a, n_ctas, st) : launch_inv3_t<KS_SE, 12, false>(a, n_ctas, st);
+  }
+  return small ? launch_inv3_t<KS_GEN, 8, false>(a, n_ctas, st) : launch_inv3_t<KS_GEN, 12, false>(a, n_ctas, st);
+}
+
+// resident CTAs per SM of the E-step kernel: the smallest figure over its instantiations for this task size
+int task3_max_ctas_per_sm(int nmax, int D) {
+  int best = 1 << 30;
+  auto probe = [&](auto kern, size_t smem) {
+    int n = 0;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, T3_THREADS, smem) != cudaSuccess) n = 1;
+    if (n < best) best = n;
+  };
+  if (nmax <= 64) {
+    const size_t smem = t3_smem_bytes<8>(D);
+    probe(k_task_inverse3<KS_SE, 8, true>, smem);
+    probe(k_task_inverse3<KS_SE, 8, false>, smem);
+    probe(k_task_inverse3<KS_GEN, 8, false>, smem);
+  } else {
+    const size_t smem = t3_smem_bytes<12>(D);
+    probe(k_task_inverse3<KS_SE, 12, true>, smem);
+    probe(k_task_inverse3<KS_SE, 12, false>, smem);
+    probe(k_task_inverse3<KS_GEN, 12, false>, smem);
+  }
+  cudaGetLastError();
+  return best > 0 && best < (1 << 30) ? best : 1;
+}

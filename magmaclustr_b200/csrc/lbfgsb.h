@@ -518,12 +518,20 @@ MB_HD int lb_formt(LbfgsbState* s) {
   return lb_formt_core<0>(s);
 }
 
-// Feed (f, g) evaluated at s->x.  A non-finite f ends the problem with fail = 99 (R raises
-// "L-BFGS-B needs finite values of 'fn'").
+// A non-finite objective (the covariance never factored, or overflow): R's optim stops with the error "L-BFGS-B needs
+// finite values of 'fn'" and no result.  The problem ends with fail = 99 and x = NaN, so that the callers' NaN guards
+// (training.R:956-963: keep the last valid hyper-parameters, stop) fire instead of training on from the failing trial point.
+MB_HD void lb_fail_nonfinite(LbfgsbState* s) {
+  s->fail = 99;
+  s->active = 0;
+  for (int i = 0; i < s->n; ++i) s->x[i] = NAN;
+}
+
+// Feed (f, g) evaluated at s->x.
 MB_HD void lb_advance(LbfgsbState* s, double f, const double* g) {
   if (!s->active) return;
   const int n = s->n;
-  if (!isfinite(f)) { s->fail = 99; s->active = 0; return; }
+  if (!isfinite(f)) { lb_fail_nonfinite(s); return; }
   s->f = f;
   for (int i = 0; i < n; ++i) s->g[i] = g[i];
   if (s->stage == LB_STAGE_START) {

@@ -216,7 +216,7 @@ __device__ __forceinline__ void lbw_advance(LbfgsbState* s, LbScratch* w, double
   if (lane == 0) {
     int code = 0;
     const int n = s->n;
-    if (!isfinite(f)) { s->fail = 99; s->active = 0; }
+    if (!isfinite(f)) lb_fail_nonfinite(s);
     else {
       s->f = f;
       for (int i = 0; i < n; ++i) s->g[i] = g[i];

@@ -279,55 +279,6 @@ __global__ void __launch_bounds__(256) k_task_objective(TaskObjArgs a) {
   }  // cluster passes
 }
 
-// ---------------------------------------------------------------------------------------
-// E step: persistent CTAs, each owning a contiguous run of tasks and a private partial of
-// the K precision sums / weighted sums, accumulated in task order (deterministic).
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_task_inverse(TaskInvArgs a) {
-  const int ld = a.ld, D = a.db.D, P = a.kd.n_hp, K = a.K, U = a.U;
-  TaskSmem s = carve((double*)task_smem_raw, a.db.nmax, ld, D);
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int64_t per = (a.db.n_tasks + gridDim.x - 1) / gridDim.x;
-  const int64_t t0 = (int64_t)blockIdx.x * per;
-  const int64_t t1 = (t0 + per < a.db.n_tasks) ? t0 + per : a.db.n_tasks;
-  double* pinv = a.part_inv ? a.part_inv + (size_t)blockIdx.x * K * U * U : nullptr;
-  double* pw = a.part_w ? a.part_w + (size_t)blockIdx.x * K * U : nullptr;
-  for (int64_t t = t0; t < t1; ++t) {
-    const int64_t row0 = a.db.offs[t];
-    const int n = (int)(a.db.offs[t + 1] - row0);
-    double hp[MB_MAX_HP];
-    for (int p = 0; p < P; ++p) hp[p] = a.hp[t * a.hp_stride + p];
-    load_task(s, a.db, row0, n);
-    double ldchol;
-    int retries = task_inverse(s, n, ld, D, a.kd, hp, nullptr, a.pen, &ldchol);
-    if (a.retries && tid == 0) a.retries[t] = retries;
-    if (retries < 0) {
-      // poison: the caller reports the failure through retries[t] = -1
-      for (int e = tid; e < n * n; e += nt) s.A[(e / n) * ld + e % n] = NAN;
-      __syncthreads();
-    }
-    if (a.inv_out) {
-      double* o = a.inv_out + a.inv_offs[t];
-      for (int e = tid; e < n * n; e += nt) o[e] = s.A[(e % n) * ld + e / n];
-    }
-    if (pinv) {
-      blk_gemv(s.al, s.A, s.yv, n, ld);  // inv_i %*% y_i
-      for (int k = 0; k < K; ++k) {
-        const double tau = a.tau ? a.tau[t * K + k] : 1.0;
-        double* pk = pinv + (size_t)k * U * U;
-        for (int e = tid; e < n * n; e += nt) {
-          int i = e / n, j = e % n;
-          size_t c = (size_t)s.gi[i] * U + s.gi[j];
-          pk[c] = pk[c] + (a.tau ? tau * s.A[i * ld + j] : s.A[i * ld + j]);
-        }
-        double* wk = pw + (size_t)k * U;
-        for (int i = tid; i < n; i += nt)
-          wk[s.gi[i]] = wk[s.gi[i]] + (a.tau ? tau * s.al[i] : s.al[i]);
-      }
-    }
-    __syncthreads();
-  }
-}
 
 // list_kern_to_cov: covariance or one derivative matrix per task, written column-major.
 __global__ void k_task_cov(TaskData db, DevKern kd, const double* hp, int64_t hp_stride,
@@ -486,29 +437,10 @@ cudaError_t launch_task_objective(TaskObjArgs a, int n_launch, cudaStream_t st) 
   return cudaGetLastError();
 }
 
-cudaError_t launch_task_inverse(TaskInvArgs a, int n_ctas, cudaStream_t st) {
-  a.ld = task_pick_ld(a.db.nmax);
-  size_t smem = task_smem_bytes(a.db.nmax, a.ld, a.db.D);
-  cudaError_t e = cudaFuncSetAttribute(k_task_inverse,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  k_task_inverse<<<n_ctas, pick_threads(a.db.nmax), smem, st>>>(a);
-  return cudaGetLastError();
-}
-
 cudaError_t launch_task_cov(TaskData db, DevKern kd, const double* hp, int64_t hp_stride,
                             int deriv, double* out, const int64_t* out_offs, cudaStream_t st) {
   k_task_cov<<<(unsigned)db.n_tasks, 256, 0, st>>>(db, kd, hp, hp_stride, deriv, out, out_offs);
   return cudaGetLastError();
-}
-
-int task_max_ctas_per_sm(int nmax, int D) {
-  int ld = task_pick_ld(nmax);
-  size_t smem = task_smem_bytes(nmax, ld, D);
-  int n = 0;
-  cudaFuncSetAttribute(k_task_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_task_inverse, pick_threads(nmax), smem);
-  return n > 0 ? n : 1;
 }
 
 cudaError_t launch_task_pred(TaskPredArgs a, int n_launch_tasks, cudaStream_t st) {

@@ -65,8 +65,15 @@ struct TaskInvArgs {       // E step / list_kern_to_inv
   int K;                     // clusters (weights tau), 1 for Magma
   const double* tau;         // n_tasks x K or NULL
   int U;
-  double* part_inv;          // gridDim.x x K x U x U partial precision sums (NULL = skip)
-  double* part_w;            // gridDim.x x K x U    partial weighted sums
+  // E step accumulators, one per LEAF (contiguous task range): leaf l adds into part_inv + l * part_stride (K x U x U
+  // precision sums) and part_w + l * part_stride (K x U weighted sums), in task order.  NULL = no accumulation.
+  double* part_inv;
+  double* part_w;
+  int64_t part_stride;       // doubles between the accumulators of consecutive leaves
+  const int64_t* leaf_offs;  // device, n_leaves + 1: first task of every leaf
+  int n_leaves;
+  int ctas_per_leaf;         // CTAs that share one leaf (ticket-ordered)
+  int* tickets;              // device, n_leaves, zero-initialised: tasks of the leaf already added
   double* inv_out;           // optional: all inverses, block t at inv_offs[t], column-major
   const int64_t* inv_offs;
   int32_t* retries;

@@ -1,0 +1,775 @@
+// tasks3.cuh -- device code of the per-task fused kernels (tasks3.cu: objective, estep3.cu: E step, mstep3.cu: M step).  One CTA of 4 warps per task,
+// four tasks resident per SM, every tile product on the FP64 tensor cores
+// (mma.sync.m8n8k4.f64 -> SASS DMMA; tcgen05 has no FP64 operand type).
+//
+// Shared-memory layout per task (N <= 64: 56 KB, so 4 CTAs share one SM):
+//   T1  upper triangle of 8x8 tiles, packed row by row      K -> R -> -X_ii R_im -> A = K^{-1}
+//   T2  full grid of 8x8 tiles                               X = R^{-1} (upper) -> B = S A
+//   * every tile is 64 contiguous doubles with the column index XOR-swizzled by ((row & 2) << 1): all four
+//     DMMA fragment patterns (row / column fragments, plain and transposed) and the double2 accumulator
+//     stores are bank-conflict free without padding;
+//   * tile strides are compile-time (N8C = 8 or 12 tiles per side) whatever the task's own size, so
+//     the unrolled inner loops address shared memory as register + immediate.
+//
+// Pipeline of one objective + gradient evaluation (reference lines in DESIGN.md):
+//   K = cov(x; theta) + jitter          build_cov3        kernel-to-matrices.R:71-503, :672
+//   K = R'R, blocked, NB = 8            chol3             chol()     -> dpotrf('U'): warp 0 eliminates an
+//                                                         8 x 32 row panel (diagonal tile + next three panel
+//                                                         tiles) in registers, one lane per column, one step
+//                                                         ahead of the other warps' trailing update
+//   X = R^{-1}                          scale3 + trtri3   chol2inv() -> dpotri('U')
+//   A = X X'                            lauum3
+//   al = A r (, be = A c1)              gemv3             one DMMA chain per row block
+//   B = S A, tr(A o S)                  S gathered from L2 straight into A-fragments, 8 accumulator tiles
+//   g_p = -1/2 sum (al al' + A B - A) o dK_p, upper tiles of A B contracted in registers
+#pragma once
+#include "linalg.cuh"
+#include "tasks.cuh"
+#include "tiles.cuh"
+#include "tile3.cuh"
+
+#define NW3 4
+#define T3_THREADS (32 * NW3)
+#define LOG_2PI 1.8378770664093453
+
+enum { KS_GEN = 0, KS_SE = 1 };
+
+// Optional phase timing (compile with -DT3_TIMING): thread 0 of every CTA adds the SM clock cycles spent
+// between marks to t3_phase_cycles[]; read with mb_debug_phase_cycles().  Not compiled into product builds.
+#ifdef T3_TIMING
+__device__ unsigned long long t3_phase_cycles[16];
+#define T3_MARK(idx) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&t3_phase_cycles[idx], (unsigned long long)(now_ - t3_last_)); t3_last_ = now_; } } while (0)
+#define T3_MARK_DECL long long t3_last_ = clock64()
+#define T3_MARK_ARG , long long& t3_last_
+#define T3_MARK_PASS , t3_last_
+extern "C" int mb_debug_phase_cycles(unsigned long long* out16, int reset) {
+  if (cudaMemcpyFromSymbol(out16, t3_phase_cycles, sizeof(unsigned long long) * 16) != cudaSuccess) return -2;
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(t3_phase_cycles, z, sizeof(z)); }
+  return 0;
+}
+#define T3_SUB_DECL long long t3c_ = clock64()
+#define T3_SUB(idx) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&t3_phase_cycles[idx], (unsigned long long)(now_ - t3c_)); t3c_ = now_; } } while (0)
+#else
+#define T3_SUB_DECL do { } while (0)
+#define T3_SUB(idx) do { } while (0)
+#define T3_MARK(idx) do { } while (0)
+#define T3_MARK_DECL do { } while (0)
+#define T3_MARK_ARG
+#define T3_MARK_PASS
+#endif
+
+template <int N8C>
+struct Lay {
+  static constexpr int NTRI = N8C * (N8C + 1) / 2;
+  static constexpr int NPAIR = (N8C / 2) * (N8C / 2 + 1) + ((N8C & 1) ? (N8C + 1) / 2 : 0);
+  // packed index of the diagonal tile (i, i); tile (i, j), i <= j, sits at tri(i) + j - i
+  __host__ __device__ static constexpr int tri(int i) { return i * N8C - (i * (i - 1)) / 2; }
+  // T2 is the larger of the full tile grid and the 2 x MB_MAX_CLUSTERS x np vectors of update_mixture
+  static constexpr size_t T2_DOUBLES = ((size_t)N8C * N8C * 64 > (size_t)2 * MB_MAX_CLUSTERS * 8 * N8C)
+                                           ? (size_t)N8C * N8C * 64 : (size_t)2 * MB_MAX_CLUSTERS * 8 * N8C;
+};
+
+struct Sm3 {
+  double *T1, *T2, *xs, *vin, *vout, *yv, *rinv, *red;
+  int *gi, *done, *flag;
+  unsigned short *tab, *tab2;
+};
+
+__host__ __device__ inline int t3_n8(int n) { return (n + 7) >> 3; }
+__host__ __device__ inline int t3_ntri(int n8) { return (n8 * (n8 + 1)) >> 1; }
+
+template <int N8C>
+__host__ __device__ inline size_t t3_smem_bytes(int D) {
+  const int np = 8 * N8C;
+  size_t dbl = (size_t)Lay<N8C>::NTRI * 64 + Lay<N8C>::T2_DOUBLES + (size_t)np * D + 6 * (size_t)np + 16 * NW3;
+  size_t ints = 2 * (size_t)np + 4;
+  size_t sh = ((size_t)Lay<N8C>::NTRI + 3) & ~(size_t)3;
+  size_t sh2 = ((size_t)Lay<N8C>::NPAIR + 3) & ~(size_t)3;
+  return dbl * sizeof(double) + ints * sizeof(int) + (sh + sh2) * sizeof(unsigned short);
+}
+
+template <int N8C>
+__device__ inline Sm3 carve3(double* base, int D) {
+  const int np = 8 * N8C;
+  Sm3 s;
+  s.T1 = base;
+  s.T2 = s.T1 + (size_t)Lay<N8C>::NTRI * 64;
+  s.xs = s.T2 + Lay<N8C>::T2_DOUBLES;
+  s.vin = s.xs + (size_t)np * D;      // [r | c1]
+  s.vout = s.vin + 2 * np;            // [al | be]
+  s.yv = s.vout + 2 * np;
+  s.rinv = s.yv + np;
+  s.red = s.rinv + np;
+  s.gi = (int*)(s.red + 16 * NW3);
+  s.done = s.gi + np;
+  s.flag = s.done + np;
+  s.tab = (unsigned short*)(s.flag + 4);
+  s.tab2 = s.tab + (((size_t)Lay<N8C>::NTRI + 3) & ~(size_t)3);
+  return s;
+}
+
+// A-operand fragments of row block i of the symmetric matrix held as packed upper tiles in T1;
+// with k a compile-time constant both candidates are register + immediate loads
+template <int N8C>
+struct SymRow {
+  const double *r0, *r1, *c0;
+  int i;
+  __device__ __forceinline__ SymRow(const double* T1, int i_, const Ln& L) {
+    i = i_;
+    const double* rb = T1 + (size_t)(Lay<N8C>::tri(i_) - i_) * 64;
+    r0 = rb + L.o_gt; r1 = rb + (L.o_gt ^ 4);
+    c0 = T1 + (size_t)i_ * 64 + L.o_tg;
+  }
+  __device__ __forceinline__ void aop(int k, double& x0, double& x1) const {
+    if (i <= k) { x0 = r0[k * 64]; x1 = r1[k * 64]; }
+    else { const int o = (Lay<N8C>::tri(k) - k) * 64; x0 = c0[o]; x1 = c0[o + 32]; }
+  }
+};
+// B-operand fragment of the symmetric tile (k, j), both compile-time after unrolling
+template <int N8C>
+__device__ __forceinline__ void sym_bop(const double* T1, int k, int j, const Ln& L, double& x0, double& x1) {
+  if (k <= j) cf(T1 + (size_t)(Lay<N8C>::tri(k) + j - k) * 64, L, x0, x1);
+  else rf(T1 + (size_t)(Lay<N8C>::tri(j) + k - j) * 64, L, x0, x1);
+}
+template <int N8C>
+__device__ __forceinline__ double symA_at(const double* T1, int r, int c) {
+  const int i = r >> 3, j = c >> 3;
+  if (i <= j) return T1[(size_t)(Lay<N8C>::tri(i) + j - i) * 64 + sw(r & 7, c & 7)];
+  return T1[(size_t)(Lay<N8C>::tri(j) + i - j) * 64 + sw(c & 7, r & 7)];
+}
+
+// deterministic CTA sum of NV values per thread (4 warps); result in every thread
+template <int NV>
+__device__ __forceinline__ void red3(double* v, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    double x = v[q];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(FULLMASK, x, off);
+    if (lane == 0) red[q * NW3 + warp] = x;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NV; ++q) v[q] = ((red[q * NW3] + red[q * NW3 + 1]) + red[q * NW3 + 2]) + red[q * NW3 + 3];
+  __syncthreads();
+}
+
+// ---- covariance functors ------------------------------------------------------------------------
+template <int KS, bool D1> struct Cov;
+
+// single SE term (+ noise): kernels.R:182-189, kernel-to-matrices.R:481-487.  D1: one input column.
+template <bool D1> struct Cov<KS_SE, D1> {
+  static constexpr int NG = 3;
+  double v, hel, en;
+  int has_noise, D;
+  const double* xs;
+  __device__ __forceinline__ void init(const DevKern& kd, const double* hp, const double* xs_, int D_) {
+    v = hp[0]; hel = exp(-hp[1]) * 0.5; has_noise = kd.has_noise; en = kd.has_noise ? exp(hp[2]) : 0.0;
+    xs = xs_; D = D_;
+  }
+  __device__ __forceinline__ void sums(int r, int c, double& d2, double& l1) const {
+    if (D1) {
+      const double df = xs[r] - xs[c];
+      d2 = df * df; l1 = fabs(df);
+    } else {
+      d2 = 0.0; l1 = 0.0;
+      for (int q = 0; q < D; ++q) { double df = xs[r * D + q] - xs[c * D + q]; d2 += df * df; l1 += fabs(df); }
+    }
+  }
+  static constexpr bool CACHEABLE = true;
+  // value and, in raw, the noise-free kernel value exp(v - top) that grad() needs again
+  __device__ __forceinline__ double value(int r, int c, double& raw) const {
+    double d2, l1;
+    sums(r, c, d2, l1);
+    double k = exp(v - hel * d2);
+    raw = k;
+    if (l1 < 0.000001) k += en;   // en == 0 without a noise HP
+    return k;
+  }
+  __device__ __forceinline__ void grad(double w, int r, int c, double* gacc) const {
+    double d2, l1;
+    sums(r, c, d2, l1);
+    const double top = hel * d2;
+    const double wk = w * exp(v - top);
+    gacc[0] += wk;
+    gacc[1] += wk * top;   // w * exp(v) * top * exp(-top) of the reference up to rounding
+    if (l1 < 0.000001) gacc[2] += w * en;
+  }
+  // same with exp(v - top) read back from the cache written by value() (bit-identical)
+  __device__ __forceinline__ void grad_cached(double w, int r, int c, double raw, double* gacc) const {
+    double d2, l1;
+    sums(r, c, d2, l1);
+    const double top = hel * d2;
+    const double wk = w * raw;
+    gacc[0] += wk;
+    gacc[1] += wk * top;
+    if (l1 < 0.000001) gacc[2] += w * en;
+  }
+};
+
+// any kernel of the reference's grammar (kernel-to-matrices.R:163-340)
+template <bool D1> struct Cov<KS_GEN, D1> {
+  static constexpr int NG = MB_MAX_HP;
+  const DevKern* kd;
+  double hp[MB_MAX_HP], hpe[MB_MAX_HP];
+  int D;
+  const double* xs;
+  __device__ __forceinline__ void init(const DevKern& kd_, const double* hp_, const double* xs_, int D_) {
+    kd = &kd_;
+    for (int p = 0; p < kd_.n_hp; ++p) hp[p] = hp_[p];
+    prep_hp(kd_, hp, hpe);
+    xs = xs_; D = D_;
+  }
+  static constexpr bool CACHEABLE = false;
+  __device__ __forceinline__ double value(int r, int c, double& raw) const {
+    raw = 0.0;
+    return cov_eval<false>(*kd, hp, hpe, xs + r * D, xs + c * D, D, true, nullptr);
+  }
+  __device__ __forceinline__ void grad_cached(double w, int r, int c, double, double* gacc) const { grad(w, r, c, gacc); }
+  __device__ __forceinline__ void grad(double w, int r, int c, double* gacc) const {
+    double dv[MB_MAX_HP];
+    cov_eval<true>(*kd, hp, hpe, xs + r * D, xs + c * D, D, true, dv);
+    for (int p = 0; p < kd->n_hp; ++p) gacc[p] += w * dv[p];
+  }
+};
+
+// ---- job tables ------------------------------------------------------------------------------------
+// tab : upper tiles (i <= j < n8) row by row, entry = (packed tile << 8) | (i << 4) | j
+// tab2: pairs of tiles (i, j), (i, j + 1) of one row, j = i, i + 2, ..., entry = (i << 4) | j
+template <int N8C>
+__device__ inline void build_tabs3(const Sm3& s, int n8) {
+  for (int i = threadIdx.x; i < n8; i += T3_THREADS) {
+    const int off = i * n8 - ((i * (i - 1)) >> 1);
+    for (int j = i; j < n8; ++j) s.tab[off + j - i] = (unsigned short)(((Lay<N8C>::tri(i) + j - i) << 8) | (i << 4) | j);
+    int off2 = 0;
+    for (int q = 0; q < i; ++q) off2 += (n8 - q + 1) >> 1;
+    for (int j = i; j < n8; j += 2, ++off2) s.tab2[off2] = (unsigned short)((i << 4) | j);
+  }
+}
+__device__ __forceinline__ int t3_npair(int n8) {
+  int c = 0;
+  for (int q = 0; q < n8; ++q) c += (n8 - q + 1) >> 1;
+  return c;
+}
+
+// ---- building blocks ---------------------------------------------------------------------------------
+// upper tiles of K + cumulative jitter (identity on the padding) into T1
+template <class CovT>
+__device__ inline void build_cov3(const Sm3& s, int n, int n8, const CovT& cov, double pen, int retries, const Ln& L,
+                                  double* kc = nullptr) {
+  const int ntri = t3_ntri(n8);
+  // three tiles (six independent exponentials) per lane and iteration: the evaluation is latency bound
+  for (int idx0 = L.warp; idx0 < ntri; idx0 += 3 * NW3) {
+    double o[3][2], raw[3][2];
+    int dst[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int idx = idx0 + u * NW3;
+      dst[u] = -1;
+      if (idx < ntri) {
+        const int e = s.tab[idx], i = (e >> 4) & 15, j = e & 15;
+        dst[u] = e >> 8;
+        const int r = 8 * i + L.g;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int c = 8 * j + 2 * L.t + q;
+          double v = 0.0;
+          raw[u][q] = 0.0;
+          if (r < n && c < n) {
+            v = cov.value(r, c, raw[u][q]);
+            if (r == c) {
+              double p = pen;
+              for (int k = 0; k <= retries; ++k) { v += p; p = 10 * p; }
+            }
+          } else if (r == c) {
+            v = 1.0;
+          }
+          o[u][q] = v;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 3; ++u)
+      if (dst[u] >= 0) {
+        *reinterpret_cast<double2*>(s.T1 + (size_t)dst[u] * 64 + L.o_c) = make_double2(o[u][0], o[u][1]);
+        if (CovT::CACHEABLE && kc)
+          reinterpret_cast<double2*>(kc + (size_t)dst[u] * 64)[L.lane] = make_double2(raw[u][0], raw[u][1]);
+      }
+  }
+  __syncthreads();
+}
+
+// A_ij -= R_ki' R_kj for the tile of job entry e (row k of R starts at packed tile dk)
+__device__ __forceinline__ void chol_update_tile(double* T1, int e, int k, int dk, const Ln& L) {
+  const int i = (e >> 4) & 15, j = e & 15;
+  double* Tij = T1 + (size_t)(e >> 8) * 64;
+  double2 cv = *reinterpret_cast<double2*>(Tij + L.o_c);
+  double a0, a1, b0, b1;
+  cf(T1 + (size_t)(dk + i - k) * 64, L, a0, a1);
+  cf(T1 + (size_t)(dk + j - k) * 64, L, b0, b1);
+  dmma884(cv.x, cv.y, -a0, b0);
+  dmma884(cv.x, cv.y, -a1, b1);
+  *reinterpret_cast<double2*>(Tij + L.o_c) = cv;
+}
+
+// Blocked upper Cholesky of the packed matrix in T1; the inverses of the diagonal tiles go to the
+// diagonal tiles of T2.  Warp 0 runs one step ahead: while warps 1..3 apply the trailing update of
+// step k it updates the first four tiles of row k+1 and eliminates that panel.
+// Returns 0 or a non-zero code (uniform) when a pivot fails.
+template <int N8C>
+__device__ inline int chol3(const Sm3& s, int n8, const Ln& L) {
+  const int vw = L.warp;
+  const int ntri = t3_ntri(n8);
+  if (threadIdx.x == 0) *s.flag = 0;
+  __syncthreads();
+  T3_SUB_DECL;
+  if (vw == 0) {
+    const int f = warp_factor_panel(s.T1, n8 < 4 ? n8 : 4, s.rinv, L.lane);
+    if (f) { if (L.lane == 0) *s.flag = f; }
+    else if (4 < n8 || n8 == 1) warp_diag_inverse(s.T1, s.rinv, s.T2, L.lane);
+  }
+  __syncthreads();
+  T3_SUB(9);
+  if (*s.flag) return *s.flag;
+  for (int k = 0; k + 1 < n8; ++k) {
+    const int dk = Lay<N8C>::tri(k);
+    double* Xkk = s.T2 + (size_t)(k * N8C + k) * 64;
+    const bool far = (k + 4 < n8);
+    if (far) {
+      // remaining panel tiles: R_kj = X_kk' A_kj
+      for (int j = k + 4 + vw; j < n8; j += NW3) {
+        double* Tkj = s.T1 + (size_t)(dk + j - k) * 64;
+        double a0, a1, b0, b1, c0 = 0.0, c1 = 0.0;
+        cf(Xkk, L, a0, a1);
+        cf(Tkj, L, b0, b1);
+        dmma884(c0, c1, a0, b0);
+        dmma884(c0, c1, a1, b1);
+        __syncwarp();
+        *reinterpret_cast<double2*>(Tkj + L.o_c) = make_double2(c0, c1);
+      }
+      __syncthreads();
+    }
+    T3_SUB(10);
+    // trailing update A_ij -= R_ki' R_kj, k < i <= j: jobs [j0, ntri) of the table
+    const int m = n8 - k - 1, nla = m < 4 ? m : 4;
+    const int j0 = (k + 1) * n8 - (((k + 1) * k) >> 1);
+    if (vw == 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < nla) chol_update_tile(s.T1, s.tab[j0 + q], k, dk, L);
+      __syncwarp();
+      T3_SUB(11);
+      const int f = warp_factor_panel(s.T1 + (size_t)Lay<N8C>::tri(k + 1) * 64, nla, s.rinv + 8 * (k + 1), L.lane);
+      T3_SUB(12);
+      if (f) { if (L.lane == 0) *s.flag = 8 * (k + 1) + f; }
+      else if (k + 5 < n8 || k + 2 == n8)
+        warp_diag_inverse(s.T1 + (size_t)Lay<N8C>::tri(k + 1) * 64, s.rinv + 8 * (k + 1),
+                          s.T2 + (size_t)((k + 1) * N8C + k + 1) * 64, L.lane);
+    } else {
+      if (!far && vw == NW3 - 1) warp_diag_inverse(s.T1 + (size_t)dk * 64, s.rinv + 8 * k, Xkk, L.lane);
+      for (int idx = j0 + nla + vw - 1; idx < ntri; idx += NW3 - 1) chol_update_tile(s.T1, s.tab[idx], k, dk, L);
+    }
+    T3_SUB(13);
+    __syncthreads();
+    T3_SUB(14);
+    if (*s.flag) return *s.flag;
+  }
+  return 0;
+}
+
+// off-diagonal tiles of T1: R_im <- -X_ii R_im, so that X_ij = sum_{i<m<=j} T1_im X_mj
+template <int N8C>
+__device__ inline void scale3(const Sm3& s, int n8, const Ln& L) {
+  const int ntri = t3_ntri(n8);
+  for (int idx = L.warp; idx < ntri; idx += NW3) {
+    const int e = s.tab[idx], i = (e >> 4) & 15, j = e & 15;
+    if (i == j) continue;
+    double* Tim = s.T1 + (size_t)(e >> 8) * 64;
+    double a0, a1, b0, b1, c0 = 0.0, c1 = 0.0;
+    rf(s.T2 + (size_t)(i * N8C + i) * 64, L, a0, a1);
+    cf(Tim, L, b0, b1);
+    dmma884(c0, c1, a0, -b0);
+    dmma884(c0, c1, a1, -b1);
+    __syncwarp();
+    *reinterpret_cast<double2*>(Tim + L.o_c) = make_double2(c0, c1);
+  }
+  __syncthreads();
+}
+
+// X = R^{-1} (upper tiles of T2); column blocks are independent, heavy and light ones alternate
+template <int N8C>
+__device__ inline void trtri3(const Sm3& s, int n8, const Ln& L) {
+  for (int q = L.warp, round = 0; q < n8; q += NW3, ++round) {
+    const int slot = (round >> 1) * NW3 + L.warp;
+    const int j = (round & 1) ? slot : n8 - 1 - slot;
+    const double* Xj = s.T2 + (size_t)j * 64;     // tile (m, j) at Xj + m * N8C * 64
+    for (int i = j - 1; i >= 0; --i) {
+      double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+      const double* Ti = s.T1 + (size_t)(Lay<N8C>::tri(i) - i) * 64;   // tile (i, m) at Ti + m * 64
+      int m = i + 1;
+      for (; m + 1 <= j; m += 2) {
+        double a0, a1, b0, b1, p0, p1, q0, q1;
+        rf(Ti + (size_t)m * 64, L, a0, a1);
+        cf(Xj + (size_t)m * N8C * 64, L, b0, b1);
+        rf(Ti + (size_t)(m + 1) * 64, L, p0, p1);
+        cf(Xj + (size_t)(m + 1) * N8C * 64, L, q0, q1);
+        dmma884(c0, c1, a0, b0);
+        dmma884(e0, e1, p0, q0);
+        dmma884(c0, c1, a1, b1);
+        dmma884(e0, e1, p1, q1);
+      }
+      if (m <= j) {
+        double a0, a1, b0, b1;
+        rf(Ti + (size_t)m * 64, L, a0, a1);
+        cf(Xj + (size_t)m * N8C * 64, L, b0, b1);
+        dmma884(c0, c1, a0, b0);
+        dmma884(c0, c1, a1, b1);
+      }
+      *reinterpret_cast<double2*>(s.T2 + (size_t)(i * N8C + j) * 64 + L.o_c) = make_double2(c0 + e0, c1 + e1);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+}
+
+// A = X X' into the packed tiles of T1 (diagonal tiles mirrored so the matrix is exactly symmetric)
+template <int N8C>
+__device__ inline void lauum3(const Sm3& s, int n8, const Ln& L) {
+  const int ntri = t3_ntri(n8);
+  for (int idx = L.warp; idx < ntri; idx += NW3) {
+    const int e = s.tab[idx], i = (e >> 4) & 15, j = e & 15;
+    const double* Xi = s.T2 + (size_t)i * N8C * 64;
+    const double* Xj = s.T2 + (size_t)j * N8C * 64;
+    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+    int m = j;
+    for (; m + 1 < n8; m += 2) {
+      double a0, a1, b0, b1, p0, p1, q0, q1;
+      rf(Xi + (size_t)m * 64, L, a0, a1);
+      rf(Xj + (size_t)m * 64, L, b0, b1);
+      rf(Xi + (size_t)(m + 1) * 64, L, p0, p1);
+      rf(Xj + (size_t)(m + 1) * 64, L, q0, q1);
+      dmma884(c0, c1, a0, b0);
+      dmma884(e0, e1, p0, q0);
+      dmma884(c0, c1, a1, b1);
+      dmma884(e0, e1, p1, q1);
+    }
+    if (m < n8) {
+      double a0, a1, b0, b1;
+      rf(Xi + (size_t)m * 64, L, a0, a1);
+      rf(Xj + (size_t)m * 64, L, b0, b1);
+      dmma884(c0, c1, a0, b0);
+      dmma884(c0, c1, a1, b1);
+    }
+    *reinterpret_cast<double2*>(s.T1 + (size_t)(e >> 8) * 64 + L.o_c) = make_double2(c0 + e0, c1 + e1);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < n8 * 64; e += T3_THREADS) {
+    const int k = e >> 6, r = (e >> 3) & 7, c = e & 7;
+    double* Tk = s.T1 + (size_t)Lay<N8C>::tri(k) * 64;
+    if (r > c) Tk[sw(r, c)] = Tk[sw(c, r)];
+  }
+  __syncthreads();
+}
+
+// chol_inv_jitter(K(x; hp)): T1 <- inverse (packed, exactly symmetric).  Returns retries or -1;
+// *sumlog = sum_j log R_jj (uniform).
+
+template <int N8C, class CovT>
+__device__ inline int task_inverse3(const Sm3& s, int n, int n8, const CovT& cov, double pen, double* sumlog, const Ln& L,
+                                    double* kc T3_MARK_ARG) {
+  int retries = 0;
+  for (;;) {
+    build_cov3(s, n, n8, cov, pen, retries, L, kc);
+    T3_MARK(1);
+    if (chol3<N8C>(s, n8, L) == 0) break;
+    __syncthreads();
+    if (++retries > TK_MAX_RETRY) return -1;
+  }
+  double v[1] = {0.0};
+  for (int j = threadIdx.x; j < n; j += T3_THREADS) v[0] += log(s.T1[(size_t)Lay<N8C>::tri(j >> 3) * 64 + sw(j & 7, j & 7)]);
+  red3<1>(v, s.red);
+  *sumlog = v[0];
+  T3_MARK(2);
+  scale3<N8C>(s, n8, L);
+  trtri3<N8C>(s, n8, L);
+  T3_MARK(3);
+  lauum3<N8C>(s, n8, L);
+  T3_MARK(4);
+  return retries;
+}
+
+// O[q][:] = A V[q][:] for q < NV <= 8 vectors of length np (V, O: NV x np), one DMMA chain per row block
+template <int N8C, int NV>
+__device__ inline void gemv3(const Sm3& s, int n8, const double* V, double* O, const Ln& L) {
+  const int np = 8 * n8;
+  for (int i = L.warp; i < n8; i += NW3) {
+    const SymRow<N8C> row(s.T1, i, L);
+    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < N8C; ++k) {
+      if (k < n8) {
+        double a0, a1;
+        row.aop(k, a0, a1);
+        const double b0 = (L.g < NV) ? V[L.g * np + 8 * k + L.t] : 0.0;
+        const double b1 = (L.g < NV) ? V[L.g * np + 8 * k + L.t + 4] : 0.0;
+        dmma884(c0, c1, a0, b0);
+        dmma884(c0, c1, a1, b1);
+      }
+    }
+    if (2 * L.t < NV) O[(2 * L.t) * np + 8 * i + L.g] = c0;
+    if (2 * L.t + 1 < NV) O[(2 * L.t + 1) * np + 8 * i + L.g] = c1;
+  }
+  __syncthreads();
+}
+
+template <int N8C>
+__device__ inline void load_task3(const Sm3& s, const TaskData& db, int64_t row0, int n, int np) {
+  for (int e = threadIdx.x; e < np * db.D; e += T3_THREADS) s.xs[e] = (e < n * db.D) ? db.X[row0 * db.D + e] : 0.0;
+  for (int i = threadIdx.x; i < np; i += T3_THREADS) {
+    s.yv[i] = (i < n) ? db.y[row0 + i] : 0.0;
+    s.gi[i] = (i < n) ? (db.gidx ? db.gidx[row0 + i] : i) : 0;
+  }
+  build_tabs3<N8C>(s, np >> 3);
+  __syncthreads();
+}
+
+// S(r, c): gathered post_cov block / corr2 of the ELBO (elbos.R:44-53)
+__device__ __forceinline__ double gather_S3(const TaskObjArgs& a, int mode, int64_t task, const int* gi, int r, int c, int n) {
+  if (r >= n || c >= n) return 0.0;
+  const int U = a.hpst.U;
+  if (mode == TK_OBJ_ELBO) {
+    double v = 0.0;
+    for (int k = 0; k < a.hpst.K; ++k) {
+      const double* mk = a.hpst.mean + (size_t)k * U;
+      const double* ck = a.hpst.cov + (size_t)k * U * U;
+      v = v + a.hpst.tau[task * a.hpst.K + k] * (mk[gi[r]] * mk[gi[c]] + ck[(size_t)gi[r] * U + gi[c]]);
+    }
+    return v;
+  }
+  return a.hpst.cov[(size_t)gi[r] * U + gi[c]];
+}
+
+// One evaluation of a task objective (+ gradient): f -> a.f[task] (K values in mode MIX), g -> a.g[task * P ..], written by
+// thread 0.  hp_eff: the task's HP vector (any address space).  do_load = false when the task's rows, outputs, grid indices
+// and job tables already sit in shared memory (they survive an evaluation: the fused M-step kernel loads them once per task).
+// MODE_T >= 0: the objective mode as a compile-time constant (the M step's TK_OBJ_MOD is instantiated that way: no
+// mode branches in the gather / product loops, the ELBO and mixture code is not in the binary); -1: mode at run time.
+template <int KS, int N8C, bool D1, int MODE_T>
+__device__ __forceinline__ void task_objective_eval3(const TaskObjArgs& a, const int64_t task, const double* hp_eff,
+                                                     const int64_t row0, const int n, const Sm3& s, const Ln& L,
+                                                     const bool do_load) {
+  const int mode = MODE_T >= 0 ? MODE_T : a.mode;
+  const int D = a.db.D, P = a.kd.n_hp, K = a.hpst.K, U = a.hpst.U;
+  const int n8 = t3_n8(n), np = 8 * n8, ntri = t3_ntri(n8);
+  const int tid = threadIdx.x;
+  double* rv = s.vin;
+  double* c1v = s.vin + np;
+  double* al = s.vout;
+  double* be = s.vout + np;
+  T3_MARK_DECL;
+  Cov<KS, D1> cov;
+  cov.init(a.kd, hp_eff, s.xs, D);
+  if (do_load) load_task3<N8C>(s, a.db, row0, n, np);
+  T3_MARK(0);
+  for (int i = tid; i < np; i += T3_THREADS) {
+    double r = 0.0, c = 0.0;
+    if (i < n) {
+      if (mode == TK_OBJ_ELBO) {
+        for (int k = 0; k < K; ++k) c = c + a.hpst.tau[task * K + k] * a.hpst.mean[(size_t)k * U + s.gi[i]];
+        r = s.yv[i];
+      } else if (mode != TK_OBJ_MIX) {
+        r = s.yv[i] - a.hpst.mean[s.gi[i]];
+      }
+    }
+    rv[i] = r;
+    c1v[i] = c;
+  }
+  double sumlog;
+  double* kc = (Cov<KS, D1>::CACHEABLE && a.kcache && a.want_grad) ? a.kcache + task * a.kcache_stride : nullptr;
+  const int retries = task_inverse3<N8C>(s, n, n8, cov, a.pen, &sumlog, L, kc T3_MARK_PASS);
+  if (a.retries && tid == 0) a.retries[task] = retries;
+  if (retries < 0) {
+    if (tid == 0) {
+      if (mode == TK_OBJ_MIX) for (int k = 0; k < K; ++k) a.f[task * K + k] = NAN;
+      else a.f[task] = NAN;
+      if (a.want_grad) for (int p = 0; p < P; ++p) a.g[task * P + p] = NAN;
+    }
+    return;
+  }
+  double logdetA;
+  if (a.logdet_chol) {
+    logdetA = -2.0 * sumlog;
+  } else {
+    // determinant() of the explicit inverse (likelihoods.R:37-41): LU on a row-major copy in T2
+    for (int e = tid; e < n * n; e += T3_THREADS) s.T2[e] = symA_at<N8C>(s.T1, e / n, e % n);
+    __syncthreads();
+    logdetA = blk_lu_logabsdet(s.T2, n, n, s.done);
+  }
+
+  if (mode == TK_OBJ_MIX) {
+    // update_mixture: K values of logL_GP_mod with the same inverse (vem-magmaclust.R:344-381)
+    double* V = s.T2;
+    double* O = s.T2 + (size_t)MB_MAX_CLUSTERS * np;
+    for (int e = tid; e < MB_MAX_CLUSTERS * np; e += T3_THREADS) {
+      const int k = e / np, i = e - k * np;
+      V[e] = (k < K && i < n) ? s.yv[i] - a.hpst.mean[(size_t)k * U + s.gi[i]] : 0.0;
+    }
+    __syncthreads();
+    gemv3<N8C, 8>(s, n8, V, O, L);
+    if (K > 8) gemv3<N8C, 8>(s, n8, V + 8 * np, O + 8 * np, L);
+    for (int k = 0; k < K; ++k) {
+      const double* ck = a.hpst.cov + (size_t)k * U * U;
+      double v[2] = {0.0, 0.0};
+      for (int i = tid; i < n; i += T3_THREADS) v[0] += V[k * np + i] * O[k * np + i];
+      for (int idx = L.warp; idx < ntri; idx += NW3) {
+        const int e = s.tab[idx], i = (e >> 4) & 15, j = e & 15;
+        const int r = 8 * i + L.g;
+        const double2 av = *reinterpret_cast<const double2*>(s.T1 + (size_t)(e >> 8) * 64 + L.o_c);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int c = 8 * j + 2 * L.t + q;
+          if (r < n && c < n && c >= r) {
+            const double w = (r == c) ? 1.0 : 2.0;
+            v[1] += w * ((q ? av.y : av.x) * ck[(size_t)s.gi[r] * U + s.gi[c]]);
+          }
+        }
+      }
+      red3<2>(v, s.red);
+      if (tid == 0) a.f[task * K + k] = 0.5 * (n * LOG_2PI - logdetA + v[0]) + 0.5 * v[1];
+    }
+    return;
+  }
+
+  if (mode == TK_OBJ_ELBO) gemv3<N8C, 2>(s, n8, s.vin, s.vout, L);
+  else gemv3<N8C, 1>(s, n8, s.vin, s.vout, L);
+  T3_MARK(5);
+
+  // B = S A with S taken from L2 as A-fragments; tr(A o S) on the way.  All (k, j) are compile-time:
+  // one accumulator tile per column block, every shared-memory address register + immediate.
+  double tr = 0.0;
+  for (int i = L.warp; i < n8; i += NW3) {
+    const SymRow<N8C> row(s.T1, i, L);
+    double sa[2 * N8C];
+#pragma unroll
+    for (int k = 0; k < N8C; ++k) {
+      sa[2 * k] = 0.0; sa[2 * k + 1] = 0.0;
+      if (k < n8) {
+        sa[2 * k] = gather_S3(a, mode, task, s.gi, 8 * i + L.g, 8 * k + L.t, n);
+        sa[2 * k + 1] = gather_S3(a, mode, task, s.gi, 8 * i + L.g, 8 * k + L.t + 4, n);
+        double a0, a1;
+        row.aop(k, a0, a1);
+        tr += sa[2 * k] * a0 + sa[2 * k + 1] * a1;
+      }
+    }
+    if (a.want_grad) {
+      double acc[2 * N8C];
+#pragma unroll
+      for (int j = 0; j < 2 * N8C; ++j) acc[j] = 0.0;
+#pragma unroll
+      for (int k = 0; k < N8C; ++k) {
+        if (k < n8) {
+#pragma unroll
+          for (int j = 0; j < N8C; ++j) {
+            if (j < n8) {
+              double b0, b1;
+              sym_bop<N8C>(s.T1, k, j, L, b0, b1);
+              dmma884(acc[2 * j], acc[2 * j + 1], sa[2 * k], b0);
+              dmma884(acc[2 * j], acc[2 * j + 1], sa[2 * k + 1], b1);
+            }
+          }
+        }
+      }
+      double* Bi = s.T2 + (size_t)i * N8C * 64 + L.o_c;
+#pragma unroll
+      for (int j = 0; j < N8C; ++j)
+        if (j < n8) *reinterpret_cast<double2*>(Bi + j * 64) = make_double2(acc[2 * j], acc[2 * j + 1]);
+    }
+  }
+  {
+    double v[3] = {0.0, tr, 0.0};
+    for (int i = tid; i < n; i += T3_THREADS) {
+      v[0] += rv[i] * al[i];
+      if (mode == TK_OBJ_ELBO) v[2] += al[i] * c1v[i];
+    }
+    T3_MARK(6);
+    red3<3>(v, s.red);   // also orders the B writes before the reads below
+    if (tid == 0) {
+      double f = 0.5 * (n * LOG_2PI - logdetA + v[0]);
+      if (mode == TK_OBJ_MOD) f = f + 0.5 * v[1];
+      if (mode == TK_OBJ_ELBO) f = f - v[2] + 0.5 * v[1];
+      a.f[task] = f;
+    }
+  }
+  T3_MARK(7);
+  if (!a.want_grad) return;
+
+  // gradient: upper tiles of T = A B, two tiles of one row per job (shared A fragments), contracted with
+  // dK on the fly
+  constexpr int NG = Cov<KS, D1>::NG;
+  double gacc[NG];
+#pragma unroll
+  for (int p = 0; p < NG; ++p) gacc[p] = 0.0;
+  const int npair = t3_npair(n8);
+  for (int q = L.warp; q < npair; q += NW3) {
+    const int e = s.tab2[q], i = e >> 4, j = e & 15;
+    const bool two = (j + 1 < n8);
+    const SymRow<N8C> row(s.T1, i, L);
+    const double* bb = s.T2 + (size_t)j * 64 + L.o_tg;   // B tile (k, j) at bb + k * N8C * 64
+    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < N8C; ++k) {
+      if (k < n8) {
+        double a0, a1, q0 = 0.0, q1 = 0.0;
+        row.aop(k, a0, a1);
+        const double b0 = bb[k * N8C * 64], b1 = bb[k * N8C * 64 + 32];
+        if (two) { q0 = bb[k * N8C * 64 + 64]; q1 = bb[k * N8C * 64 + 96]; }
+        dmma884(c0, c1, a0, b0);
+        dmma884(e0, e1, a0, q0);
+        dmma884(c0, c1, a1, b1);
+        dmma884(e0, e1, a1, q1);
+      }
+    }
+    const int r = 8 * i + L.g;
+    const double* Arow = s.T1 + (size_t)(Lay<N8C>::tri(i) + j - i) * 64 + L.o_c;
+    double2 kv[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
+    if (kc) {
+      const double2* kp = reinterpret_cast<const double2*>(kc + (size_t)(Lay<N8C>::tri(i) + j - i) * 64) + L.lane;
+      kv[0] = kp[0];
+      if (two) kv[1] = kp[32];
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 0 || two) {
+        const double2 av = *reinterpret_cast<const double2*>(Arow + h * 64);
+#pragma unroll
+        for (int qq = 0; qq < 2; ++qq) {
+          const int c = 8 * (j + h) + 2 * L.t + qq;
+          if (r < n && c < n && c >= r) {
+            const double tij = h ? (qq ? e1 : e0) : (qq ? c1 : c0);
+            const double arc = qq ? av.y : av.x;
+            double lr = al[r], lc = al[c];
+            if (mode == TK_OBJ_ELBO) { lr -= 2 * be[r]; lc -= 2 * be[c]; }
+            double w;
+            if (r == c) w = lr * al[r] + tij - arc;
+            else w = (lr * al[c] + lc * al[r]) + 2.0 * (tij - arc);
+            if (kc) cov.grad_cached(w, r, c, qq ? kv[h].y : kv[h].x, gacc);
+            else cov.grad(w, r, c, gacc);
+          }
+        }
+      }
+    }
+  }
+  T3_MARK(8);
+#pragma unroll
+  for (int p0 = 0; p0 < NG; p0 += 4) {
+    if (p0 < P) {
+      double v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = (p0 + q < NG) ? gacc[(p0 + q < NG) ? p0 + q : 0] : 0.0;
+      red3<4>(v, s.red);
+      if (tid == 0)
+        for (int q = 0; q < 4 && p0 + q < P; ++q) a.g[task * P + p0 + q] = -0.5 * v[q];
+    }
+  }
+}

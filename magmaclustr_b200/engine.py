@@ -59,6 +59,10 @@ class Context:
         self._ar_cb = L.ALLREDUCE_FN(_cb)
         check(L.lib().mb_set_allreduce(self._h, self._ar_cb, None, int(rank), int(world)))
 
+    def set_shard(self, first_task_global, n_tasks_global):
+        """Position of the resident tasks in the global task list (multi-GPU: results independent of the GPU count)."""
+        check(L.lib().mb_set_shard(self._h, int(first_task_global), int(n_tasks_global)))
+
     # ---- the five native builders (R matrices are column-major) ---------------------------
     def _legacy(self, name, m1, m2, par=None):
         m1 = np.asfortranarray(np.atleast_2d(np.asarray(m1, dtype=np.float64).T).T)

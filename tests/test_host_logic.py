@@ -129,14 +129,30 @@ def test_host_lbfgsb_matches_oracle_bitwise():
 
 
 def test_shard_tasks_partition():
+    """Shards are unions of whole E-step leaves (mb_shard_range): contiguous, covering, and nested -- the range of a rank
+    at world = 2 is the union of two ranges at world = 4 -- which is what makes the sums independent of the GPU count."""
+    import ctypes as C
     offs = np.r_[0, np.cumsum([64] * 10)]
-    parts = [shard_tasks(offs, r, 4) for r in range(4)]
+    parts = [shard_tasks(offs, r, 4, 201) for r in range(4)]
     assert parts[0][0] == 0 and parts[-1][1] == 10
     assert all(parts[i][1] == parts[i + 1][0] for i in range(3))
-    assert shard_tasks(offs, 0, 1) == (0, 10)
-    ragged = np.r_[0, np.cumsum([4, 4, 4, 4, 64, 4, 4])]
-    a, b = shard_tasks(ragged, 0, 2), shard_tasks(ragged, 1, 2)
-    assert a[1] == b[0] and b[1] == 7
+    assert shard_tasks(offs, 0, 1, 201) == (0, 10)
+    for m, u in ((10000, 201), (10000, 2000), (256, 4096), (70, 100), (11, 60)):
+        offs = np.arange(m + 1) * 8
+        nl = L.lib().mb_estep_leaves(m, u)
+        assert nl >= 1 and (nl & (nl - 1)) == 0 and nl <= min(128, m)
+        assert nl * (u * u + u) * 8 <= (1 << 30) or nl == 1
+        for world in (2, 4, 8):
+            if nl < world:
+                continue
+            pr = [shard_tasks(offs, r, world, u) for r in range(world)]
+            assert pr[0][0] == 0 and pr[-1][1] == m and all(pr[i][1] == pr[i + 1][0] for i in range(world - 1))
+            assert all(hi > lo for lo, hi in pr)
+            if world > 2:
+                half = [shard_tasks(offs, r, world // 2, u) for r in range(world // 2)]
+                assert all(half[r] == (pr[2 * r][0], pr[2 * r + 1][1]) for r in range(world // 2))
+    with pytest.raises(L.MagmaError):
+        shard_tasks(np.arange(4) * 8, 0, 8, 10)      # 3 tasks cannot feed 8 ranks
 
 
 _GLOO = r'''
@@ -150,8 +166,8 @@ dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 case = make_case(12, 9, 4)
 p, o = case["prep"], case["odb"]
-lo, hi = shard_tasks(p.offs, rank, world)
 U = len(p.grid_keys)
+lo, hi = shard_tasks(p.offs, rank, world, U)
 part = np.zeros((U, U)); w = np.zeros(U)
 for t in range(lo, hi):                      # this rank's partial precision / weighted sums
     i = p.ids[t]
