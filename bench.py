@@ -258,6 +258,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launches - launches0
     prof = ctx.profile_read()
+    cyc = ctx.mstep_cycles()
     ctx.profile(False)
     total_ms = float(np.sum(ms))
     evals_local = prof["evals"]
@@ -314,7 +315,12 @@ def main():
                    "step": "first EM iteration from the initial hyper-parameters, repeated",
                    "l2": "256 MiB flush between timed iterations",
                    "tasks_per_rank": int(hi_ - lo), "task_evals_per_step": int(stats[2]),
-                   "lockstep_rounds": int(stats[1]), "hp0_evals": int(stats[0]), "logL": logL},
+                   "lockstep_rounds": int(stats[1]), "hp0_evals": int(stats[0]),
+                   "tasks_stopped_on_nonfinite_objective": int(stats[3]), "logL": logL,
+                   "m_step": "lock-step rounds while > MB_FUSED_BELOW (default 3 x resident CTAs) tasks are active, then the "
+                             "persistent per-task optimiser kernel (objective + L-BFGS-B step fused, atomic task queue)",
+                   "m_step_eval_share_of_cta_cycles": (cyc["eval_cycles"] / (cyc["eval_cycles"] + cyc["optimiser_cycles"])
+                                                        if cyc["eval_cycles"] > 0 else None)},
         "clocks": clocks,
         "e2e": {"value": args.steps / (e2e_total * 1e-3), "unit": "EM steps/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -270,6 +270,12 @@ int mb_profile_read(mb_context*, double* out3);
 /* Call BEFORE mb_profile_read: out2[0] = stream milliseconds between consecutive profiled launches inside the
  * lock-step M step (optimiser advance kernel + host round trip), out2[1] = the longer gaps (E step, monitoring). */
 int mb_profile_read_gaps(mb_context*, double* out2);
+/* SM cycles the persistent per-task M-step kernel (R/em-magma.R:200-230: one optim() per task) of the last M step spent
+ * in objective evaluations (out2[0]) and in L-BFGS-B steps (out2[1]), summed over its CTAs.  Environment knobs read at
+ * mb_create: MB_FUSED_BELOW = number of still-active tasks below which the lock-step rounds hand over to the persistent
+ * kernel (default 3 x the resident CTAs; 0 = lock-step only; a huge value = persistent kernel from the first evaluation);
+ * MB_RESERVE_SMS = SMs kept free for the union-grid kernels of the concurrent hp_0 / cluster problem (default 4). */
+int mb_mstep_cycles(mb_context*, double* out2);
 /* Write `bytes` of device memory (L2 flush between timed iterations). */
 int mb_flush_l2(mb_context*, int64_t bytes);
 

@@ -28,6 +28,8 @@ cudaError_t launch_task_cov_sym(TaskData db, DevKern kd, const double* hp, int64
                                 const int64_t* out_offs, int sm_count, cudaStream_t st);
 cudaError_t launch_task_pred(TaskPredArgs a, int n_launch_tasks, cudaStream_t st);
 cudaError_t launch_task_objective3(TaskObjArgs a, int n_launch, cudaStream_t st);
+cudaError_t launch_task_optimise3(TaskObjArgs a, int* queue, int sm_count, int reserve_sms, unsigned long long* cycles,
+                                  cudaStream_t st);
 cudaError_t launch_task_inverse3(TaskInvArgs a, int n_ctas, cudaStream_t st);
 int task3_max_ctas_per_sm(int nmax, int D);
 
@@ -154,6 +156,13 @@ struct mb_context {
   cudaStream_t st = nullptr, st2 = nullptr, st3 = nullptr;   // st3: device-to-host copies of the round counters
   int64_t launches = 0;
   int logdet_chol = 0;
+  // per-task M step: lock-step rounds (one objective launch + one optimiser launch over all active tasks) while more than
+  // fused_below problems are still active, then the persistent kernel of mstep3.cu finishes every remaining trajectory.
+  // fused_below: -1 = 3 x the resident CTAs (default), 0 = lock-step only, a huge value = persistent kernel from the start
+  int64_t fused_below = -1;
+  int reserve_sms = 4;
+  bool single_blocking = false;
+  unsigned long long h_cycles[2] = {0, 0};
   // resident dataset
   bool have_db = false;
   TaskData db;
@@ -479,6 +488,9 @@ extern "C" int mb_create(mb_context** out, int device) {
   // reference's determinant() (LU of the explicit inverse, likelihoods.R:37-41) -- see DESIGN.md
   const char* env = getenv("MB_LOGDET");
   c->logdet_chol = (env && env[0] == 'l' && env[1] == 'u') ? 0 : 1;
+  if (const char* e = getenv("MB_FUSED_BELOW")) c->fused_below = atoll(e);
+  if (const char* e = getenv("MB_RESERVE_SMS")) { c->reserve_sms = atoi(e); if (c->reserve_sms < 0) c->reserve_sms = 0; if (c->reserve_sms > c->sm_count / 2) c->reserve_sms = c->sm_count / 2; }
+  c->single_blocking = getenv("MB_SINGLE_BLOCKING") != nullptr;
   *out = c;
   return 0;
 }
@@ -1047,14 +1059,45 @@ static int optimise(mb_context* c, std::vector<SingleProblem>& singles, bool tas
   bool tasks_active = tasks_on;
   if (tasks_on) {
     MB_TRY(c->lb.ensure(M * sizeof(LbfgsbState)));
-    MB_TRY(c->counters.ensure(4096 * sizeof(int)));
-    CU(cudaMemsetAsync(c->counters.p, 0, 4096 * sizeof(int), c->st));
+    MB_TRY(c->counters.ensure(4096 * sizeof(int) + 2 * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(c->counters.p, 0, 4096 * sizeof(int) + 2 * sizeof(unsigned long long), c->st));
     LAUNCH(c, launch_lbfgsb_init(c->lb.as<LbfgsbState>(), M, P_i, hp_i_dev, P_i, 1e13, 0.0, 25, c->st));
     if (skip_dev) LAUNCH(c, launch_lbfgsb_mask(c->lb.as<LbfgsbState>(), M, skip_dev, c->st));
     a.lb = c->lb.as<LbfgsbState>();
     a.hp = nullptr;
     a.want_grad = 1;
   }
+  // persistent-kernel path (mstep3.cu): objective modes of the DMMA kernel, tasks that fit shared memory
+  const int64_t fused_below = c->fused_below >= 0 ? c->fused_below
+                                                  : (int64_t)3 * c->sm_count * task_ctas_per_sm_any(c->db.nmax, c->db.D);
+  const bool fused_ok = tasks_on && fused_below > 0 && c->db.nmax <= TK_MAXN &&
+                        (a.mode == TK_OBJ_MOD || a.mode == TK_OBJ_ELBO);
+  bool fused_pending = fused_ok;
+  bool fused_now = fused_ok && M <= fused_below;     // few tasks (e.g. a shard of 8 GPUs): no lock-step round at all
+  auto launch_fused = [&]() -> int {
+    TaskObjArgs af = a;
+    const int n8 = 0; (void)n8;
+    af.kcache_stride = (int64_t)(a.db.nmax <= 64 ? 36 : 78) * 64;
+    MB_TRY(c->kcache.ensure((size_t)a.db.n_tasks * af.kcache_stride * 8));
+    af.kcache = c->kcache.as<double>();
+    int* queue = c->counters.as<int>() + 4095;
+    unsigned long long* cyc = reinterpret_cast<unsigned long long*>(c->counters.as<int>() + 4096);
+    const int reserve = singles.empty() ? 0 : c->reserve_sms;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->prof_on) {
+      if (c->prof_used == c->prof_ev.size()) {
+        CU(cudaEventCreate(&e0));
+        CU(cudaEventCreate(&e1));
+        c->prof_ev.push_back({e0, e1});
+      }
+      auto& ev = c->prof_ev[c->prof_used++];
+      e0 = ev.first; e1 = ev.second;
+      CU(cudaEventRecord(e0, c->st));
+    }
+    LAUNCH(c, launch_task_optimise3(af, queue, c->sm_count, reserve, cyc, c->st));
+    if (e1) CU(cudaEventRecord(e1, c->st));
+    return 0;
+  };
   size_t cur = 0;  // singles are optimised one after the other (they share ws0)
   // The host runs LB_LAG round(s) ahead of the device: round r + LB_LAG is enqueued before the active count of
   // round r is read, so the stream never drains between rounds.  The price is LB_LAG empty rounds at the end
@@ -1077,6 +1120,14 @@ static int optimise(mb_context* c, std::vector<SingleProblem>& singles, bool tas
   int* hinfo = c->h_pin_i + 8;
   while (tasks_active || cur < singles.size()) {
     bool progressed = false;
+    if (tasks_active && fused_pending && fused_now) {
+      // hand the remaining trajectories to the persistent kernel (it skips the problems that have stopped)
+      MB_TRY(launch_fused());
+      fused_pending = false;
+      tasks_active = false;
+      rounds = enq;
+      progressed = true;
+    }
     if (tasks_active && enq - read <= LB_LAG) {
       if (enq >= 4095) MB_FAIL(2, "L-BFGS-B lock-step did not terminate");
       MB_TRY(launch_obj(c, a, (int)M, c->st, true));
@@ -1094,7 +1145,7 @@ static int optimise(mb_context* c, std::vector<SingleProblem>& singles, bool tas
       SingleProblem& sp = singles[cur];
       if (!single_inflight) {
         if (!sp.s.active) { cur++; }
-        else if (dense_use_big(sp.n) || getenv("MB_SINGLE_BLOCKING")) {   // the large-matrix path synchronises inside (host jitter loop): blocking evaluation
+        else if (dense_use_big(sp.n) || c->single_blocking) {   // the large-matrix path synchronises inside (host jitter loop): blocking evaluation
           double f, g[MB_MAX_HP];
           MB_TRY(run_single_eval(c, sp, pen, &f, g));
           lb_advance(&sp.s, f, g);
@@ -1127,7 +1178,9 @@ static int optimise(mb_context* c, std::vector<SingleProblem>& singles, bool tas
       const bool idle = !progressed && !(cur < singles.size());
       const cudaError_t q = idle ? cudaEventSynchronize(c->ev_cp[read % RING]) : cudaEventQuery(c->ev_cp[read % RING]);
       if (q == cudaSuccess) {
-        if (c->h_pin_i[64 + (read % RING)] == 0) { tasks_active = false; rounds = read + 1; }
+        const int still = c->h_pin_i[64 + (read % RING)];
+        if (still == 0) { tasks_active = false; rounds = read + 1; }
+        else if (fused_pending && still <= fused_below) fused_now = true;   // the tail: one task's latency per round from here on
         read++;
       } else if (q != cudaErrorNotReady) {
         mb_set_error(__FILE__, __LINE__, cudaGetErrorString(q));
@@ -1142,6 +1195,7 @@ static int optimise(mb_context* c, std::vector<SingleProblem>& singles, bool tas
     std::vector<int> hf(M), hn(M);
     MB_TRY(d2h(hf.data(), c->fails.p, M * 4, c->st));
     MB_TRY(d2h(hn.data(), c->nfgv.p, M * 4, c->st));
+    if (fused_ok && !fused_pending) MB_TRY(d2h(c->h_cycles, c->counters.as<int>() + 4096, 2 * sizeof(unsigned long long), c->st));
     CU(cudaStreamSynchronize(c->st));
     int64_t tot = 0, bad = 0;
     for (int64_t t = 0; t < M; ++t) { tot += hn[t]; if (hf[t] == 99) bad++; }
@@ -1787,6 +1841,22 @@ extern "C" int mb_profile_read_gaps(mb_context* c, double* out2) {
   MB_TRY(prof_collect(c));
   out2[0] = c->prof_gap_ms; out2[1] = c->prof_other_ms;
   c->prof_gap_ms = 0; c->prof_other_ms = 0;
+  return 0;
+}
+// SM cycles the persistent M-step kernel of the LAST per-task M step spent in objective evaluations (out2[0]) and in
+// optimiser steps incl. the staging of the state (out2[1]), summed over its CTAs
+extern "C" int mb_mstep_cycles(mb_context* c, double* out2) {
+  MB_TRY(check_ctx(c));
+  out2[0] = (double)c->h_cycles[0]; out2[1] = (double)c->h_cycles[1];
+  return 0;
+}
+// diagnostics (tests / scripts/debug): the E step's last [post_inv | weighted] (which = 0) or its per-leaf sums (which = 1)
+extern "C" int mb_debug_estep_buffers(mb_context* c, int which, double* out, int64_t count) {
+  MB_TRY(check_ctx(c));
+  DBuf& b = which == 0 ? c->post_inv : c->leafbuf;
+  if (!b.p || (size_t)count * 8 > b.cap) MB_FAIL(-1, "buffer not available");
+  MB_TRY(d2h(out, b.p, (size_t)count * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
   return 0;
 }
 extern "C" int mb_flush_l2(mb_context* c, int64_t bytes) {

@@ -518,13 +518,18 @@ MB_HD int lb_formt(LbfgsbState* s) {
   return lb_formt_core<0>(s);
 }
 
-// A non-finite objective (the covariance never factored, or overflow): R's optim stops with the error "L-BFGS-B needs
-// finite values of 'fn'" and no result.  The problem ends with fail = 99 and x = NaN, so that the callers' NaN guards
-// (training.R:956-963: keep the last valid hyper-parameters, stop) fire instead of training on from the failing trial point.
+// A non-finite objective (a trial point of the line search at which the covariance overflows or never factors): R's optim
+// stops with the error "L-BFGS-B needs finite values of 'fn'" and train_magma aborts.  Here the problem ends with fail = 99
+// at its LAST ACCEPTED iterate (the start of the running line search; the initial point when the very first evaluation
+// fails), so that the caller neither trains on from the failing trial point nor loses the other tasks' work; the count of
+// such tasks is returned in stats[3] and their code by mb_last_task_status.
 MB_HD void lb_fail_nonfinite(LbfgsbState* s) {
   s->fail = 99;
   s->active = 0;
-  for (int i = 0; i < s->n; ++i) s->x[i] = NAN;
+  if (s->stage == LB_STAGE_LNSRCH) {
+    for (int i = 0; i < s->n; ++i) { s->x[i] = s->t[i]; s->g[i] = s->r[i]; }
+    s->f = s->fold;
+  }
 }
 
 // Feed (f, g) evaluated at s->x.

@@ -307,6 +307,18 @@ __global__ void __launch_bounds__(LB_ADV_THREADS) k_lbfgsb_advance(LbfgsbState* 
   if (lane == 0 && s->active) atomicAdd(n_active, 1);
 }
 
+// Entry point for the fused M-step kernel (mstep3.cu, linked as relocatable device code): the problem's state and scratch
+// sit at the given offsets (in doubles) of the CALLING kernel's dynamic shared memory -- `extern __shared__` arrays of all
+// translation units alias that one window, so the accesses below compile to shared-memory loads / stores, not generic ones.
+// Executed by one full warp; this unit is built with -fmad=false, which is the point of the separate compilation.
+__device__ __noinline__ void lbw_advance_smem(int state_off, int scratch_off, double f, const double* g, int lane) {
+  extern __shared__ double lb_dyn_smem[];
+  LbfgsbState* s = reinterpret_cast<LbfgsbState*>(lb_dyn_smem + state_off);
+  LbScratch* w = reinterpret_cast<LbScratch*>(lb_dyn_smem + scratch_off);
+  lbw_advance(s, w, f, g, lane);
+  __syncwarp();
+}
+
 // x -> HP table; fail codes and evaluation counts out.
 __global__ void k_lbfgsb_export(const LbfgsbState* st, int64_t m, int n, double* x,
                                 int64_t x_stride, int* fail, int* nfgv) {

@@ -276,6 +276,11 @@ class Context:
         return {"ms": out[0], "launches": int(out[1]), "evals": int(out[2]), "round_gap_ms": gaps[0],
                 "other_ms": gaps[1]}
 
+    def mstep_cycles(self):
+        out = np.zeros(2)
+        check(L.lib().mb_mstep_cycles(self._h, ptr(out)))
+        return {"eval_cycles": float(out[0]), "optimiser_cycles": float(out[1])}
+
     def flush_l2(self, nbytes=256 << 20):
         check(L.lib().mb_flush_l2(self._h, int(nbytes)))
 

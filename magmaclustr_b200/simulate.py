@@ -40,7 +40,20 @@ def _draw(rng, lo, hi, size=None):
 
 def simu_db(M=10, N=10, K=1, common_input=False, seed=0, pool=None):
     """Returns a legacy-format DataFrame (ID, Input, Output) with 1-D inputs, plus a
-    dict of the generating quantities."""
+    dict of the generating quantities.
+
+    The draws go through LAPACK / BLAS (Cholesky factor of an ill-conditioned covariance, L z), whose rounding depends on
+    the number of BLAS threads -- and torchrun sets OMP_NUM_THREADS = 1 for world > 1 only.  The generator therefore always
+    runs single-threaded, so that every rank of every world size simulates the SAME bits for a seed."""
+    try:
+        from threadpoolctl import threadpool_limits
+    except ImportError:                      # pragma: no cover
+        return _simu_db(M, N, K, common_input, seed, pool)
+    with threadpool_limits(limits=1):
+        return _simu_db(M, N, K, common_input, seed, pool)
+
+
+def _simu_db(M, N, K, common_input, seed, pool):
     rng = np.random.default_rng(seed)
     if pool is None:
         pool = np.round(np.arange(-1.0, 1.0 + 1e-9, 0.01), 2)

@@ -33,6 +33,7 @@ def test_c2_full_size_sampled_tasks(ctx):
     h0, hi, st = ctx.m_step(k0, hp0, ki, hpi, np.zeros(U), pm, pc)
     conv, nev = ctx.last_task_status()
     assert st[2] == nev.sum() and np.all(np.isfinite(hi))
+    assert st[3] == np.sum(conv == 99) and st[3] <= 5      # trial points with a non-finite objective (R would raise): reported
     rng = np.random.default_rng(0)
     for t in sorted(rng.choice(M, size=12, replace=False)):
         sl = slice(prep.offs[t], prep.offs[t + 1])

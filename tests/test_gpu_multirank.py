@@ -21,7 +21,7 @@ _SCRIPT = r'''
 import os, sys
 sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
 import numpy as np, torch, torch.distributed as dist
-from helpers import make_case
+from magmaclustr_b200 import _lib as L
 from magmaclustr_b200.engine import Context
 from magmaclustr_b200.parallel import shard_tasks
 
@@ -41,12 +41,26 @@ def hook(ptr, count):                     # sum all-reduce of `count` device dou
     t.copy_(h)
     torch.cuda.synchronize()
 
+# the inputs were simulated ONCE by the parent (the generator draws through LAPACK, whose rounding depends on the thread
+# count torchrun sets per world size): every world reads the same bits
+inputs = np.load(sys.argv[2])
+k0, ki = L.parse_kernel("SE", False), L.parse_kernel("SE", True)
+
+class Case(dict):
+    pass
+
+def load_case(tag):
+    c = Case({k: inputs[tag + "_" + k] for k in ("offs", "X", "y", "grid_index", "grid_X", "hp0", "hpi")})
+    c["k0"], c["ki"] = k0, ki
+    return c
+
 def shard(case, ctx):
-    p = case["prep"]
-    M = len(p.offs) - 1
-    lo, hi = shard_tasks(p.offs, rank, world, len(p.grid_X))
-    r0, r1 = int(p.offs[lo]), int(p.offs[hi])
-    ctx.upload_dataset((p.offs[lo:hi + 1] - p.offs[lo]).astype(np.int64), p.X[r0:r1], p.y[r0:r1], p.grid_index[r0:r1], p.grid_X)
+    M = len(case["offs"]) - 1
+    offs = case["offs"]
+    lo, hi = shard_tasks(offs, rank, world, len(case["grid_X"]))
+    r0, r1 = int(offs[lo]), int(offs[hi])
+    ctx.upload_dataset((offs[lo:hi + 1] - offs[lo]).astype(np.int64), case["X"][r0:r1], case["y"][r0:r1],
+                       case["grid_index"][r0:r1], case["grid_X"])
     if world > 1:
         ctx.set_allreduce(hook, rank, world)
         ctx.set_shard(lo, M)
@@ -55,7 +69,7 @@ def shard(case, ctx):
 res = {}
 ctx = Context(0)
 # ---- Magma: 70 ragged-grid tasks (64 leaves: some hold two tasks) ------------------------------------
-case = make_case(70, 12, 11)
+case = load_case("magma")
 lo, hi = shard(case, ctx)
 hpi = np.ascontiguousarray(case["hpi"][lo:hi])
 U = ctx.U
@@ -75,10 +89,10 @@ h0s, his, st = ctx.m_step(case["k0"], h0s, case["ki"], his, np.zeros(U), pm, pc,
 res["shared_hpi"] = his[0]
 res["shared_evals"] = np.array([st[1]])
 # ---- MagmaClust: ve_step / vm_step / elbo on 40 tasks, 3 clusters -------------------------------------
-case = make_case(40, 10, 4, shared=False, K=KC)
+case = load_case("clust")
 lo, hi = shard(case, ctx)
 U = ctx.U
-M = len(case["prep"].offs) - 1
+M = len(case["offs"]) - 1
 rng = np.random.default_rng(4)
 mix = rng.dirichlet(np.ones(KC), size=M).round(5)
 hp_k = np.array([[1.0 + 0.3 * k, -1.5 - 0.2 * k] for k in range(KC)])
@@ -102,22 +116,36 @@ print("rank", rank, "done")
 '''
 
 
-def _run(world, tmp_path, port):
+def _inputs(tmp_path):
+    from helpers import make_case
+    arrs = {}
+    for tag, case in (("magma", make_case(70, 12, 11)), ("clust", make_case(40, 10, 4, shared=False, K=3))):
+        p = case["prep"]
+        for k, v in (("offs", p.offs), ("X", p.X), ("y", p.y), ("grid_index", p.grid_index), ("grid_X", p.grid_X),
+                     ("hp0", case["hp0"]), ("hpi", case["hpi"])):
+            arrs[tag + "_" + k] = np.asarray(v)
+    path = tmp_path / "inputs.npz"
+    np.savez(path, **arrs)
+    return path
+
+
+def _run(world, tmp_path, port, inputs):
     script = tmp_path / "multirank.py"
     script.write_text(_SCRIPT % {"root": ROOT})
     out = tmp_path / ("world%d.npz" % world)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world,
-                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script), str(out)],
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script), str(out), str(inputs)],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     return np.load(out)
 
 
 def test_results_bit_identical_for_world_1_2_4(tmp_path):
-    ref = _run(1, tmp_path, 29631)
+    inputs = _inputs(tmp_path)
+    ref = _run(1, tmp_path, 29631, inputs)
     assert len(ref["seq"]) >= 2
     for world, port in ((2, 29632), (4, 29633)):
-        got = _run(world, tmp_path, port)
+        got = _run(world, tmp_path, port, inputs)
         for key in ref.files:
             assert got[key].shape == ref[key].shape, (world, key)
             assert np.array_equal(got[key], ref[key], equal_nan=True), (world, key, float(np.max(np.abs(got[key] - ref[key]))))
