@@ -53,14 +53,16 @@ def ini_hp4(*a):
     return ini_hp(*a)
 
 
-def make_inputs(m_tasks=M_TASKS):
+def make_inputs(broadcast=False):
+    """Dataset + initial HPs of config 2.  ini_hp_i: one draw PER TASK from hp()'s ranges (shared_hp = FALSE,
+    hyperparameters.R:70-77); broadcast = True repeats ONE draw for every task (an ini_hp_i without an ID
+    column, training.R:831-833) -- the variant round 1 measured, reported beside the headline."""
     from magmaclustr_b200.dataprep import Prepared
     from magmaclustr_b200.simulate import simu_db, ini_hp
     df, _ = simu_db(M=M_TASKS, N=N_POINTS, seed=DATA_SEED)
     prep = Prepared(df.ID.values, df.Input.values, df.Output.values)
     hp0 = ini_hp("SE", ["0"], True, False, HP0_SEED).drop(columns="ID").iloc[0].to_numpy(dtype=np.float64)
-    # ini_hp_i without an ID column is broadcast to every task (training.R:831-833)
-    hpi = ini_hp("SE", prep.ids, True, True, HPI_SEED).drop(columns="ID").to_numpy(dtype=np.float64)
+    hpi = ini_hp("SE", prep.ids, broadcast, True, HPI_SEED).drop(columns="ID").to_numpy(dtype=np.float64)
     return df, prep, np.ascontiguousarray(hp0), np.ascontiguousarray(hpi)
 
 
@@ -134,16 +136,18 @@ def dgemm_peak_tflops():
 
 
 def oracle_sample_step(df, m_sample, procs):
-    """One EM step of the oracle on the first m_sample tasks; returns (seconds, evals)."""
+    """One EM step of the oracle on the first m_sample tasks (ID order), from the bench's own initial HPs; returns
+    (seconds, evals, logL)."""
     from oracle import magma as OM
     from oracle import parallel as OP
     from magmaclustr_b200.simulate import ini_hp
-    ids = sorted(df.ID.unique(), key=lambda s: s.encode())[:m_sample]
-    sub = df[df.ID.isin(ids)]
+    all_ids = sorted(df.ID.unique(), key=lambda s: s.encode())
+    ids = all_ids[:m_sample]
+    sub = df[df.ID.isin(ids)] if m_sample < len(all_ids) else df
     db = OM.Dataset(sub.ID.values, sub.Input.values, sub.Output.values)
     h0 = ini_hp("SE", ["0"], True, False, HP0_SEED).drop(columns="ID").iloc[0].to_dict()
-    hi_row = ini_hp("SE", ["x"], True, True, HPI_SEED).drop(columns="ID").iloc[0].to_dict()
-    hi = {i: dict(hi_row) for i in db.ids}
+    tab = ini_hp("SE", all_ids, False, True, HPI_SEED).set_index("ID")      # the same per-task draws as the GPU arm
+    hi = {i: tab.loc[i].to_dict() for i in db.ids}
     t = time.perf_counter()
     _, _, ll, evals = OP.em_step(db, 0.0, "SE", "SE", h0, hi, 1e-10, procs)
     return time.perf_counter() - t, evals, ll
@@ -155,22 +159,32 @@ def run_reference(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count()
-    m_sample = args.cpu_sample or 2048      # a few seconds of CPU work per step
     df, _, _, _ = make_inputs()
+    n_runs = args.warmup + args.steps
+    budget_s = 200.0                        # the whole arm has to end within a few minutes
+    if args.cpu_sample:
+        m_sample = args.cpu_sample
+    else:                                   # ALL tasks per step when that fits the budget, else the largest sample that does
+        dt0, _, _ = oracle_sample_step(df, 1024, cores)
+        est_full = dt0 * M_TASKS / 1024.0
+        m_sample = M_TASKS if est_full * n_runs <= budget_s else int(max(1024, min(M_TASKS, M_TASKS * budget_s / (est_full * n_runs)))) // 256 * 256
     secs = []
-    for s in range(args.warmup + args.steps):
+    for s in range(n_runs):
         dt, evals, ll = oracle_sample_step(df, m_sample, cores)
         if s >= args.warmup:
             secs.append(dt)
     per_step_full = float(np.mean(secs)) * (M_TASKS / m_sample)
     value = 1.0 / per_step_full
-    sample = ("first %d of %d tasks per step (one EM step = e_step + m_step + logL_monitoring), "
-              "time scaled linearly in M (DESCRIPTION:23-24)" % (m_sample, M_TASKS))
+    sample = ("%s of %d tasks per step (one EM step = e_step + m_step + logL_monitoring), %.2f s measured per step%s"
+              % ("ALL" if m_sample == M_TASKS else "first %d" % m_sample, M_TASKS, float(np.mean(secs)),
+                 "" if m_sample == M_TASKS else ", scaled linearly in M (DESCRIPTION:23-24)"))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "EM steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": per_step_full * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2: train_magma EM step, M=10000 tasks x N=64, SE, shared_hp=FALSE, U=201"},
+            "config": {"workload": "C2: train_magma EM step (e_step + m_step + logL_monitoring), M=10000 tasks x N=64, SE kernel, "
+                                   "shared_hp=FALSE, U=201, seeds data=2024 hp_0=6 hp_i=106 (one hp_i draw per task)",
+                       "tasks_per_step": int(m_sample), "seconds_per_step_measured": float(np.mean(secs))},
             "cpu_baseline": {"value": value, "unit": "EM steps/s", "cores": cores, "kind": "port",
                              "sample": sample},
             "e2e": {"value": value, "unit": "EM steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -188,6 +202,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fit", action="store_true")
     ap.add_argument("--no-c4", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -299,6 +314,25 @@ def main():
         fit = {"em_steps": int(len(res["seq_loglikelihood"])), "converged": bool(res["converged"]),
                "seconds": time.perf_counter() - t0, "final_logL": float(res["seq_loglikelihood"][-1])}
 
+    # ---- the variant round 1 measured: ONE hp_i draw broadcast to every task (reported beside the headline) ----
+    variants = None
+    if world == 1 and not args.no_variants:
+        _, _, _, hpi_b = make_inputs(broadcast=True)
+        ctx.set_state(k0, hp0, ki, hpi_b, m0)
+        for _ in range(2):
+            ctx.em_step_resident(k0, ki, restart=True)
+        msb = []
+        for _ in range(max(3, args.steps // 2)):
+            ctx.flush_l2()
+            barrier()
+            ctx.timer_start()
+            llb, stb = ctx.em_step_resident(k0, ki, restart=True)
+            msb.append(ctx.timer_stop_ms())
+        variants = {"hp_i_broadcast_to_all_tasks": {"value": 1e3 / float(np.mean(msb)), "unit": "EM steps/s",
+                                                    "ms_per_step": float(np.mean(msb)), "task_evals_per_step": int(stb[2]),
+                                                    "lockstep_rounds": int(stb[1]), "logL": llb}}
+        ctx.set_state(k0, hp0, ki, hpi_loc, m0)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -311,7 +345,7 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C2: train_magma EM step (e_step + m_step + logL_monitoring), "
                                "M=10000 tasks x N=64, SE kernel, shared_hp=FALSE, U=201, seeds data=2024 "
-                               "hp_0=6 hp_i=106 (hp_i broadcast to all tasks)",
+                               "hp_0=6 hp_i=106 (one hp_i draw per task)",
                    "step": "first EM iteration from the initial hyper-parameters, repeated",
                    "l2": "256 MiB flush between timed iterations",
                    "tasks_per_rank": int(hi_ - lo), "task_evals_per_step": int(stats[2]),
@@ -336,6 +370,8 @@ def main():
     }
     if fit:
         line["fit"] = fit
+    if variants:
+        line["variants"] = variants
     if world == 1:
         # second half of BASELINE.json's metric: batched Cholesky FP64 TFLOP/s, device-only
         ms_inv, fl = ctx.bench_task_inverse(ki, reps=5)

@@ -44,51 +44,59 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_optimis
   // the evaluation leaves T2 free: optimiser state + scratch are staged there
   double* stage = s.T2;
   const int state_off = (int)(stage - (double*)task3_smem_raw);
-  int* sh_item = s.flag + 1;          // s.flag[0] belongs to chol3
-  long long t_eval = 0, t_adv = 0;
+  // per-CTA bookkeeping lives in 64 extra bytes of shared memory behind the evaluation's layout, not in registers (the
+  // evaluation needs all 128 of them): [0] queue item, [1] rows of the task, [2..3] first row, [4..7] cycle counters
+  int* book = reinterpret_cast<int*>(reinterpret_cast<char*>(task3_smem_raw) + t3_smem_bytes<N8C>(a.db.D));
+  long long* book_ll = reinterpret_cast<long long*>(book);
+  if (tid == 0) { book_ll[2] = 0; book_ll[3] = 0; }
   for (;;) {
-    if (tid == 0) *sh_item = atomicAdd(o.queue, 1);
+    if (tid == 0) book[0] = atomicAdd(o.queue, 1);
     __syncthreads();
-    const int item = *sh_item;
-    __syncthreads();
+    const int item = book[0];
     if (item >= o.n_items) break;
-    const int64_t task = item;
-    LbfgsbState* gs = const_cast<LbfgsbState*>(a.lb) + task;
-    if (!gs->active) continue;
-    const int64_t row0 = a.db.offs[task];
-    const int n = (int)(a.db.offs[task + 1] - row0);
+    {
+      const LbfgsbState* gs0 = a.lb + item;
+      if (!gs0->active) { __syncthreads(); continue; }
+      if (tid == 0) {
+        const int64_t r0 = a.db.offs[item];
+        book_ll[1] = r0;
+        book[1] = (int)(a.db.offs[item + 1] - r0);
+      }
+    }
+    __syncthreads();
     bool first = true;
     for (;;) {
-      long long c0 = 0;
-      if (o.cycles && tid == 0) c0 = clock64();
-      const double* hp_src = gs->x;
-      double hp_pre[3] = {0.0, 0.0, 0.0};
-      if (KS == KS_SE) { hp_pre[0] = hp_src[0]; hp_pre[1] = hp_src[1]; if (a.kd.has_noise) hp_pre[2] = hp_src[2]; }
-      task_objective_eval3<KS, N8C, D1, MODE_T>(a, task, KS == KS_SE ? hp_pre : hp_src, row0, n, s, L, first);
+      const int64_t task = book[0];
+      if (o.cycles && tid == 0) book_ll[4] = clock64();
+      {
+        const double* hp_src = a.lb[task].x;
+        double hp_pre[3] = {0.0, 0.0, 0.0};
+        if (KS == KS_SE) { hp_pre[0] = hp_src[0]; hp_pre[1] = hp_src[1]; if (a.kd.has_noise) hp_pre[2] = hp_src[2]; }
+        task_objective_eval3<KS, N8C, D1, MODE_T>(a, task, KS == KS_SE ? hp_pre : hp_src, book_ll[1], book[1], s, L, first);
+      }
       first = false;
       __syncthreads();
-      long long c1 = 0;
-      if (o.cycles && tid == 0) { c1 = clock64(); t_eval += c1 - c0; }
       {
+        const int64_t task2 = book[0];
+        LbfgsbState* gs = const_cast<LbfgsbState*>(a.lb) + task2;
+        if (o.cycles && tid == 0) { const long long c1 = clock64(); book_ll[2] += c1 - book_ll[4]; book_ll[4] = c1; }
         const double* src = reinterpret_cast<const double*>(gs);
         for (int e = tid; e < LB_STATE_DOUBLES; e += T3_THREADS) stage[e] = src[e];
-      }
-      __syncthreads();
-      if (L.warp == 0) lbw_advance_smem(state_off, state_off + LB_SCRATCH_OFF, a.f[task], a.g + task * a.kd.n_hp, L.lane);
-      __syncthreads();
-      {
+        __syncthreads();
+        if (L.warp == 0) lbw_advance_smem(state_off, state_off + LB_SCRATCH_OFF, a.f[task2], a.g + task2 * a.kd.n_hp, L.lane);
+        __syncthreads();
         double* dst = reinterpret_cast<double*>(gs);
         for (int e = tid; e < LB_STATE_DOUBLES; e += T3_THREADS) dst[e] = stage[e];
       }
       const int still = reinterpret_cast<const LbfgsbState*>(stage)->active;
       __syncthreads();
-      if (o.cycles && tid == 0) t_adv += clock64() - c1;
+      if (o.cycles && tid == 0) book_ll[3] += clock64() - book_ll[4];
       if (!still) break;
     }
   }
   if (o.cycles && tid == 0) {
-    atomicAdd(o.cycles, (unsigned long long)t_eval);
-    atomicAdd(o.cycles + 1, (unsigned long long)t_adv);
+    atomicAdd(o.cycles, (unsigned long long)book_ll[2]);
+    atomicAdd(o.cycles + 1, (unsigned long long)book_ll[3]);
   }
 }
 
@@ -97,7 +105,7 @@ static inline bool is_se(const DevKern& kd) { return kd.n_terms == 1 && kd.types
 
 template <int KS, int N8C, bool D1, int MODE_T>
 static cudaError_t launch_opt3_m(const TaskOptArgs& o, int n_ctas, cudaStream_t st) {
-  const size_t smem = t3_smem_bytes<N8C>(o.obj.db.D);
+  const size_t smem = t3_smem_bytes<N8C>(o.obj.db.D) + 64;   // + the kernel's bookkeeping words
   cudaError_t e = cudaFuncSetAttribute(k_task_optimise3<KS, N8C, D1, MODE_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k_task_optimise3<KS, N8C, D1, MODE_T><<<n_ctas, T3_THREADS, smem, st>>>(o);

@@ -44,12 +44,12 @@ def em_step(db, m_0, kern_0, kern_i, hp_0, hp_i, pen_diag=1e-10, procs=None):
     """One iteration of train_magma's loop body (training.R:905-1030), shared_hp = FALSE.
     Returns (new_hp_0, new_hp_i, logL, n_task_evals)."""
     procs = procs or os.cpu_count()
+    _limit_blas_threads()       # 64 x 64 matrices: BLAS threads only add overhead, and the pool below already uses every core
     U = db.grid_X.shape[0]
     m0 = M._mean_vec(m_0, U)
     pm, pc = M.e_step(db, m0, kern_0, kern_i, hp_0, hp_i, pen_diag)
     _G.update(db=db, hp_i=hp_i, kern_i=kern_i, pm=pm, pc=pc, pen=pen_diag)
     ctx = mp.get_context("fork")
-    _limit_blas_threads()
     with ctx.Pool(procs, initializer=_limit_blas_threads) as pool:
         fut = pool.map_async(_task_opt, db.ids, chunksize=max(1, len(db.ids) // (4 * procs)))
         new_hp_0, _ = M._optim(
