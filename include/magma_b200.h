@@ -65,6 +65,10 @@ int mb_kernel_parse(const char* kern, int has_noise, mb_kernel* out);
 const char* mb_kernel_hp_name(const mb_kernel* k, int p);
 /* counters: kernels launched by this context since creation (bench.py `gpu_launches`) */
 int64_t mb_launch_count(mb_context* ctx);
+/* tuning / diagnostic switches of one context: "fused_below" (MB_FUSED_BELOW), "reserve_sms" (MB_RESERVE_SMS),
+ * "dense_split" (0 = MB_DENSE_NOSPLIT), "logdet_chol" (0 = the reference's LU log-determinant, R/likelihoods.R:37-41,
+ * like MB_LOGDET=lu; 1 = read off the Cholesky diagonal).  The environment variables are read once at mb_create. */
+int mb_set_option(mb_context* ctx, const char* name, int64_t value);
 
 /* optional sum-all-reduce over ranks of `count` doubles in DEVICE memory, called on the
  * context's stream after it was synchronised (multi-GPU sharding).  The hook

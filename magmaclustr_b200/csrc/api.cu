@@ -54,7 +54,7 @@ cudaError_t launch_legacy_builder(int which, const double* m1, int n1, const dou
                                   int d, double par, double* out, cudaStream_t st);
 bool dense_sm_fits(int n);
 cudaError_t launch_dense_cholinv_sm(const double* src, int ld_src, double* inv, int n, double pen, int mode,
-                                    int* info, double* out, cudaStream_t st);
+                                    int* info, double* out, double* xt, cudaStream_t st);
 cudaError_t launch_gemm_dmma(int m, int n, int k, const double* A, int64_t ars, int64_t acs, const double* B,
                              int64_t brs, int64_t bcs, double* C, int64_t ldc, double alpha, const double* Cin,
                              double beta, cudaStream_t st);
@@ -161,7 +161,7 @@ struct mb_context {
   // fused_below: -1 = 3 x the resident CTAs (default), 0 = lock-step only, a huge value = persistent kernel from the start
   int64_t fused_below = -1;
   int reserve_sms = 4;
-  bool single_blocking = false;
+  bool single_blocking = false, split_lauum = true;
   unsigned long long h_cycles[2] = {0, 0};
   // resident dataset
   bool have_db = false;
@@ -470,6 +470,12 @@ extern "C" int mb_create(mb_context** out, int device) {
     MB_FAIL(-2, "no CUDA device: the magma_b200 library has no CPU fallback");
   }
   if (device < 0 || device >= ndev) MB_FAIL(-1, "bad device index");
+  // one process per GPU: kernel attributes (shared-memory opt-ins) and a few scratch buffers are set up once
+  // per process for the device of the first context; further contexts must use the same device
+  static int process_device = -1;
+  if (process_device >= 0 && process_device != device)
+    MB_FAIL(-1, "this process already drives another CUDA device: use one process per GPU");
+  process_device = device;
   CU(cudaSetDevice(device));
   mb_context* c = new mb_context();
   c->device = device;
@@ -491,6 +497,7 @@ extern "C" int mb_create(mb_context** out, int device) {
   if (const char* e = getenv("MB_FUSED_BELOW")) c->fused_below = atoll(e);
   if (const char* e = getenv("MB_RESERVE_SMS")) { c->reserve_sms = atoi(e); if (c->reserve_sms < 0) c->reserve_sms = 0; if (c->reserve_sms > c->sm_count / 2) c->reserve_sms = c->sm_count / 2; }
   c->single_blocking = getenv("MB_SINGLE_BLOCKING") != nullptr;
+  c->split_lauum = getenv("MB_DENSE_NOSPLIT") == nullptr;
   *out = c;
   return 0;
 }
@@ -528,6 +535,18 @@ extern "C" int mb_destroy(mb_context* c) {
 }
 
 extern "C" int64_t mb_launch_count(mb_context* c) { return c ? c->launches : 0; }
+
+// Tuning / diagnostic switches of a context (the environment variables of the same meaning are read once at mb_create)
+extern "C" int mb_set_option(mb_context* c, const char* name, int64_t value) {
+  if (!c || !name) MB_FAIL(-1, "null argument");
+  const std::string n(name);
+  if (n == "fused_below") c->fused_below = value;                 // MB_FUSED_BELOW
+  else if (n == "reserve_sms") c->reserve_sms = (int)(value < 0 ? 0 : (value > c->sm_count / 2 ? c->sm_count / 2 : value));   // MB_RESERVE_SMS
+  else if (n == "dense_split") c->split_lauum = value != 0;       // MB_DENSE_NOSPLIT (inverted)
+  else if (n == "logdet_chol") c->logdet_chol = value != 0;       // MB_LOGDET=lu <-> 0
+  else MB_FAIL(-1, "unknown option");
+  return 0;
+}
 
 extern "C" int mb_set_allreduce(mb_context* c, mb_allreduce_fn fn, void* user, int rank, int world) {
   if (!c) MB_FAIL(-1, "null ctx");
@@ -677,7 +696,8 @@ static int big_cholinv_sync(mb_context* c, DenseWs& ws, const double* src, int n
 static int dev_cholinv(mb_context* c, DenseWs& ws, const double* src, int n, double pen,
                        cudaStream_t s, int* retries, double* jitter, double* sumlogdiag) {
   if (dense_use_sm(n))
-    LAUNCH(c, launch_dense_cholinv_sm(src, n, ws.A.as<double>(), n, pen, 0, ws.info.as<int>(), ws.res.as<double>() + 16, s));
+    LAUNCH(c, launch_dense_cholinv_sm(src, n, ws.A.as<double>(), n, pen, 0, ws.info.as<int>(), ws.res.as<double>() + 16,
+                                      c->split_lauum ? ws.Bp.as<double>() : nullptr, s));
   else
     MB_TRY(big_cholinv_sync(c, ws, src, n, pen, 0, ws.A.as<double>(), ws.info.as<int>(), ws.res.as<double>() + 16, s));
   MB_TRY(d2h(c->h_pin_i, ws.info.p, sizeof(int), s));
@@ -875,7 +895,7 @@ static int dense_obj_enqueue(mb_context* c, DenseWs& ws, const DevKern& kd, cons
   LAUNCH(c, launch_dense_cov(kd, hp_host, X, n, X, n, D, -1, 1, ws.Kmat.as<double>(), n, 1, s));
   if (dense_use_sm(n))
     LAUNCH(c, launch_dense_cholinv_sm(ws.Kmat.as<double>(), n, ws.A.as<double>(), n, pen, 0, ws.info.as<int>(),
-                                      ws.res.as<double>() + 16, s));
+                                      ws.res.as<double>() + 16, c->split_lauum ? ws.Bp.as<double>() : nullptr, s));
   else
     MB_TRY(big_cholinv_sync(c, ws, ws.Kmat.as<double>(), n, pen, 0, ws.A.as<double>(), ws.info.as<int>(),
                             ws.res.as<double>() + 16, s));
@@ -992,7 +1012,7 @@ static int dev_e_step(mb_context* c, int K, const mb_kernel* kern_k, const doubl
 // sum log diag chol(src) without jitter (likelihoods.R:303-307, elbos.R:259-264)
 static cudaError_t launch_chol_logdiag_any(mb_context* c, DenseWs& ws, const double* src, int n, int* info,
                                            double* out, cudaStream_t s) {
-  if (dense_use_sm(n)) return launch_dense_cholinv_sm(src, n, nullptr, n, 0.0, 1, info, out, s);
+  if (dense_use_sm(n)) return launch_dense_cholinv_sm(src, n, nullptr, n, 0.0, 1, info, out, nullptr, s);
   const int64_t ldw = ((int64_t)n + 7) / 8 * 8;
   return launch_big_cholinv_attempt(src, n, ws.Ap.as<double>(), ws.Bp.as<double>(), ldw, nullptr, n, 0.0, 0, 1,
                                     ws.info.as<int>() + 4, info, out, s, &c->launches);
@@ -1922,7 +1942,7 @@ extern "C" int mb_bench_dense(mb_context* c, int what, int n, int reps, double* 
     } else if (what == 3) {   // the single-CTA shared-memory kernel of the union grid (n <= 224)
       if (!dense_sm_fits(n)) MB_FAIL(-1, "what = 3 needs n <= 224");
       LAUNCH(c, launch_dense_cholinv_sm(ws.Kmat.as<double>(), n, ws.A.as<double>(), n, 1e-10, 0, ws.info.as<int>(),
-                                        ws.res.as<double>() + 16, c->st));
+                                        ws.res.as<double>() + 16, c->split_lauum ? ws.Bp.as<double>() : nullptr, c->st));
     } else {
       CU(launch_big_cholinv_attempt(ws.Kmat.as<double>(), n, ws.Ap.as<double>(), ws.Bp.as<double>(), ldw, ws.A.as<double>(),
                                     n, 1e-10, 0, what == 1 ? 1 : 0, ws.info.as<int>() + 4, ws.info.as<int>(),

@@ -14,7 +14,6 @@
 
 #include <stdlib.h>
 
-#include <map>
 #include <utility>
 
 #define DSM_SPLIT_N 128   /* smallest matrix for which the X X' product leaves the single CTA */
@@ -309,8 +308,11 @@ __global__ void k_resid_gemv(int n, const double* A, const double* y, const doub
 }
 
 // ---- launchers -----------------------------------------------------------------------------------------
+// xt: caller-owned scratch of at least npad^2 doubles (npad = n rounded up to 8), private to the stream `st` (the
+// contexts pass the workspace of that stream's DenseWs); NULL keeps the whole inverse in the one CTA.
+// The kernel's shared-memory opt-in is per device: a process drives ONE device (mb_create enforces it).
 cudaError_t launch_dense_cholinv_sm(const double* src, int ld_src, double* inv, int n, double pen, int mode,
-                                    int* info, double* out, cudaStream_t st) {
+                                    int* info, double* out, double* xt, cudaStream_t st) {
   const size_t smem = dense_sm_bytes(n);
   static size_t configured = 0;
   if (smem > configured) {
@@ -318,23 +320,9 @@ cudaError_t launch_dense_cholinv_sm(const double* src, int ld_src, double* inv, 
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  // mode 0 at n >= DSM_SPLIT_N: the kernel stops after X = R^-1 and a multi-CTA kernel forms X X' (k_mid_lauum); the packed
-  // X lives in a scratch buffer per stream (calls on different streams may overlap)
-  double* xt = nullptr;
-  if (mode == 0 && n >= DSM_SPLIT_N && !getenv("MB_DENSE_NOSPLIT")) {
-    static std::map<std::pair<int, cudaStream_t>, double*> scratch;   // (device, stream): one host thread drives a context
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const std::pair<int, cudaStream_t> key(dev, st);
-    auto it = scratch.find(key);
-    if (it == scratch.end()) {
-      double* p = nullptr;
-      const size_t cap = (size_t)(DSM_MAX_N8 * (DSM_MAX_N8 + 1) / 2) * 64 * sizeof(double);
-      if (cudaMalloc(&p, cap) != cudaSuccess) { cudaGetLastError(); p = nullptr; }
-      it = scratch.emplace(key, p).first;
-    }
-    xt = it->second;
-  }
+  // mode 0 at n >= DSM_SPLIT_N: the kernel stops after X = R^-1 and a multi-CTA kernel forms X X' (k_mid_lauum) from the
+  // packed X in xt
+  if (!(mode == 0 && n >= DSM_SPLIT_N)) xt = nullptr;
   k_dense_cholinv_sm<<<1, DSM_THREADS, smem, st>>>(src, ld_src, inv, n, pen, 40, mode, info, out, xt);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || !xt) return e;

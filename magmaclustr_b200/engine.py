@@ -59,6 +59,9 @@ class Context:
         self._ar_cb = L.ALLREDUCE_FN(_cb)
         check(L.lib().mb_set_allreduce(self._h, self._ar_cb, None, int(rank), int(world)))
 
+    def set_option(self, name, value):
+        check(L.lib().mb_set_option(self._h, name.encode(), int(value)))
+
     def set_shard(self, first_task_global, n_tasks_global):
         """Position of the resident tasks in the global task list (multi-GPU: results independent of the GPU count)."""
         check(L.lib().mb_set_shard(self._h, int(first_task_global), int(n_tasks_global)))

@@ -84,8 +84,9 @@ def test_big_chol_inv_jitter_retry(ctx):
     a = b @ b.T
     inv, retries, jit = ctx.chol_inv_jitter(a, 1e-20)
     ref, r_ref = OK.chol_inv_jitter(a, 1e-20, return_info=True)
+    print("rank-deficient 320 x 320: retries gpu %d oracle %d" % (retries, r_ref))
     assert retries > 0
-    assert abs(retries - r_ref) <= 1      # the failing pivot sits at rounding level: allow one step
+    assert retries == r_ref               # the escalation count is a discrete decision of the reference: exact
     assert jit == _total_jitter(1e-20, retries)
 
 

@@ -375,11 +375,11 @@ def test_chol_inv_jitter_split_product_is_bit_identical(ctx):
         a = rng.normal(size=(n, n))
         spd = a @ a.T + n * np.eye(n)
         inv, retries, _ = ctx.chol_inv_jitter(spd, 1e-10)
-        os.environ["MB_DENSE_NOSPLIT"] = "1"
+        ctx.set_option("dense_split", 0)
         try:
             inv1, retries1, _ = ctx.chol_inv_jitter(spd, 1e-10)
         finally:
-            del os.environ["MB_DENSE_NOSPLIT"]
+            ctx.set_option("dense_split", 1)
         assert retries == retries1 == 0
         assert np.array_equal(inv, inv1), n
         assert np.array_equal(inv, inv.T)
