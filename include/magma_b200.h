@@ -249,6 +249,16 @@ int mb_elbo_monitoring(mb_context*, int n_clusters, const mb_kernel* kern_k, con
                        const double* m_k, const double* post_mean, const double* post_cov,
                        const double* tau, const double* prop_mixture, double pen_diag,
                        double* elbo);
+/* train_magmaclust's VEM loop (R/training.R:1586-1758) with the state resident on the device.  hp_k [K x P_k], hp_i [tasks x
+ * P_i] and m_k [K x U] are in/out; ini_mixture [tasks x K]; fast_approx != 0 stops after the first VE step with the ELBO of
+ * the initial hyper-parameters (training.R:1633-1647).  seq_elbo holds n_iter_max doubles; mixture_out [tasks x K],
+ * prop_mixture_out [K], post_mean [K x U], post_cov [K x U x U] may be NULL.  With sharded tasks (mb_set_shard) every rank
+ * passes its own rows of hp_i / ini_mixture and gets identical hp_k, m_k, ELBO sequence and step count. */
+int mb_train_magmaclust(mb_context* ctx, int n_clusters, const mb_kernel* kern_k, double* hp_k, const mb_kernel* kern_i,
+                        double* hp_i, int shared_hp_k, int shared_hp_i, double* m_k, const double* ini_mixture,
+                        double pen_diag, int n_iter_max, double cv_threshold, int fast_approx, double* seq_elbo,
+                        int32_t* n_iter, int32_t* converged, double* mixture_out, double* prop_mixture_out,
+                        double* post_mean, double* post_cov);
 
 /* ---- device-resident EM state and timing (measurement support; no reference counterpart:
  * the reference keeps hp_0 / hp_i in R tibbles between iterations, training.R:896-1030) ------ */

@@ -78,6 +78,8 @@ _SIGS = {
                    C.c_double, _dp, _lp],
     "mb_elbo_monitoring": [_vp, C.c_int, _kp, _dp, _kp, _dp, C.c_int, _dp, _dp, _dp, _dp, _dp,
                            C.c_double, _dp],
+    "mb_train_magmaclust": [_vp, C.c_int, _kp, _dp, _kp, _dp, C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_int, C.c_double,
+                            C.c_int, _dp, _ip, _ip, _dp, _dp, _dp, _dp],
     "mb_set_state": [_vp, _kp, _dp, _kp, _dp, _dp],
     "mb_em_step_resident": [_vp, _kp, _kp, C.c_int, C.c_double, C.c_int, _dp, _lp],
     "mb_get_state": [_vp, _kp, _dp, _kp, _dp],

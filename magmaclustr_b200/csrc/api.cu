@@ -2421,37 +2421,31 @@ static int shared_k_eval(mb_context* c, int K, const DevKern& kdk, const double*
   return 0;
 }
 
-extern "C" int mb_vm_step(mb_context* c, int n_clusters, const mb_kernel* kern_k, double* hp_k,
-                          const mb_kernel* kern_i, double* hp_i, int shared_hp_k, int shared_hp_i, double* m_k,
-                          const double* post_mean, const double* post_cov, const double* tau, double pen_diag,
-                          double* prop_mixture, int64_t* stats) {
-  MB_TRY(need_db(c, true));
-  if (!kern_k || !hp_k || !kern_i || !hp_i || !m_k || !post_mean || !post_cov || !tau || !prop_mixture)
-    MB_FAIL(-1, "null argument");
-  const int K = n_clusters, U = c->U;
-  if (K < 1 || K > MB_MAX_CLUSTERS) MB_FAIL(-1, "bad cluster count");
+// vm_step on device-resident state: c->pm / c->pc / c->tau hold the K hyper-posteriors and the mixture, hp_i_dev the task HP
+// table (in/out).  post_mean_host (K x U) and tau_host (local tasks x K) are the host copies the O(K U + M K) scalar glue of
+// the reference reads (vem-magmaclust.R:229-232, :265-266).  m_k (host, K x U) and prop_mixture are outputs.
+static int dev_vm_step(mb_context* c, int K, const mb_kernel* kern_k, double* hp_k, const mb_kernel* kern_i,
+                       double* hp_i_dev, int shared_hp_k, int shared_hp_i, double* m_k, const double* post_mean_host,
+                       const double* tau_host, double pen_diag, double* prop_mixture, int64_t* stats) {
+  const int U = c->U;
   const int64_t M = c->db.n_tasks;
   DevKern kdk = make_devkern(kern_k), kdi = make_devkern(kern_i);
   const int Pi = kdi.n_hp, Pk = kdk.n_hp;
   if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
-  MB_TRY(put_hyperpost(c, K, post_mean, post_cov, tau));
   // m_k <- mean of the hyper-posterior mean, replicated (vem-magmaclust.R:229-232)
   for (int k = 0; k < K; ++k) {
-    double mu = r_mean(post_mean + (size_t)k * U, U);
+    double mu = r_mean(post_mean_host + (size_t)k * U, U);
     for (int u = 0; u < U; ++u) m_k[(size_t)k * U + u] = mu;
   }
   MB_TRY(h2d(c->m0.p, m_k, (size_t)K * U * 8, c->st));
   // pi_k = colMeans(tau) (:265-266) over the tasks of every rank
   {
     double colsum[MB_MAX_CLUSTERS];
-    MB_TRY(leaf_sum_columns_host(c, tau, K, colsum));
+    MB_TRY(leaf_sum_columns_host(c, tau_host, K, colsum));
     const double m_all = (double)(c->shard_set ? c->g_total : M);
     for (int k = 0; k < K; ++k) prop_mixture[k] = colsum[k] / m_all;
   }
-  MB_TRY(c->hp_k.ensure((size_t)M * Pi * 8));
-  MB_TRY(h2d(c->hp_k.p, hp_i, (size_t)M * Pi * 8, c->st));
   CU(cudaStreamSynchronize(c->st));
-  double* hp_i_dev = c->hp_k.as<double>();
   TaskObjArgs a = make_obj_args(c, kdi, hp_i_dev, Pi, TK_OBJ_ELBO, 1, pen_diag, K, c->pm.as<double>(),
                                 c->pc.as<double>(), c->tau.as<double>(), c->f_t.as<double>(), c->g_t.as<double>());
   // cluster processes: K independent problems, or one shared problem handled after the tasks
@@ -2468,12 +2462,13 @@ extern "C" int mb_vm_step(mb_context* c, int n_clusters, const mb_kernel* kern_k
   }
   if (!shared_hp_i) {
     MB_TRY(optimise(c, singles, true, a, hp_i_dev, Pi, pen_diag, stats));
-    MB_TRY(d2h(hp_i, hp_i_dev, (size_t)M * Pi * 8, c->st));
-    CU(cudaStreamSynchronize(c->st));
   } else {
     MB_TRY(optimise(c, singles, false, a, hp_i_dev, Pi, pen_diag, stats));
     LbfgsbState s;
-    lb_init(&s, Pi, hp_i, 1e13, 0.0, 25);       // block of the first task (:236-238)
+    double x0[MB_MAX_HP];
+    MB_TRY(d2h(x0, hp_i_dev, Pi * 8, c->st));     // block of the first task (:236-238): the same on every rank
+    CU(cudaStreamSynchronize(c->st));
+    lb_init(&s, Pi, x0, 1e13, 0.0, 25);
     int evals = 0;
     while (s.active) {
       double f, g[MB_MAX_HP];
@@ -2481,8 +2476,11 @@ extern "C" int mb_vm_step(mb_context* c, int n_clusters, const mb_kernel* kern_k
       lb_advance(&s, f, g);
       evals++;
     }
+    std::vector<double> tab((size_t)M * Pi);
     for (int64_t t = 0; t < M; ++t)
-      for (int p = 0; p < Pi; ++p) hp_i[t * Pi + p] = s.x[p];
+      for (int p = 0; p < Pi; ++p) tab[t * Pi + p] = s.x[p];
+    MB_TRY(h2d(hp_i_dev, tab.data(), tab.size() * 8, c->st));
+    CU(cudaStreamSynchronize(c->st));
     if (stats) { stats[1] = evals; stats[2] = (int64_t)evals * M; stats[3] = (s.fail == 99); }
   }
   if (!shared_hp_k) {
@@ -2509,26 +2507,39 @@ extern "C" int mb_vm_step(mb_context* c, int n_clusters, const mb_kernel* kern_k
   return 0;
 }
 
-extern "C" int mb_elbo_monitoring(mb_context* c, int n_clusters, const mb_kernel* kern_k, const double* hp_k,
-                                  const mb_kernel* kern_i, const double* hp_i, int hp_i_shared, const double* m_k,
-                                  const double* post_mean, const double* post_cov, const double* tau,
-                                  const double* prop_mixture, double pen_diag, double* elbo) {
+extern "C" int mb_vm_step(mb_context* c, int n_clusters, const mb_kernel* kern_k, double* hp_k,
+                          const mb_kernel* kern_i, double* hp_i, int shared_hp_k, int shared_hp_i, double* m_k,
+                          const double* post_mean, const double* post_cov, const double* tau, double pen_diag,
+                          double* prop_mixture, int64_t* stats) {
   MB_TRY(need_db(c, true));
-  if (!kern_k || !hp_k || !kern_i || !hp_i || !m_k || !post_mean || !post_cov || !tau || !prop_mixture || !elbo)
+  if (!kern_k || !hp_k || !kern_i || !hp_i || !m_k || !post_mean || !post_cov || !tau || !prop_mixture)
     MB_FAIL(-1, "null argument");
-  const int K = n_clusters, U = c->U;
+  const int K = n_clusters;
   if (K < 1 || K > MB_MAX_CLUSTERS) MB_FAIL(-1, "bad cluster count");
+  const int64_t M = c->db.n_tasks;
+  const int Pi = kern_i->n_hp;
+  MB_TRY(put_hyperpost(c, K, post_mean, post_cov, tau));
+  MB_TRY(c->hp_k.ensure((size_t)M * Pi * 8));
+  MB_TRY(h2d(c->hp_k.p, hp_i, (size_t)M * Pi * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  MB_TRY(dev_vm_step(c, K, kern_k, hp_k, kern_i, c->hp_k.as<double>(), shared_hp_k, shared_hp_i, m_k, post_mean, tau,
+                     pen_diag, prop_mixture, stats));
+  MB_TRY(d2h(hp_i, c->hp_k.p, (size_t)M * Pi * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+// elbo_monitoring_VEM on device-resident state (c->pm / c->pc / c->tau / c->m0 = m_k); hp_i_dev with the given stride
+static int dev_elbo_monitoring(mb_context* c, int K, const mb_kernel* kern_k, const double* hp_k, const mb_kernel* kern_i,
+                               const double* hp_i_dev, int64_t stride, const double* tau_host, const double* prop_mixture,
+                               double pen_diag, double* elbo) {
+  const int U = c->U;
   const int64_t M = c->db.n_tasks;
   const size_t UU = (size_t)U * U;
   DevKern kdk = make_devkern(kern_k), kdi = make_devkern(kern_i);
-  int64_t stride;
-  MB_TRY(put_hp_i(c, kern_i, hp_i, hp_i_shared, &stride));
-  MB_TRY(put_hyperpost(c, K, post_mean, post_cov, tau));
   MB_TRY(c->ws1.ensure(U));
-  MB_TRY(h2d(c->m0.p, m_k, (size_t)K * U * 8, c->st));
-  CU(cudaStreamSynchronize(c->st));
   // task sum (elbos.R:221-235)
-  TaskObjArgs a = make_obj_args(c, kdi, c->hp_i.as<double>(), stride, TK_OBJ_ELBO, 0, pen_diag, K, c->pm.as<double>(),
+  TaskObjArgs a = make_obj_args(c, kdi, hp_i_dev, stride, TK_OBJ_ELBO, 0, pen_diag, K, c->pm.as<double>(),
                                 c->pc.as<double>(), c->tau.as<double>(), c->f_t.as<double>(), c->g_t.as<double>());
   MB_TRY(launch_obj(c, a, (int)M, c->st));
   MB_TRY(c->sums.ensure(64 * 8));
@@ -2542,7 +2553,7 @@ extern "C" int mb_elbo_monitoring(mb_context* c, int n_clusters, const mb_kernel
     std::vector<double> terms((size_t)M * K);
     for (int64_t t = 0; t < M; ++t)
       for (int k = 0; k < K; ++k) {
-        const double tk = tau[t * K + k], pi_k = prop_mixture[k];
+        const double tk = tau_host[t * K + k], pi_k = prop_mixture[k];
         terms[t * K + k] = (tk == 0.0 || pi_k == 0.0) ? 0.0 : tk * log(pi_k / tk);
       }
     MB_TRY(leaf_sum_columns_host(c, terms.data(), K, sum_tau_k));
@@ -2566,5 +2577,131 @@ extern "C" int mb_elbo_monitoring(mb_context* c, int n_clusters, const mb_kernel
     sum_corr += sum_tau_k[k] + c->h_pin[8];
   }
   *elbo = -sum_ll_k - sum_ll_i + sum_corr;
+  return 0;
+}
+
+extern "C" int mb_elbo_monitoring(mb_context* c, int n_clusters, const mb_kernel* kern_k, const double* hp_k,
+                                  const mb_kernel* kern_i, const double* hp_i, int hp_i_shared, const double* m_k,
+                                  const double* post_mean, const double* post_cov, const double* tau,
+                                  const double* prop_mixture, double pen_diag, double* elbo) {
+  MB_TRY(need_db(c, true));
+  if (!kern_k || !hp_k || !kern_i || !hp_i || !m_k || !post_mean || !post_cov || !tau || !prop_mixture || !elbo)
+    MB_FAIL(-1, "null argument");
+  const int K = n_clusters, U = c->U;
+  if (K < 1 || K > MB_MAX_CLUSTERS) MB_FAIL(-1, "bad cluster count");
+  int64_t stride;
+  MB_TRY(put_hp_i(c, kern_i, hp_i, hp_i_shared, &stride));
+  MB_TRY(put_hyperpost(c, K, post_mean, post_cov, tau));
+  MB_TRY(h2d(c->m0.p, m_k, (size_t)K * U * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return dev_elbo_monitoring(c, K, kern_k, hp_k, kern_i, c->hp_i.as<double>(), stride, tau, prop_mixture, pen_diag, elbo);
+}
+
+// train_magmaclust's VEM loop (/root/reference/R/training.R:1586-1758) with the state resident on the device: the K
+// hyper-posteriors (K x U x U), the task HP table and the mixture never cross PCIe inside the loop; per iteration the host
+// reads the K x U posterior means (m_k = their averages, vem-magmaclust.R:229-232) and the M x K table of per-cluster
+// likelihoods for the reference's softmax + round(5) (vem-magmaclust.R:383-392).
+// hp_k: K x P_k, hp_i: local tasks x P_i, m_k: K x U (all in/out); ini_mixture: local tasks x K.  fast_approx != 0 stops
+// after the first VE step with the ELBO of the initial HPs (training.R:1633-1647).  Outputs may be NULL.
+extern "C" int mb_train_magmaclust(mb_context* c, int n_clusters, const mb_kernel* kern_k, double* hp_k,
+                                   const mb_kernel* kern_i, double* hp_i, int shared_hp_k, int shared_hp_i, double* m_k,
+                                   const double* ini_mixture, double pen_diag, int n_iter_max, double cv_threshold,
+                                   int fast_approx, double* seq_elbo, int32_t* n_iter, int32_t* converged,
+                                   double* mixture_out, double* prop_mixture_out, double* post_mean, double* post_cov) {
+  MB_TRY(need_db(c, true));
+  if (!kern_k || !hp_k || !kern_i || !hp_i || !m_k || !ini_mixture || !seq_elbo || !n_iter || !converged || n_iter_max < 1)
+    MB_FAIL(-1, "bad argument");
+  const int K = n_clusters, U = c->U;
+  if (K < 1 || K > MB_MAX_CLUSTERS) MB_FAIL(-1, "bad cluster count");
+  const int64_t M = c->db.n_tasks;
+  const size_t UU = (size_t)U * U;
+  const int Pi = kern_i->n_hp, Pk = kern_k->n_hp;
+  DevKern kdi = make_devkern(kern_i);
+  MB_TRY(ensure_em_buffers(c, K));
+  const size_t tab = (size_t)M * Pi * 8;
+  MB_TRY(c->hp_k.ensure(2 * tab));
+  double* cur = c->hp_k.as<double>();
+  double* nxt = cur + (size_t)M * Pi;
+  MB_TRY(h2d(cur, hp_i, tab, c->st));
+  MB_TRY(c->tau.ensure((size_t)M * K * 8));
+  std::vector<double> mixture(ini_mixture, ini_mixture + (size_t)M * K), post_mix((size_t)M * K), pm_host((size_t)K * U),
+      new_m_k((size_t)K * U), new_hp_k(hp_k, hp_k + (size_t)K * Pk), htab((size_t)M * Pi);
+  double prop[MB_MAX_CLUSTERS], new_prop[MB_MAX_CLUSTERS];
+  {
+    double colsum[MB_MAX_CLUSTERS];
+    MB_TRY(leaf_sum_columns_host(c, mixture.data(), K, colsum));      // prop_mixture = colMeans(ini_mixture) (:1609-1612)
+    const double m_all = (double)(c->shard_set ? c->g_total : M);
+    for (int k = 0; k < K; ++k) prop[k] = colsum[k] / m_all;
+  }
+  double elbo = -INFINITY;
+  *converged = 0;
+  *n_iter = 0;
+  for (int it = 1; it <= n_iter_max; ++it) {
+    // ---- VE step (vem-magmaclust.R:32-150): hyper-posteriors with the current mixture, then the mixture update (not at
+    // iteration 1, :130-131)
+    MB_TRY(h2d(c->tau.p, mixture.data(), (size_t)M * K * 8, c->st));
+    MB_TRY(h2d(c->m0.p, m_k, (size_t)K * U * 8, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    MB_TRY(dev_e_step(c, K, kern_k, hp_k, kdi, cur, Pi, c->m0.as<double>(), c->tau.as<double>(), c->d_gridX.as<double>(), U,
+                      nullptr, pen_diag, c->pm.as<double>(), c->pc.as<double>(), nullptr));
+    if (it > 1) {
+      MB_TRY(dev_update_mixture(c, K, kdi, cur, Pi, c->pm.as<double>(), c->pc.as<double>(), prop, pen_diag, post_mix.data()));
+      MB_TRY(h2d(c->tau.p, post_mix.data(), (size_t)M * K * 8, c->st));
+    } else {
+      post_mix = mixture;
+    }
+    MB_TRY(d2h(pm_host.data(), c->pm.p, (size_t)K * U * 8, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    if (fast_approx) {
+      MB_TRY(dev_elbo_monitoring(c, K, kern_k, hp_k, kern_i, cur, Pi, post_mix.data(), prop, pen_diag, &elbo));
+      seq_elbo[0] = elbo;
+      *n_iter = 1;
+      mixture = post_mix;
+      break;
+    }
+    // ---- VM step on a copy of the HP table: a NaN leaves the last valid values in place (training.R:1672-1679)
+    CU(cudaMemcpyAsync(nxt, cur, tab, cudaMemcpyDeviceToDevice, c->st));
+    for (size_t q = 0; q < new_hp_k.size(); ++q) new_hp_k[q] = hp_k[q];
+    MB_TRY(dev_vm_step(c, K, kern_k, new_hp_k.data(), kern_i, nxt, shared_hp_k, shared_hp_i, new_m_k.data(), pm_host.data(),
+                       post_mix.data(), pen_diag, new_prop, nullptr));
+    MB_TRY(d2h(htab.data(), nxt, tab, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    bool bad = false;
+    for (double v : new_hp_k) if (isnan(v)) bad = true;
+    for (double v : htab) if (isnan(v)) { bad = true; break; }
+    if (c->world > 1) {
+      MB_TRY(c->sums.ensure(64 * 8));
+      const double flag = bad ? 1.0 : 0.0;
+      double tot = 0.0;
+      CU(cudaMemcpyAsync(c->sums.as<double>() + 33, &flag, 8, cudaMemcpyHostToDevice, c->st));
+      CU(cudaStreamSynchronize(c->st));
+      MB_TRY(ctx_allreduce(c, c->sums.as<double>() + 33, 1, c->st));
+      CU(cudaMemcpyAsync(&tot, c->sums.as<double>() + 33, 8, cudaMemcpyDeviceToHost, c->st));
+      CU(cudaStreamSynchronize(c->st));
+      bad = tot != 0.0;
+    }
+    if (bad) break;
+    double new_elbo;
+    MB_TRY(dev_elbo_monitoring(c, K, kern_k, new_hp_k.data(), kern_i, nxt, Pi, post_mix.data(), new_prop, pen_diag, &new_elbo));
+    double diff = new_elbo - elbo;
+    if (isnan(diff)) diff = -INFINITY;
+    for (size_t q = 0; q < new_hp_k.size(); ++q) hp_k[q] = new_hp_k[q];
+    for (size_t q = 0; q < new_m_k.size(); ++q) m_k[q] = new_m_k[q];
+    for (int k = 0; k < K; ++k) prop[k] = new_prop[k];
+    std::swap(cur, nxt);
+    mixture = post_mix;
+    elbo = new_elbo;
+    seq_elbo[it - 1] = elbo;
+    *n_iter = it;
+    double eps = diff / fabs(elbo);
+    if (isnan(eps)) eps = 1.0;
+    if (fabs(eps) < cv_threshold) { *converged = 1; break; }
+  }
+  MB_TRY(d2h(hp_i, cur, tab, c->st));
+  if (post_mean) MB_TRY(d2h(post_mean, c->pm.p, (size_t)K * U * 8, c->st));
+  if (post_cov) MB_TRY(d2h(post_cov, c->pc.p, K * UU * 8, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  if (mixture_out) memcpy(mixture_out, mixture.data(), (size_t)M * K * 8);
+  if (prop_mixture_out) for (int k = 0; k < K; ++k) prop_mixture_out[k] = prop[k];
   return 0;
 }

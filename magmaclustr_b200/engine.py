@@ -488,8 +488,30 @@ class Context:
         return mean, var, cov, mm, mv
 
     def train_magmaclust(self, K, kk, hp_k, ki, hp_i, ini_mixture, shared_hp_k=True, shared_hp_i=True,
-                         pen_diag=1e-10, n_iter_max=25, cv_threshold=1e-3, m_k=None):
-        """VEM loop of train_magmaclust (training.R:1622-1758); every step runs in the library."""
+                         pen_diag=1e-10, n_iter_max=25, cv_threshold=1e-3, m_k=None, fast_approx=False):
+        """VEM loop of train_magmaclust (training.R:1586-1758): one library call, hyper-posteriors / HP table / mixture
+        resident on the device (mb_train_magmaclust)."""
+        hp_k, hp_i = f64(hp_k).copy(), f64(hp_i).copy()
+        m_k = np.zeros((K, self.U)) if m_k is None else f64(np.broadcast_to(np.asarray(m_k, dtype=np.float64).reshape(K, -1),
+                                                                              (K, self.U))).copy()
+        mix0 = f64(ini_mixture)
+        seq = np.zeros(n_iter_max)
+        n_iter, conv = C.c_int32(0), C.c_int32(0)
+        mixture = np.zeros_like(mix0)
+        prop = np.zeros(K)
+        pm = np.zeros((K, self.U))
+        pc = np.zeros((K, self.U, self.U))
+        check(L.lib().mb_train_magmaclust(self._h, int(K), C.byref(kk), ptr(hp_k), C.byref(ki), ptr(hp_i),
+                                          1 if shared_hp_k else 0, 1 if shared_hp_i else 0, ptr(m_k), ptr(mix0),
+                                          float(pen_diag), int(n_iter_max), float(cv_threshold), 1 if fast_approx else 0,
+                                          ptr(seq), C.byref(n_iter), C.byref(conv), ptr(mixture), ptr(prop), ptr(pm), ptr(pc)))
+        return {"hp_k": hp_k, "hp_i": hp_i, "m_k": m_k, "mixture": mixture, "prop_mixture": prop,
+                "post_mean": pm, "post_cov": pc, "seq_elbo": seq[: n_iter.value].copy(), "converged": bool(conv.value)}
+
+    def train_magmaclust_stepwise(self, K, kk, hp_k, ki, hp_i, ini_mixture, shared_hp_k=True, shared_hp_i=True,
+                                  pen_diag=1e-10, n_iter_max=25, cv_threshold=1e-3, m_k=None):
+        """The same loop driven from the host through mb_ve_step / mb_vm_step / mb_elbo_monitoring (what an R shim that keeps
+        the reference's own loop would call); kept as a cross-check of mb_train_magmaclust."""
         hp_k, hp_i = f64(hp_k).copy(), f64(hp_i).copy()
         m_k = np.zeros((K, self.U)) if m_k is None else f64(m_k).copy()
         mixture = f64(ini_mixture).copy()

@@ -116,6 +116,18 @@ def test_train_magmaclust_small(ctx):
     np.testing.assert_allclose(res["seq_elbo"], ores["seq_elbo"], rtol=2e-3)
     assert np.array_equal(np.argmax(res["mixture"], axis=1), np.argmax(ores["mixture"], axis=1))
     assert np.all(np.diff(res["seq_elbo"]) > -1e-6 * np.abs(res["seq_elbo"][1:]))
+    # the resident loop (one library call) and the same steps driven from the host give the same bits
+    step = ctx.train_magmaclust_stepwise(KC, case["k0"], hp_k, case["ki"], case["hpi"], mix, True, True, n_iter_max=6)
+    for key in ("seq_elbo", "hp_k", "hp_i", "m_k", "mixture", "prop_mixture", "post_mean", "post_cov"):
+        assert np.array_equal(np.asarray(res[key]), np.asarray(step[key])), key
+    # fast_approx: one VE step, ELBO of the initial hyper-parameters (training.R:1633-1647)
+    fa = ctx.train_magmaclust(KC, case["k0"], hp_k, case["ki"], case["hpi"], mix, True, True, fast_approx=True)
+    assert len(fa["seq_elbo"]) == 1 and not fa["converged"] and np.array_equal(fa["hp_k"], hp_k)
+    omean, ocov, omix = _oracle_ve(case, mix, o_hp_k)
+    o_prop = mix.mean(axis=0)
+    o_fa = OC.elbo_monitoring_VEM(o_hp_k, case["o_hpi"], case["odb"], "SE", "SE", omean, ocov, omix,
+                                  [np.zeros(ctx.U)] * KC, o_prop, 1e-10)
+    assert abs(fa["seq_elbo"][0] - o_fa) < 2e-3 * abs(o_fa)
 
 
 def test_hyperposterior_clust_and_pred_magmaclust(ctx):
@@ -156,3 +168,41 @@ def test_hyperposterior_clust_and_pred_magmaclust(ctx):
     np.testing.assert_allclose(mv, opred["Var"], rtol=1e-7, atol=1e-10)
     assert np.all(mv >= 0)
     prep.set_grid(None)
+
+
+def test_select_nb_cluster(ctx):
+    """select_nb_cluster (training.R:2286-2454): one fast_approx training per K and the variational BIC; K = 1 is
+    train_magma's E step + logL_monitoring, K > 1 the first VE step + elbo_monitoring_VEM.  Against the oracle's steps."""
+    import math
+    from magmaclustr_b200.selection import select_nb_cluster, vbic
+    case, _, _, _ = _setup(ctx, M=12, N=10, seed=4, shared_i=True)
+    prep, odb = case["prep"], case["odb"]
+    rng = np.random.default_rng(3)
+    mixes = {}
+    for k in (2, 3):
+        lab = rng.integers(0, k, size=12)
+        lab[:k] = np.arange(k)                       # every cluster populated
+        m = np.zeros((12, k))
+        m[np.arange(12), lab] = 1.0
+        mixes[k] = m
+    hp_k1 = np.array([1.1, -1.4])
+    res = select_nb_cluster(ctx, prep, case["k0"], case["ki"], hp_k1, case["hpi"], grid_nb_cluster=[1, 2, 3],
+                            fast_approx=True, ini_mixtures=mixes)
+    U = ctx.U
+    o_hp = dict(zip(case["names_0"], hp_k1))
+    # K = 1
+    pm, pc = OM.e_step(odb, 0.0, "SE", "SE", o_hp, case["o_hpi"], 1e-10)
+    ll1 = OM.logL_monitoring(o_hp, case["o_hpi"], odb, 0.0, "SE", "SE", pm, pc, 1e-10)
+    expect = {1: ll1}
+    for k in (2, 3):
+        hk = [dict(o_hp) for _ in range(k)]
+        mean_k, cov_k, omix = OC.ve_step(odb, [np.zeros(U)] * k, "SE", "SE", hk, case["o_hpi"], mixes[k], 1, 1e-10, None)
+        expect[k] = OC.elbo_monitoring_VEM(hk, case["o_hpi"], odb, "SE", "SE", mean_k, cov_k, omix, [np.zeros(U)] * k,
+                                           mixes[k].mean(axis=0), 1e-10)
+    for k in (1, 2, 3):
+        assert abs(res["seq_elbo"][k] - expect[k]) < 2e-3 * abs(expect[k]), (k, res["seq_elbo"][k], expect[k])
+        # shared hp_i (3 distinct values) + one hp_k row (2 distinct values) + K - 1 proportions
+        pen = 0.5 * (2 + 3 + k - 1) * math.log(12)
+        assert abs(res["seq_vbic"][k] - (res["seq_elbo"][k] - pen)) < 1e-9
+    assert res["best_k"] == max((1, 2, 3), key=lambda k: expect[k] - 0.5 * (5 + k - 1) * math.log(12))
+    assert res["model"] is not None and "V-BIC" in res["model"]
