@@ -35,8 +35,9 @@ extern "C" {
 #define MB_MAX_HP 12
 #define MB_MAX_CLUSTERS 16
 
-/* base kernels, /root/reference/R/kernels.R:164-398 */
-enum { MB_KERN_SE = 0, MB_KERN_PERIO = 1, MB_KERN_RQ = 2, MB_KERN_LIN = 3 };
+/* base kernels, /root/reference/R/kernels.R:164-398; MB_KERN_CONV = the multi-output convolution kernel with one latent
+ * process, /root/reference/R/kernels.R:16-140 */
+enum { MB_KERN_SE = 0, MB_KERN_PERIO = 1, MB_KERN_RQ = 2, MB_KERN_LIN = 3, MB_KERN_CONV = 4 };
 
 /*
  * A kernel string of the reference's grammar "(k1 * k2 * ...) + k + k ..."
@@ -44,6 +45,12 @@ enum { MB_KERN_SE = 0, MB_KERN_PERIO = 1, MB_KERN_RQ = 2, MB_KERN_LIN = 3 };
  * remaining terms are added.  HP layout, in term order: SE (variance, lengthscale);
  * PERIO (variance, lengthscale, period); RQ (variance, lengthscale, scale); LIN (slope, offset);
  * then `noise` last when has_noise != 0.  n_hp is the total (filled by mb_kernel_parse).
+ *
+ * Multi-output: kern = "CONV<O>" (e.g. "CONV2"; what `kern = convolution_kernel` is in R) is ONE term of type MB_KERN_CONV
+ * with n_prod = O outputs.  Inputs then carry the 0-based output index of every point as their LAST column (the
+ * reference's Output_ID, part of the Reference key "o<id>;<coords>", kernel-to-matrices.R:94-96) and the HP vector is
+ * flatten_hp_mo()'s (R/hyperparameters.R:348-396): l_t_1..l_t_O, S_t_1..S_t_O, l_u_t, then noise_1..noise_O when
+ * has_noise != 0 (per-output noise exp(noise_o) on the diagonal, kernel-to-matrices.R:146-157).  O <= 3 with noise.
  */
 typedef struct mb_kernel {
   int32_t n_terms;

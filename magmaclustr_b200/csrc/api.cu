@@ -566,6 +566,14 @@ extern "C" int mb_kernel_parse(const char* kern, int has_noise, mb_kernel* out) 
   }
   if (tok.empty() || tok[0] == "+" || tok[0] == "*")
     MB_FAIL(-1, "The string in 'kern' should start with a kernel not an operator.");
+  if (tok.size() == 1 && tok[0].compare(0, 4, "CONV") == 0) {   // "CONV<O>": the multi-output convolution kernel
+    const int O = atoi(tok[0].c_str() + 4);
+    if (O < 1) MB_FAIL(-1, "multi-output kernel: write CONV<number of outputs>, e.g. CONV2");
+    out->n_terms = 1; out->n_prod = O; out->types[0] = MB_KERN_CONV; out->has_noise = has_noise ? 1 : 0;
+    out->n_hp = 2 * O + 1 + (has_noise ? O : 0);
+    if (out->n_hp > MB_MAX_HP) MB_FAIL(-1, "too many hyper-parameters: the convolution kernel supports up to 3 outputs with noise");
+    return 0;
+  }
   bool seen_plus = false, expect_kernel = true;
   int nhp = 0;
   for (size_t i = 0; i < tok.size(); ++i) {
@@ -603,6 +611,15 @@ extern "C" const char* mb_kernel_hp_name(const mb_kernel* k, int p) {
                                     {"rq_variance", "rq_lengthscale", "rq_scale"},
                                     {"lin_slope", "lin_offset", nullptr}};
   if (!k || p < 0 || p >= k->n_hp) return nullptr;
+  if (k->n_terms == 1 && k->types[0] == MB_KERN_CONV) {   // flatten_hp_mo() names with output labels 1..O
+    static thread_local char buf[32];
+    const int O = k->n_prod;
+    if (p < O) snprintf(buf, sizeof(buf), "l_t_%d", p + 1);
+    else if (p < 2 * O) snprintf(buf, sizeof(buf), "S_t_%d", p - O + 1);
+    else if (p == 2 * O) snprintf(buf, sizeof(buf), "l_u_t");
+    else snprintf(buf, sizeof(buf), "noise_%d", p - 2 * O);
+    return buf;
+  }
   int off = 0;
   for (int t = 0; t < k->n_terms; ++t) {
     int np = mb_term_nhp(k->types[t]);
@@ -1470,6 +1487,7 @@ extern "C" int mb_pred_magma_tasks(mb_context* c, const mb_kernel* kern, const d
                                    int32_t n_pred, const double* x_pred, const int32_t* pred_index, double pen_diag,
                                    double* pred_mean, double* pred_var, double* pred_mean_k, double* pred_var_k,
                                    int32_t* retries) {
+  if (kern && kern->n_terms == 1 && kern->types[0] == MB_KERN_CONV) MB_FAIL(-4, "prediction with the multi-output convolution kernel is not on the accelerated path yet");
   MB_TRY(need_hyperpost(c, 0, true));
   const int K = c->hpr_K, D = c->db.D, P = kern ? kern->n_hp : 0;
   const int64_t M = c->db.n_tasks;
@@ -2070,6 +2088,7 @@ extern "C" int mb_pred_magma(mb_context* c, const mb_kernel* k, const double* hp
                              const double* mean_obs, const double* mean_pred, const double* cov_obs,
                              const double* cov_pred, const double* cov_crossed, double pen_diag,
                              double* pred_mean, double* pred_var, double* pred_cov) {
+  if (k && k->n_terms == 1 && k->types[0] == MB_KERN_CONV) MB_FAIL(-4, "prediction with the multi-output convolution kernel is not on the accelerated path yet");
   MB_TRY(check_ctx(c));
   if (!k || !hp || !x_obs || !y_obs || !x_pred || !mean_obs || !mean_pred || !cov_obs || !cov_pred ||
       !cov_crossed || !pred_mean || !pred_var || n_obs < 1 || n_pred < 1 || d < 1)

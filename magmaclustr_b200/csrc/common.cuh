@@ -24,6 +24,11 @@ inline DevKern make_devkern(const mb_kernel* k) {
   d.n_terms = k->n_terms;
   d.n_prod = k->n_prod;
   d.has_noise = k->has_noise;
+  if (k->n_terms == 1 && k->types[0] == MB_KERN_CONV) {   // multi-output: n_prod = number of outputs
+    for (int i = 0; i < MB_MAX_TERMS; ++i) { d.types[i] = i == 0 ? MB_KERN_CONV : 0; d.hp_off[i] = 0; }
+    d.n_hp = 2 * k->n_prod + 1 + (k->has_noise ? k->n_prod : 0);
+    return d;
+  }
   int off = 0;
   for (int i = 0; i < MB_MAX_TERMS; ++i) {
     d.types[i] = (i < k->n_terms) ? k->types[i] : 0;
@@ -59,6 +64,10 @@ __device__ __forceinline__ PairSums pair_sums(const double* xa, const double* xb
 // exp(offset)); noise: exp(noise).  They are the very sub-expressions of kernels.R, so hoisting
 // them does not change any rounding.
 __device__ __forceinline__ void prep_hp(const DevKern& kd, const double* hp, double* hpe) {
+  if (kd.types[0] == MB_KERN_CONV) {      // exp() of every entry: l = exp(l_t), S = exp(S_t), l_u = exp(l_u_t), exp(noise_o)
+    for (int p = 0; p < kd.n_hp; ++p) hpe[p] = exp(hp[p]);
+    return;
+  }
   for (int t = 0; t < kd.n_terms; ++t) {
     const double* h = hp + kd.hp_off[t];
     double* e = hpe + kd.hp_off[t];
@@ -137,10 +146,40 @@ __device__ __forceinline__ double base_kernel(int type, const double* hp, const 
 // HP derivatives, following the fold of kernel-to-matrices.R:163-340: the derivative w.r.t. an
 // HP of a product factor is d(k_j) * prod_{i != j} k_i (left-to-right), of a summand d(k_j)
 // alone; the noise term adds exp(noise) on coincident pairs (:440-447,:481-487).
+// Multi-output convolution kernel with one latent process (/root/reference/R/kernels.R:50-140, vectorised branch) between
+// two points whose LAST input column is the 0-based output index:
+//   K = S_i S_j / (2 pi den)^(d/2) exp(-dist^2 / (2 den)),  den = l_i + l_j + l_u,  d = number of coordinates,
+//   dK/dl_u_t = common l_u,  dK/dl_t_o = common (l_i [o_i = o] + l_j [o_j = o]),  dK/dS_t_o = K ([o_i = o] + [o_j = o]),
+//   common = K (-d / (2 den) + dist^2 / (2 den^2));  noise: exp(noise_o) on coincident points of output o
+//   (kernel-to-matrices.R:121-157).  HP layout: l_t[O], S_t[O], l_u_t, noise[O].
+template <bool WITH_DERIV>
+__device__ __forceinline__ double conv_eval(const DevKern& kd, const double* hpe, const double* xa, const double* xb, int D,
+                                            bool with_noise, double* dval) {
+  const int O = kd.n_prod, dc = D - 1;
+  PairSums s = pair_sums(xa, xb, dc);
+  const int oi = (int)xa[dc], oj = (int)xb[dc];
+  const double li = hpe[oi], lj = hpe[oj], lu = hpe[2 * O];
+  const double den = (li + lj) + lu;
+  const double k = (hpe[O + oi] * hpe[O + oj]) / pow(2 * MB_PI * den, dc / 2.0) * exp(-0.5 * s.d2 / den);
+  const bool same = (oi == oj) && s.l1 < 0.000001;
+  if (WITH_DERIV) {
+    for (int p = 0; p < kd.n_hp; ++p) dval[p] = 0.0;
+    const double common = k * ((-0.5 * dc / den) + (0.5 * s.d2 / (den * den)));
+    dval[2 * O] = common * lu;
+    dval[oi] += common * li;
+    dval[oj] += common * lj;
+    dval[O + oi] += k;
+    dval[O + oj] += k;
+    if (kd.has_noise && same) dval[2 * O + 1 + oi] = hpe[2 * O + 1 + oi];
+  }
+  return (kd.has_noise && with_noise && same) ? k + hpe[2 * O + 1 + oi] : k;
+}
+
 template <bool WITH_DERIV>
 __device__ __forceinline__ double cov_eval(const DevKern& kd, const double* hp, const double* hpe,
                                            const double* xa, const double* xb, int D,
                                            bool with_noise, double* dval) {
+  if (kd.types[0] == MB_KERN_CONV) return conv_eval<WITH_DERIV>(kd, hpe, xa, xb, D, with_noise, dval);
   PairSums s = pair_sums(xa, xb, D);
   double val;
   if (kd.n_terms == 1) {

@@ -225,10 +225,58 @@ def _compound(kern, x, y, hp, deriv):
     return out
 
 
+def convolution_kernel(x, y, hp, n_outputs, deriv=None):
+    """The vectorised branch of convolution_kernel (kernels.R:50-140) for ONE latent process plus kern_to_cov's multi-output
+    wrapper (kernel-to-matrices.R:88-160): x, y are matrices whose LAST column is the 0-based output index (the reference's
+    Output_ID column); hp is flatten_hp_mo()'s named vector with output labels 1..O: l_t_<o>, S_t_<o>, l_u_t[, noise_<o>]
+    (hyperparameters.R:348-396).  Noise (value and derivative) only on the square matrix of a set of points against itself."""
+    x, y = _mat(x), _mat(y)
+    O = int(n_outputs)
+    same_inputs = x.shape == y.shape and np.array_equal(x, y)
+    ox, oy = x[:, -1].astype(int), y[:, -1].astype(int)
+    xc, yc = x[:, :-1], y[:, :-1]
+    input_dim = xc.shape[1]
+    if deriv is not None and deriv.startswith("noise"):           # :121-141
+        mat = np.zeros((len(x), len(y)))
+        if same_inputs:
+            out_lab = int(deriv.split("_")[-1]) - 1
+            mat[np.arange(len(x)), np.arange(len(x))] = np.where(ox == out_lab, math.exp(hp[deriv]), 0.0)
+        return mat
+    distance_sq = cpp_dist(xc, yc)
+    l_t = np.array([hp["l_t_%d" % (o + 1)] for o in range(O)])
+    S_t = np.array([hp["S_t_%d" % (o + 1)] for o in range(O)])
+    l1, l2 = np.exp(l_t[ox]), np.exp(l_t[oy])
+    S1, S2 = np.exp(S_t[ox]), np.exp(S_t[oy])
+    l_u = math.exp(hp["l_u_t"])
+    denom = np.add.outer(l1, l2) + l_u
+    K = np.multiply.outer(S1, S2) / ((2 * math.pi * denom) ** (input_dim / 2)) * np.exp(-0.5 * distance_sq / denom)
+    if deriv is None:
+        if any(k.startswith("noise") for k in hp) and same_inputs:        # :146-157
+            noise = np.array([hp["noise_%d" % (o + 1)] for o in range(O)])
+            K = K + np.diag(np.exp(noise[ox]))
+        return K
+    common = K * ((-0.5 * input_dim / denom) + (0.5 * distance_sq / (denom ** 2)))
+    if deriv == "l_u_t":
+        return common * l_u
+    out_lab = int(deriv.split("_")[-1]) - 1
+    mask_i = np.multiply.outer(ox == out_lab, np.ones(len(y), dtype=bool))
+    mask_j = np.multiply.outer(np.ones(len(x), dtype=bool), oy == out_lab)
+    if deriv.startswith("l_t"):
+        l_i_mat = np.repeat(l1[:, None], len(y), axis=1)
+        l_j_mat = np.repeat(l2[None, :], len(x), axis=0)
+        return common * (l_i_mat * mask_i + l_j_mat * mask_j)
+    if deriv.startswith("S_t"):
+        return K * (mask_i.astype(float) + mask_j.astype(float))
+    raise ValueError("Invalid 'deriv' argument: " + deriv)
+
+
 def kern_to_cov(inputs, kern, hp, deriv=None, input_2=None):
-    """kernel-to-matrices.R:71-503 for character kernels (se/perio/rq/lin)."""
+    """kernel-to-matrices.R:71-503 for character kernels (se/perio/rq/lin); "CONV<O>" stands for
+    kern = convolution_kernel on inputs whose last column is the output index."""
     x = _mat(inputs)
     y = x if input_2 is None else _mat(input_2)
+    if kern.startswith("CONV"):
+        return convolution_kernel(x, y, hp, int(kern[4:]), deriv)
     if deriv is not None and deriv == "noise":
         return cpp_noise(x, y, hp["noise"])                       # :440-447
     mat = _compound(kern, x, y, hp, deriv)
@@ -283,6 +331,10 @@ def logdet_lu(mat):
 
 def hp_names(kern, noise):
     """Column order of hp() for a character kernel (hyperparameters.R)."""
+    if kern.startswith("CONV"):
+        O = int(kern[4:])
+        return (["l_t_%d" % (o + 1) for o in range(O)] + ["S_t_%d" % (o + 1) for o in range(O)] + ["l_u_t"] +
+                (["noise_%d" % (o + 1) for o in range(O)] if noise else []))
     names = []
     for t in kern.split(" "):
         if t in _KERNELS:

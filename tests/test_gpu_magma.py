@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from helpers import make_case, upload, relerr, ulp_perturb
+from magmaclustr_b200.dataprep import Prepared
 from magmaclustr_b200 import _lib as L
 from oracle import kernels as OK
 from oracle import magma as OM
@@ -388,3 +389,67 @@ def test_chol_inv_jitter_split_product_is_bit_identical(ctx):
     bad = np.full((130, 130), np.nan)
     with pytest.raises(L.MagmaError):
         ctx.chol_inv_jitter(bad, 1e-10)
+
+
+# ---- multi-output convolution kernel (kernels.R:16-140) as a kernel type: "CONV<O>" -------------------------
+def _mo_case(seed=31, O=2, M=6, n=7):
+    rng = np.random.default_rng(seed)
+    pool = np.round(np.linspace(-1, 1, 41), 3)
+    ids, X, y = [], [], []
+    for t in range(M):
+        for o in range(O):
+            pts = np.sort(rng.choice(pool, size=n, replace=False))
+            ids += ["t%02d" % t] * n
+            X.append(np.column_stack([pts, np.full(n, float(o))]))        # last column: 0-based output index
+            y.append(np.sin(3 * pts) * (1 + o) + 0.1 * rng.normal(size=n) + t * 0.05)
+    return ids, np.vstack(X), np.concatenate(y)
+
+
+def test_convolution_kernel_matrices(ctx):
+    """kern_to_cov with kern = convolution_kernel: value, every derivative, cross-covariance; list_kern_to_inv per task."""
+    k = L.parse_kernel("CONV2", True)
+    names = L.hp_names(k)
+    assert names == OK.hp_names("CONV2", True) == ["l_t_1", "l_t_2", "S_t_1", "S_t_2", "l_u_t", "noise_1", "noise_2"]
+    ids, X, y = _mo_case()
+    hp = np.array([-1.2, -0.7, 0.4, -0.3, -2.0, -1.5, -2.5])
+    hpd = dict(zip(names, hp))
+    x1, x2 = X[:14], X[14:25]
+    np.testing.assert_allclose(ctx.kern_to_cov(k, hp, x1), OK.kern_to_cov(x1, "CONV2", hpd), rtol=1e-13, atol=1e-300)
+    np.testing.assert_allclose(ctx.kern_to_cov(k, hp, x1, x2), OK.kern_to_cov(x1, "CONV2", hpd, input_2=x2), rtol=1e-13)
+    for p, nm in enumerate(names):
+        np.testing.assert_allclose(ctx.kern_to_cov(k, hp, x1, deriv=p), OK.kern_to_cov(x1, "CONV2", hpd, deriv=nm),
+                                   rtol=1e-12, atol=1e-15, err_msg=nm)
+    k3 = L.parse_kernel("CONV3", True)
+    assert k3.n_hp == 10
+    with pytest.raises(L.MagmaError):
+        L.parse_kernel("CONV4", True)                       # 13 hyper-parameters > MB_MAX_HP
+
+
+def test_convolution_kernel_e_step_and_objective(ctx):
+    """A multi-output Magma E step and the per-task objective / gradient with kern_0 = kern_i = convolution_kernel: points
+    are (coordinate, output) pairs, the union grid is over those pairs."""
+    ids, X, y = _mo_case()
+    prep = Prepared(ids, X, y)
+    odb = OM.Dataset(ids, X, y)
+    k0, ki = L.parse_kernel("CONV2", False), L.parse_kernel("CONV2", True)
+    n0, ni = L.hp_names(k0), L.hp_names(ki)
+    hp0 = np.array([-1.0, -0.8, 0.5, 0.2, -1.5])
+    hpi = np.array([[-1.2 + 0.01 * t, -0.7, 0.4, -0.3 - 0.02 * t, -2.0, -1.5, -2.5] for t in range(len(prep.ids))])
+    o_hp0 = dict(zip(n0, hp0))
+    o_hpi = {i: dict(zip(ni, hpi[t])) for t, i in enumerate(prep.ids)}
+    ctx.upload_dataset(prep.offs, prep.X, prep.y, prep.grid_index, prep.grid_X)
+    U = ctx.U
+    pm, pc, info = ctx.e_step(k0, hp0, ki, hpi, np.zeros(U))
+    opm, opc = OM.e_step(odb, 0.0, "CONV2", "CONV2", o_hp0, o_hpi, 1e-10)
+    rng = np.random.default_rng(0)
+    h = OM.e_step(odb, 0.0, "CONV2", "CONV2", dict(zip(n0, ulp_perturb(hp0, rng))), o_hpi, 1e-10)
+    sm, sc = relerr(h[0], opm), relerr(h[1], opc)
+    assert relerr(pm, opm) < 30 * sm + 1e-9 and relerr(pc, opc) < 30 * sc + 1e-9
+    f, g, r = ctx.logL_GP_mod_tasks(ki, hpi, opm, opc)
+    for t, i in enumerate(prep.ids):
+        _, Xi, yi = odb.tasks[i]
+        idx = odb.index[i]
+        of = OM.logL_GP_mod(o_hpi[i], Xi, yi, opm[idx], "CONV2", opc[np.ix_(idx, idx)], 1e-10)
+        og = OM.gr_GP_mod(o_hpi[i], Xi, yi, opm[idx], "CONV2", opc[np.ix_(idx, idx)], 1e-10)
+        assert abs(f[t] - of) <= 1e-9 * max(1.0, abs(of))
+        np.testing.assert_allclose(g[t], og, rtol=1e-8, atol=1e-8)
