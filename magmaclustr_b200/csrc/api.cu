@@ -674,6 +674,9 @@ extern "C" int mb_kern_to_cov(mb_context* c, const mb_kernel* k, const double* h
   MB_TRY(check_ctx(c));
   if (!k || !hp || !x1 || !out || n1 < 0 || d < 1) MB_FAIL(-1, "bad argument");
   if (deriv >= k->n_hp) MB_FAIL(-1, "deriv out of range");
+  // the multi-output kernel carries its per-output noise only on the square matrix of a set of points against itself
+  // (kernel-to-matrices.R:121-157); the single-output kernels add exp(noise) on every coincident pair (:481-487)
+  const bool cross = x2 != nullptr && x2 != x1;
   if (!x2) { x2 = x1; n2 = n1; }
   if (n1 == 0 || n2 == 0) return 0;
   DevKern kd = make_devkern(k);
@@ -685,7 +688,16 @@ extern "C" int mb_kern_to_cov(mb_context* c, const mb_kernel* k, const double* h
   MB_TRY(h2d(d1, x1, b1, c->st));
   MB_TRY(h2d(d2, x2, b2, c->st));
   // column-major n1 x n2 output: element (i,j) at i + j*n1
-  LAUNCH(c, launch_dense_cov(kd, hp, d1, n1, d2, n2, d, deriv, 1, dout, 1, n1, c->st));
+  DevKern kd_eff = kd;
+  if (cross && kd.types[0] == MB_KERN_CONV) {
+    if (deriv >= 2 * kd.n_prod + 1) {       // derivative w.r.t. a noise term of a cross-covariance: zero matrix
+      std::vector<double> z((size_t)n1 * n2, 0.0);
+      memcpy(out, z.data(), z.size() * 8);
+      return 0;
+    }
+    kd_eff.has_noise = 0;
+  }
+  LAUNCH(c, launch_dense_cov(kd_eff, hp, d1, n1, d2, n2, d, deriv, 1, dout, 1, n1, c->st));
   MB_TRY(d2h(out, dout, bo, c->st));
   CU(cudaStreamSynchronize(c->st));
   return 0;
