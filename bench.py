@@ -365,8 +365,10 @@ def main():
                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (no FP64 figure in MEASURED_PEAKS.json)",
                      "kernel_ms_per_step": prof["ms"] / args.steps,
                      "kernel_share_of_step": prof["ms"] / float(np.sum(ms)),
-                     "round_overhead_ms_per_step": prof["round_gap_ms"] / args.steps,
-                     "e_step_and_monitoring_ms_per_step": prof["other_ms"] / args.steps},
+                     "persistent_m_step_kernel_ms_per_step": prof["persistent_kernel_ms"] / args.steps,
+                     "between_launches_ms_per_step": prof["round_gap_ms"] / args.steps,
+                     "phases_ms_per_step": {"e_step": prof["e_step_ms"] / args.steps, "m_step": prof["m_step_ms"] / args.steps,
+                                            "logL_monitoring": prof["monitoring_ms"] / args.steps}},
     }
     if fit:
         line["fit"] = fit

@@ -88,6 +88,7 @@ _SIGS = {
     "mb_profile": [_vp, C.c_int],
     "mb_profile_read": [_vp, _dp],
     "mb_profile_read_gaps": [_vp, _dp],
+    "mb_profile_read_phases": [_vp, _dp],
     "mb_mstep_cycles": [_vp, _dp],
     "mb_flush_l2": [_vp, C.c_int64],
     "mb_matmul": [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int],

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include <dlfcn.h>
@@ -192,6 +193,9 @@ struct mb_context {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
   size_t prof_used = 0;
   double prof_ms = 0.0, prof_gap_ms = 0.0, prof_other_ms = 0.0;
+  // wall-clock phases of dev_em_step while profiling: [0] E step, [1] M step, [2] monitoring, [3] persistent M-step kernel (device)
+  double prof_phase[4] = {0.0, 0.0, 0.0, 0.0};
+  std::vector<char> prof_kind;     // per profiled launch: 0 = lock-step objective launch, 1 = persistent M-step kernel
   int64_t prof_launches = 0, prof_evals = 0;
   // tasks with more than TK_MAXN points: multi-stream pipelines of the large-matrix kernels (bigtasks.cu)
   BigTaskPool* big = nullptr;
@@ -231,6 +235,8 @@ static int launch_obj(mb_context* c, const TaskObjArgs& a, int n_launch, cudaStr
     CU(cudaEventCreate(&e1));
     c->prof_ev.push_back({e0, e1});
   }
+  if (c->prof_kind.size() <= c->prof_used) c->prof_kind.resize(c->prof_used + 1);
+  c->prof_kind[c->prof_used] = 0;
   auto& ev = c->prof_ev[c->prof_used++];
   CU(cudaEventRecord(ev.first, st));
   LAUNCH(c, launch_task_objective_any(a2, n_launch, st));
@@ -244,6 +250,7 @@ static int prof_collect(mb_context* c) {
     CU(cudaEventElapsedTime(&ms, c->prof_ev[i].first, c->prof_ev[i].second));
     c->prof_ms += ms;
     c->prof_launches++;
+    if (i < c->prof_kind.size() && c->prof_kind[i] == 1) c->prof_phase[3] += ms;
     if (i + 1 < c->prof_used) {   // stream time between two profiled launches: advance kernel + host round trip
       float gap = 0;
       CU(cudaEventSynchronize(c->prof_ev[i + 1].first));
@@ -1139,6 +1146,8 @@ static int optimise(mb_context* c, std::vector<SingleProblem>& singles, bool tas
         CU(cudaEventCreate(&e1));
         c->prof_ev.push_back({e0, e1});
       }
+      if (c->prof_kind.size() <= c->prof_used) c->prof_kind.resize(c->prof_used + 1);
+      c->prof_kind[c->prof_used] = 1;
       auto& ev = c->prof_ev[c->prof_used++];
       e0 = ev.first; e1 = ev.second;
       CU(cudaEventRecord(e0, c->st));
@@ -1728,12 +1737,21 @@ static int dev_em_step(mb_context* c, const mb_kernel* kern_0, double* hp_0, con
                        double* hp_i_dev, int shared_hp, const double* m0_dev, double pen, double* logL,
                        int64_t* stats) {
   DevKern kdi = make_devkern(kern_i);
+  // every phase ends with the host waiting for its result, so host time stamps are stream time (mb_profile only)
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = c->prof_on ? now() : 0.0;
   MB_TRY(dev_e_step(c, 1, kern_0, hp_0, kdi, hp_i_dev, kdi.n_hp, m0_dev, nullptr, c->d_gridX.as<double>(),
                     c->U, nullptr, pen, c->pm.as<double>(), c->pc.as<double>(), nullptr));
+  const double t1 = c->prof_on ? now() : 0.0;
   MB_TRY(dev_m_step(c, kern_0, hp_0, kern_i, hp_i_dev, shared_hp, m0_dev, c->pm.as<double>(),
                     c->pc.as<double>(), pen, stats));
+  const double t2 = c->prof_on ? now() : 0.0;
   MB_TRY(dev_logL_monitoring(c, kern_0, hp_0, kern_i, hp_i_dev, kdi.n_hp, m0_dev, c->pm.as<double>(),
                              c->pc.as<double>(), pen, logL));
+  if (c->prof_on) {
+    const double t3 = now();
+    c->prof_phase[0] += t1 - t0; c->prof_phase[1] += t2 - t1; c->prof_phase[2] += t3 - t2;
+  }
   return 0;
 }
 
@@ -1891,6 +1909,13 @@ extern "C" int mb_profile_read_gaps(mb_context* c, double* out2) {
   MB_TRY(prof_collect(c));
   out2[0] = c->prof_gap_ms; out2[1] = c->prof_other_ms;
   c->prof_gap_ms = 0; c->prof_other_ms = 0;
+  return 0;
+}
+// Call AFTER mb_profile_read: host-clock milliseconds dev_em_step spent in the E step, the M step and the monitoring
+// (each ends with a synchronisation) and the device milliseconds of the persistent M-step kernel, since the last read
+extern "C" int mb_profile_read_phases(mb_context* c, double* out4) {
+  MB_TRY(check_ctx(c));
+  for (int i = 0; i < 4; ++i) { out4[i] = c->prof_phase[i]; c->prof_phase[i] = 0.0; }
   return 0;
 }
 // SM cycles the persistent M-step kernel of the LAST per-task M step spent in objective evaluations (out2[0]) and in

@@ -71,32 +71,19 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_inverse
       for (int k = 0; k < K; ++k) {
         const double tau = a.tau ? a.tau[task * K + k] : 1.0;
         double* pk = pinv + (size_t)k * U * U;
-        // read-modify-write of the leaf's accumulator in L2 (ld.cg / st.cg: other SMs wrote it before).  The grid positions
-        // of one task are distinct, so the targets of one task never alias: eight independent loads are in flight before
-        // the first store.
-        for (int e0 = tid; e0 < n * n; e0 += 8 * T3_THREADS) {
-          size_t c[8];
-          double v[8], old[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int e = e0 + q * T3_THREADS;
-            c[q] = 0; v[q] = 0.0; old[q] = 0.0;
-            if (e < n * n) {
-              const int i = e / n, j = e - i * n;
-              c[q] = (size_t)s.gi[i] * U + s.gi[j];
-              const double x = bad ? NAN : symA_at<N8C>(s.T1, i, j);
-              v[q] = a.tau ? tau * x : x;
-              old[q] = __ldcg(pk + c[q]);
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (e0 + q * T3_THREADS < n * n) __stcg(pk + c[q], old[q] + v[q]);
+        // The leaf's accumulator lives in L2; the ticket admits one task at a time and the grid positions of one task are
+        // distinct, so every accumulator element receives at most one addend per ticket: a fire-and-forget reduction
+        // (red.global.add.f64 -- no load round trip on the ordered section) adds exactly what a read-modify-write would,
+        // in the same order.  The fence below completes them before the ticket moves on.
+        for (int e = tid; e < n * n; e += T3_THREADS) {
+          const int i = e / n, j = e - i * n;
+          const double x = bad ? NAN : symA_at<N8C>(s.T1, i, j);
+          atomicAdd(pk + (size_t)s.gi[i] * U + s.gi[j], a.tau ? tau * x : x);
         }
         double* wk = pw + (size_t)k * U;
         for (int i = tid; i < n; i += T3_THREADS) {
           const double v = bad ? NAN : al[i];
-          __stcg(wk + s.gi[i], __ldcg(wk + s.gi[i]) + (a.tau ? tau * v : v));
+          atomicAdd(wk + s.gi[i], a.tau ? tau * v : v);
         }
       }
       __threadfence();

@@ -276,8 +276,11 @@ class Context:
         check(L.lib().mb_profile_read_gaps(self._h, ptr(gaps)))
         out = np.zeros(3)
         check(L.lib().mb_profile_read(self._h, ptr(out)))
+        ph = np.zeros(4)
+        check(L.lib().mb_profile_read_phases(self._h, ptr(ph)))
         return {"ms": out[0], "launches": int(out[1]), "evals": int(out[2]), "round_gap_ms": gaps[0],
-                "other_ms": gaps[1]}
+                "other_ms": gaps[1], "e_step_ms": ph[0], "m_step_ms": ph[1], "monitoring_ms": ph[2],
+                "persistent_kernel_ms": ph[3]}
 
     def mstep_cycles(self):
         out = np.zeros(2)
