@@ -192,6 +192,120 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
+def run_c4(args, rank, world, local_rank):
+    """--config c4: BASELINE config 4 (common_input = TRUE, M = 256 tasks on one N = U = 4096-point grid, SE kernels,
+    shared_hp = FALSE), the tasks sharded over the ranks.  Every task is a pipeline of 4096 x 4096 factorisations and
+    products on HBM-resident matrices; a step is one EM iteration from the initial hyper-parameters."""
+    import torch
+    from magmaclustr_b200 import _lib as L
+    from magmaclustr_b200.engine import Context
+    from magmaclustr_b200.parallel import shard_tasks, init_library_nccl
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    m4, n4 = args.c4_tasks, args.c4_points
+    df4, _ = simu_db_c4(m4, n4)
+    prep = Prepared4(df4.ID.values, df4.Input.values, df4.Output.values)
+    hp0 = ini_hp4("SE", ["0"], True, False, 6).drop(columns="ID").iloc[0].to_numpy(dtype=np.float64)
+    hpi = ini_hp4("SE", prep.ids, False, True, 106).drop(columns="ID").to_numpy(dtype=np.float64)
+    k0, ki = L.parse_kernel("SE", False), L.parse_kernel("SE", True)
+    ctx = Context(local_rank)
+    lo, hi_ = shard_tasks(prep.offs, rank, world, len(prep.grid_X))
+    offs = (prep.offs[lo:hi_ + 1] - prep.offs[lo]).astype(np.int64)
+    r0, r1 = int(prep.offs[lo]), int(prep.offs[hi_])
+    X_h, y_h, gi_h = (np.ascontiguousarray(prep.X[r0:r1]), np.ascontiguousarray(prep.y[r0:r1]),
+                      np.ascontiguousarray(prep.grid_index[r0:r1]))
+    hpi_loc = np.ascontiguousarray(hpi[lo:hi_])
+    if world > 1:
+        init_library_nccl(ctx, dist, rank, world)
+        ctx.set_shard(lo, len(prep.offs) - 1)
+    ctx.upload_dataset(offs, X_h, y_h, gi_h, prep.grid_X)
+    m0 = np.zeros(ctx.U)
+    ctx.set_state(k0, hp0, ki, hpi_loc, m0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    for _ in range(args.warmup):
+        ctx.em_step_resident(k0, ki, restart=True)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launches
+    ms, stats, logL = [], None, None
+    for _ in range(args.steps):
+        barrier()                           # operands (256 x 134 MB of factors and products per pass) exceed L2 many times over
+        ctx.timer_start()
+        logL, stats = ctx.em_step_resident(k0, ki, restart=True)
+        ms.append(ctx.timer_stop_ms())
+        barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launches - launches0
+    total_ms = float(np.sum(ms))
+    evals = float(stats[2])
+    if world > 1:
+        t = torch.tensor([total_ms, 0.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t[0].item())
+        t = torch.tensor([evals], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        evals = float(t[0].item())
+    # end to end: host buffers in, host buffers out
+    e2e_ms = []
+    h0_h, hi_h = hp0.copy(), hpi_loc.copy()
+    for s in range(1 + args.steps):
+        h0_h[:] = hp0
+        hi_h[:] = hpi_loc
+        barrier()
+        t0 = time.perf_counter()
+        ctx.upload_dataset(offs, X_h, y_h, gi_h, prep.grid_X)
+        ctx.em_step(k0, h0_h, ki, hi_h, m0)
+        dt = (time.perf_counter() - t0) * 1e3
+        barrier()
+        if s >= 1:
+            e2e_ms.append(dt)
+    e2e_total = float(np.sum(e2e_ms))
+    if world > 1:
+        t = torch.tensor([e2e_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_total = float(t.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak = dgemm_peak_tflops()
+    ms_g = ctx.bench_dense(0, n4, reps=3)
+    gemm_tf = 2.0 * float(n4) ** 3 / ms_g / 1e9
+    step_tf = evals * FLOPS_PER_EVAL * float(n4) ** 3 / (total_ms / args.steps) / 1e9
+    line = {
+        "metric": "train_magma EM steps/sec at M=%d,N=%d (config 4)" % (m4, n4), "value": args.steps / (total_ms * 1e-3),
+        "unit": "EM steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C4: train_magma EM step, common_input=TRUE, M=%d tasks on one N=U=%d grid, SE kernels, "
+                               "shared_hp=FALSE" % (m4, n4),
+                   "l2": "inputs larger than L2 (every task streams 134 MB matrices)", "tasks_per_rank": int(hi_ - lo),
+                   "task_evals_per_step": int(evals), "hp0_evals": int(stats[0]), "logL": logL},
+        "clocks": clocks,
+        "e2e": {"value": args.steps / (e2e_total * 1e-3), "unit": "EM steps/s",
+                "h2d_bytes_per_step": int(offs.nbytes + X_h.nbytes + y_h.nbytes + gi_h.nbytes + prep.grid_X.nbytes + hi_h.nbytes + m0.nbytes),
+                "d2h_bytes_per_step": int(hi_h.nbytes + 8)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "k_big_gemm (128 x 128 DMMA tiles)", "achieved": gemm_tf, "peak": peak,
+                     "unit": "TFLOP/s", "frac": gemm_tf / peak if peak else None, "traffic": None,
+                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this run",
+                     "whole_step_tflops_at_5n3_per_eval": step_tf,
+                     "whole_step_frac_of_dgemm": step_tf / peak / world if peak else None},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -203,12 +317,18 @@ def main():
     ap.add_argument("--no-fit", action="store_true")
     ap.add_argument("--no-c4", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--config", default="c2", choices=["c2", "c4"])
+    ap.add_argument("--c4-tasks", type=int, default=256)
+    ap.add_argument("--c4-points", type=int, default=4096)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.config == "c4":
+        run_c4(args, rank, world, local_rank)
         return
 
     import torch

@@ -60,8 +60,43 @@ __device__ __forceinline__ void bg_load_tile(double* dst, const double* src, int
 
 extern __shared__ double4 big_smem_raw[];
 
-template <bool AK, bool BK, bool V16, bool GRAD>
+// ---- bulk asynchronous copies (TMA engine, SASS UBLKCP) completing on shared-memory mbarriers ----------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(b), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem)),
+               "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// BULK (k-major operands with 16-byte aligned rows only): the operand tiles of a stage arrive as 2 x 16 bulk copies -- one
+// 1 KB row of the k-major tile each, issued by the 32 lanes of warp 0 into the padded rows of the shared-memory tile --
+// that complete on the stage's mbarrier; the other 15 warps issue nothing but fragment loads and DMMAs.  Otherwise: the
+// cp.async pipeline (every thread copies two 16-byte pieces per operand and stage).
+template <bool AK, bool BK, bool V16, bool GRAD, bool BULK>
 __global__ void __launch_bounds__(BG_THREADS, 1) k_big_gemm(const __grid_constant__ BigGemmArgs a) {
+  static_assert(!BULK || (AK && BK && V16), "bulk copies need k-major operands with aligned rows");
   if (a.fail && *a.fail) return;
   const int m0 = blockIdx.y * BG_BM, n0 = blockIdx.x * BG_BN;
   const int gr0 = a.row0 + m0, gc0 = a.col0 + n0;
@@ -81,25 +116,46 @@ __global__ void __launch_bounds__(BG_THREADS, 1) k_big_gemm(const __grid_constan
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  auto load = [&](int kt) {
-    double* As = sm + (size_t)(kt % BG_STAGES) * 2 * BG_TILE_D;
-    double* Bs = As + BG_TILE_D;
-    const int k0 = klo + kt * BG_BK;
-    bg_load_tile<AK, V16>(As, a.A, a.lda, k0, a.K, m0, a.M, tid);
-    bg_load_tile<BK, V16>(Bs, a.B, a.ldb, k0, a.K, n0, a.N, tid);
-  };
-#pragma unroll
-  for (int s = 0; s < BG_STAGES - 1; ++s) {
-    if (s < nk) load(s);
-    cp_commit();
-  }
-  for (int kt = 0; kt < nk; ++kt) {
-    cp_wait<BG_STAGES - 2>();
+  if constexpr (BULK) {
+    uint64_t* full = reinterpret_cast<uint64_t*>(sm + (size_t)BG_STAGES * 2 * BG_TILE_D);
+    if (tid == 0) {
+      for (int s = 0; s < BG_STAGES; ++s) mbar_init(full + s, 32);
+      mbar_fence_init();
+    }
     __syncthreads();
-    if (kt + BG_STAGES - 1 < nk) load(kt + BG_STAGES - 1);
-    cp_commit();
-    const double* As = sm + (size_t)(kt % BG_STAGES) * 2 * BG_TILE_D;
-    const double* Bs = As + BG_TILE_D;
+    // warp 0, lane = 16 * operand + row of the k-tile
+    const int op = lane >> 4, row = lane & 15;
+    const double* src = op ? a.B : a.A;
+    const int64_t ld = op ? a.ldb : a.lda;
+    const int x0 = op ? n0 : m0;
+    int cnt = (op ? a.N : a.M) - x0;
+    cnt = cnt > BG_BM ? BG_BM : cnt;
+    auto issue = [&](int kt) {
+      const int stage = kt % BG_STAGES;
+      double* dst = sm + (size_t)stage * 2 * BG_TILE_D + (size_t)op * BG_TILE_D + (size_t)row * BG_LDK;
+      const int kk = klo + kt * BG_BK + row;
+      unsigned bytes = 0;
+      if (kk < a.K) {
+        bytes = 8u * (unsigned)(cnt & ~1);
+        if (cnt & 1) { dst[cnt - 1] = src[(int64_t)kk * ld + x0 + cnt - 1]; fence_proxy_async_smem(); }
+      } else {   // rows beyond K multiply every output: zeros (only the last k-tile of a ragged K)
+        for (int c = 0; c < BG_BM; ++c) dst[c] = 0.0;
+        fence_proxy_async_smem();
+      }
+      mbar_arrive_expect_tx(full + stage, bytes);
+      if (bytes) bulk_g2s(dst, src + (int64_t)kk * ld + x0, bytes, full + stage);
+    };
+    if (warp == 0) {
+#pragma unroll
+      for (int s = 0; s < BG_STAGES - 1; ++s)
+        if (s < nk) issue(s);
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+      mbar_wait(full + (kt % BG_STAGES), (unsigned)((kt / BG_STAGES) & 1));
+      __syncthreads();   // every warp has left the stage that is refilled next
+      if (warp == 0 && kt + BG_STAGES - 1 < nk) issue(kt + BG_STAGES - 1);
+      const double* As = sm + (size_t)(kt % BG_STAGES) * 2 * BG_TILE_D;
+      const double* Bs = As + BG_TILE_D;
 #pragma unroll
     for (int ks = 0; ks < BG_BK; ks += 4) {
       double fa[4], fb[4];
@@ -114,8 +170,44 @@ __global__ void __launch_bounds__(BG_THREADS, 1) k_big_gemm(const __grid_constan
 #pragma unroll
         for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
     }
+    }
+  } else {
+    auto load = [&](int kt) {
+      double* As = sm + (size_t)(kt % BG_STAGES) * 2 * BG_TILE_D;
+      double* Bs = As + BG_TILE_D;
+      const int k0 = klo + kt * BG_BK;
+      bg_load_tile<AK, V16>(As, a.A, a.lda, k0, a.K, m0, a.M, tid);
+      bg_load_tile<BK, V16>(Bs, a.B, a.ldb, k0, a.K, n0, a.N, tid);
+    };
+  #pragma unroll
+    for (int s = 0; s < BG_STAGES - 1; ++s) {
+      if (s < nk) load(s);
+      cp_commit();
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+      cp_wait<BG_STAGES - 2>();
+      __syncthreads();
+      if (kt + BG_STAGES - 1 < nk) load(kt + BG_STAGES - 1);
+      cp_commit();
+      const double* As = sm + (size_t)(kt % BG_STAGES) * 2 * BG_TILE_D;
+      const double* Bs = As + BG_TILE_D;
+  #pragma unroll
+      for (int ks = 0; ks < BG_BK; ks += 4) {
+        double fa[4], fb[4];
+  #pragma unroll
+        for (int i = 0; i < 4; ++i)
+          fa[i] = AK ? As[(ks + t) * BG_LDK + wm + 8 * i + g] : As[(wm + 8 * i + g) * BG_LDM + ks + t];
+  #pragma unroll
+        for (int j = 0; j < 4; ++j)
+          fb[j] = BK ? Bs[(ks + t) * BG_LDK + wn + 8 * j + g] : Bs[(wn + 8 * j + g) * BG_LDM + ks + t];
+  #pragma unroll
+        for (int i = 0; i < 4; ++i)
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+      }
+    }
+    cp_wait<0>();
   }
-  cp_wait<0>();
 
   if (GRAD) {
     // contraction with the kernel derivatives (upper triangle, off-diagonal weight 2)
@@ -195,18 +287,25 @@ __global__ void __launch_bounds__(BG_THREADS, 1) k_big_gemm(const __grid_constan
   }
 }
 
-static const size_t BG_SMEM = (size_t)BG_STAGES * 2 * BG_TILE_D * sizeof(double);
+static const size_t BG_SMEM = (size_t)BG_STAGES * 2 * BG_TILE_D * sizeof(double) + BG_STAGES * sizeof(uint64_t);
 
-template <bool AK, bool BK, bool V16, bool GRAD>
+template <bool AK, bool BK, bool V16, bool GRAD, bool BULK = false>
 static cudaError_t bg_launch_t(const BigGemmArgs& a, dim3 grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_big_gemm<AK, BK, V16, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BG_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(k_big_gemm<AK, BK, V16, GRAD, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BG_SMEM);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  k_big_gemm<AK, BK, V16, GRAD><<<grid, BG_THREADS, BG_SMEM, st>>>(a);
+  k_big_gemm<AK, BK, V16, GRAD, BULK><<<grid, BG_THREADS, BG_SMEM, st>>>(a);
   return cudaGetLastError();
+}
+
+// MB_BIG_GEMM_LOADER=cpasync keeps the cp.async pipeline for k-major operands too (A/B measurements)
+static bool bg_use_bulk() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MB_BIG_GEMM_LOADER"); v = (e && !strcmp(e, "cpasync")) ? 0 : 1; }
+  return v == 1;
 }
 
 void big_gemm_grid(int M, int N, int* gx, int* gy) { *gx = (N + BG_BN - 1) / BG_BN; *gy = (M + BG_BM - 1) / BG_BM; }
@@ -218,8 +317,10 @@ cudaError_t launch_big_gemm(const BigGemmArgs& a, int a_kmajor, int b_kmajor, cu
                    ((((uintptr_t)a.B) & 15) == 0);
   if (a.flags & BG_EPI_GRAD) {
     if (!a_kmajor || !b_kmajor) return cudaErrorInvalidValue;
+    if (v16 && bg_use_bulk()) return bg_launch_t<true, true, true, true, true>(a, grid, st);
     return v16 ? bg_launch_t<true, true, true, true>(a, grid, st) : bg_launch_t<true, true, false, true>(a, grid, st);
   }
+  if (a_kmajor && b_kmajor && v16 && bg_use_bulk()) return bg_launch_t<true, true, true, false, true>(a, grid, st);
 #define BG_CASE(ak, bk)                                                                     \
   if ((a_kmajor != 0) == ak && (b_kmajor != 0) == bk)                                       \
     return v16 ? bg_launch_t<ak, bk, true, false>(a, grid, st) : bg_launch_t<ak, bk, false, false>(a, grid, st);
