@@ -291,10 +291,12 @@ int mb_profile_read(mb_context*, double* out3);
 /* Call BEFORE mb_profile_read: out2[0] = stream milliseconds between consecutive profiled launches inside the
  * lock-step M step (optimiser advance kernel + host round trip), out2[1] = the longer gaps (E step, monitoring). */
 int mb_profile_read_gaps(mb_context*, double* out2);
-/* Call AFTER mb_profile_read: out4 = host-clock milliseconds of the E step, the M step and the monitoring of the
- * profiled mb_em_step* calls (each phase ends with a synchronisation), and the device milliseconds of the persistent
- * M-step kernel among the profiled launches.  Diagnostics only (bench.py). */
-int mb_profile_read_phases(mb_context*, double* out4);
+/* Call AFTER mb_profile_read: out12[0..2] = host-clock milliseconds of the E step, the M step and the monitoring of the
+ * profiled mb_em_step* calls (each phase ends with a synchronisation), [3] = device milliseconds of the persistent
+ * M-step kernel among the profiled launches, [4..8] = stream milliseconds of the E step's segments (memsets + task
+ * kernel, wait for inv_0, leaf reduction incl. the all-reduce, inverse of post_inv + mean, retry statistics), [9..11]
+ * reserved.  Diagnostics only (bench.py). */
+int mb_profile_read_phases(mb_context*, double* out12);
 /* SM cycles the persistent per-task M-step kernel (R/em-magma.R:200-230: one optim() per task) of the last M step spent
  * in objective evaluations (out2[0]) and in L-BFGS-B steps (out2[1]), summed over its CTAs.  Environment knobs read at
  * mb_create: MB_FUSED_BELOW = number of still-active tasks below which the lock-step rounds hand over to the persistent

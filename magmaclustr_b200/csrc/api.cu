@@ -80,6 +80,7 @@ cudaError_t launch_dense_obj(const DevKern& kd, const double* hp_host, const dou
                              const double* al, const double* r, const double* logdet,
                              int from_chol, int want_grad, double* part, double* res,
                              cudaStream_t st);
+cudaError_t launch_mirror_upper(double* m, int U, int nmat, int64_t stride, cudaStream_t st);
 cudaError_t launch_reduce_tree(int64_t count, int nparts, const double* base, const double* part, int64_t part_stride,
                                double* out, cudaStream_t st);
 cudaError_t launch_leaf_sums(const double* v, int P, const int64_t* leaf_offs, int n_leaves, double* out, cudaStream_t st);
@@ -194,7 +195,8 @@ struct mb_context {
   size_t prof_used = 0;
   double prof_ms = 0.0, prof_gap_ms = 0.0, prof_other_ms = 0.0;
   // wall-clock phases of dev_em_step while profiling: [0] E step, [1] M step, [2] monitoring, [3] persistent M-step kernel (device)
-  double prof_phase[4] = {0.0, 0.0, 0.0, 0.0};
+  double prof_phase[12] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  cudaEvent_t ev_mark[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // E-step segment marks on st (mb_profile)
   std::vector<char> prof_kind;     // per profiled launch: 0 = lock-step objective launch, 1 = persistent M-step kernel
   int64_t prof_launches = 0, prof_evals = 0;
   // tasks with more than TK_MAXN points: multi-stream pipelines of the large-matrix kernels (bigtasks.cu)
@@ -343,7 +345,7 @@ static int ctx_allreduce(mb_context* c, void* dev, int64_t count, cudaStream_t s
 // ================================================================================================
 static int leaf_count(int64_t g_total, int U) {
   const int64_t per = ((int64_t)U * U + U) * 8;
-  int64_t cap = per > 0 ? ((int64_t)1 << 30) / per : 128;
+  int64_t cap = per > 0 ? ((int64_t)1 << 31) / per : 128;
   if (cap < 1) cap = 1;
   int64_t m = 128;
   if (g_total < m) m = g_total;
@@ -524,6 +526,7 @@ extern "C" int mb_destroy(mb_context* c) {
   c->hpr_cov.release();
   if (c->nccl && nccl_api()) nccl_api()->CommDestroy(c->nccl);
   for (auto& ev : c->prof_ev) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  for (auto& ev : c->ev_mark) if (ev) cudaEventDestroy(ev);
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
   if (c->ev_single) cudaEventDestroy(c->ev_single);
@@ -974,25 +977,22 @@ static int dev_e_step(mb_context* c, int K, const mb_kernel* kern_k, const doubl
   MB_TRY(c->post_inv.ensure(K * UU * 8));
   MB_TRY(c->retries.ensure(c->db.n_tasks * 4));
   int max_r0 = 0, max_rp = 0;
-  // inverse prior covariances on st2 (independent of the task work on st)
-  for (int k = 0; k < K; ++k) {
-    LAUNCH(c, launch_dense_cov(kdk, hp_k_host + (size_t)k * kdk.n_hp, gridX, U, gridX, U, c->db.D, -1, 1,
-                               c->ws1.Kmat.as<double>(), U, 1, c->st2));
-    int r = 0;
-    int rc = dev_cholinv(c, c->ws1, c->ws1.Kmat.as<double>(), U, pen, c->st2, &r, nullptr, nullptr);
-    if (rc != 0) return rc;
-    if (r > max_r0) max_r0 = r;
-    CU(cudaMemcpyAsync(c->inv0.as<double>() + k * UU, c->ws1.A.p, UU * 8, cudaMemcpyDeviceToDevice, c->st2));
-  }
   // task inverses, added leaf by leaf in task order (estep3.cu); one accumulator [K x U x U | K x U] per local leaf
   const bool big = c->db.nmax > TK_MAXN;
   MB_TRY(ctx_leaves(c, U));
   const int nl = c->lv_n;
   const int64_t pstride = (int64_t)K * (UU + U);
   MB_TRY(c->leafbuf.ensure((size_t)nl * pstride * 8));
-  MB_TRY(c->tickets.ensure((size_t)nl * sizeof(int)));
+  MB_TRY(c->tickets.ensure((size_t)(nl + 2) * sizeof(int)));   // [nl] = the E-step kernel's work counter
+  auto mark = [&](int i) -> int {
+    if (!c->prof_on) return 0;
+    if (!c->ev_mark[i]) CU(cudaEventCreate(&c->ev_mark[i]));
+    CU(cudaEventRecord(c->ev_mark[i], c->st));
+    return 0;
+  };
+  MB_TRY(mark(0));
   CU(cudaMemsetAsync(c->leafbuf.p, 0, (size_t)nl * pstride * 8, c->st));
-  CU(cudaMemsetAsync(c->tickets.p, 0, (size_t)nl * sizeof(int), c->st));
+  CU(cudaMemsetAsync(c->tickets.p, 0, (size_t)(nl + 2) * sizeof(int), c->st));
   TaskInvArgs a;
   memset(&a, 0, sizeof(a));
   a.db = c->db;
@@ -1004,15 +1004,41 @@ static int dev_e_step(mb_context* c, int K, const mb_kernel* kern_k, const doubl
   if (big) {
     MB_TRY(big_tasks_inverse(&c->big, a, c->h_offs.data(), nullptr, c->lv_offs.data(), c->st, &c->launches));
   } else {
-    // the CTAs of a leaf wait for each other: the whole grid has to be resident at once
-    const int cap = c->sm_count * task_ctas_per_sm_any(c->db.nmax, c->db.D);
+    // Dealing of the (leaf, position) items to persistent CTAs (estep3.cu).  Default: static -- CTA b serves leaf b % nl,
+    // positions b / nl, b / nl + per, ...; the CTAs of a leaf wait for each other, so the whole grid has to be resident.
+    // MB_ESTEP_DYNAMIC: items pulled in order from a device counter (any grid size is safe, all CTA slots used); measured
+    // 6 % slower at C2 (1.31 vs 1.23 ms, same box): more CTAs per leaf queue up behind the leaf's ordered section.
+    int64_t cap = (int64_t)c->sm_count * task_ctas_per_sm_any(c->db.nmax, c->db.D);
+    if (cap > c->db.n_tasks) cap = c->db.n_tasks;
     int64_t longest = 1;
     for (int l = 0; l < nl; ++l) if (c->lv_offs[l + 1] - c->lv_offs[l] > longest) longest = c->lv_offs[l + 1] - c->lv_offs[l];
-    int per = cap / nl;
-    if (per < 1) per = 1;          // more leaves than resident CTAs: one CTA per leaf never waits
-    if (per > longest) per = (int)longest;
-    a.ctas_per_leaf = per;
-    LAUNCH(c, launch_task_inverse_any(a, nl * per, c->st));
+    a.leaf_max = (int)longest;
+    static const bool static_deal = getenv("MB_ESTEP_DYNAMIC") == nullptr;
+    int64_t per = cap / nl;
+    if (static_deal && per >= 1) {
+      if (per > longest) per = longest;
+      a.queue = nullptr;
+      a.leaf_max = (int)(((longest + per - 1) / per) * per);
+      LAUNCH(c, launch_task_inverse_any(a, (int)(nl * per), c->st));
+    } else {
+      a.queue = c->tickets.as<int>() + nl;
+      LAUNCH(c, launch_task_inverse_any(a, (int)cap, c->st));
+    }
+  }
+  MB_TRY(mark(1));
+  // inverse prior covariances on st2, enqueued AFTER the task kernel so that their host synchronisations (retry counts)
+  // are spent while the tasks are being factorised on st
+  for (int k = 0; k < K; ++k) {
+    LAUNCH(c, launch_dense_cov(kdk, hp_k_host + (size_t)k * kdk.n_hp, gridX, U, gridX, U, c->db.D, -1, 1,
+                               c->ws1.Kmat.as<double>(), U, 1, c->st2));
+    int r = 0;
+    int rc = dev_cholinv(c, c->ws1, c->ws1.Kmat.as<double>(), U, pen, c->st2, &r, nullptr, nullptr);
+    if (rc != 0) {   // the mean process is replicated: every rank fails here alike, nobody is left in a collective
+      cudaStreamSynchronize(c->st);
+      return rc;
+    }
+    if (r > max_r0) max_r0 = r;
+    CU(cudaMemcpyAsync(c->inv0.as<double>() + k * UU, c->ws1.A.p, UU * 8, cudaMemcpyDeviceToDevice, c->st2));
   }
   CU(cudaStreamSynchronize(c->st2));
   // [post_inv_k | weighted_k] = [inv_k | inv_k m_k] + tree over the leaves of all ranks
@@ -1022,7 +1048,11 @@ static int dev_e_step(mb_context* c, int K, const mb_kernel* kern_k, const doubl
   for (int k = 0; k < K; ++k)
     LAUNCH(c, launch_gemv(U, U, c->inv0.as<double>() + k * UU, U, m_k_dev + (size_t)k * U, nullptr, base + K * UU + (size_t)k * U, c->st));
   MB_TRY(c->post_inv.ensure((size_t)pstride * 8));
+  MB_TRY(mark(2));
   MB_TRY(leaf_reduce(c, c->leafbuf.as<double>(), pstride, pstride, base, c->post_inv.as<double>(), c->st));
+  // the per-task kernel adds upper triangles only (estep3.cu)
+  LAUNCH(c, launch_mirror_upper(c->post_inv.as<double>(), U, K, (int64_t)UU, c->st));
+  MB_TRY(mark(3));
   double* weighted = c->post_inv.as<double>() + K * UU;
   for (int k = 0; k < K; ++k) {
     int r = 0;
@@ -1034,9 +1064,20 @@ static int dev_e_step(mb_context* c, int K, const mb_kernel* kern_k, const doubl
                           post_mean + (size_t)k * U, c->st));
   }
   // task retry statistics: the largest count and the "never factored" flag are reduced on the device
+  MB_TRY(mark(4));
   LAUNCH(c, launch_retry_stats(c->retries.as<int32_t>(), c->db.n_tasks, c->tickets.as<int>(), c->st));
   MB_TRY(d2h(c->h_pin_i + 16, c->tickets.p, 2 * sizeof(int), c->st));
+  MB_TRY(mark(5));
   CU(cudaStreamSynchronize(c->st));
+  if (c->prof_on) {
+    // stream time of the segments: [4] memsets + task kernel, [5] idle until inv_0 is there (host wait) + base copy,
+    // [6] leaf reduction (+ all-reduce), [7] inverse of post_inv + mean, [8] retry statistics
+    for (int i = 0; i < 5; ++i) {
+      float ms = 0.f;
+      CU(cudaEventElapsedTime(&ms, c->ev_mark[i], c->ev_mark[i + 1]));
+      c->prof_phase[4 + i] += ms;
+    }
+  }
   int rc_tasks = 0;
   if (c->h_pin_i[17] != 0) { mb_set_error(__FILE__, __LINE__, "chol_inv_jitter: no positive-definite jitter found for a task"); rc_tasks = 1; }
   rc_tasks = ctx_agree(c, rc_tasks, c->st);
@@ -1913,9 +1954,9 @@ extern "C" int mb_profile_read_gaps(mb_context* c, double* out2) {
 }
 // Call AFTER mb_profile_read: host-clock milliseconds dev_em_step spent in the E step, the M step and the monitoring
 // (each ends with a synchronisation) and the device milliseconds of the persistent M-step kernel, since the last read
-extern "C" int mb_profile_read_phases(mb_context* c, double* out4) {
+extern "C" int mb_profile_read_phases(mb_context* c, double* out12) {
   MB_TRY(check_ctx(c));
-  for (int i = 0; i < 4; ++i) { out4[i] = c->prof_phase[i]; c->prof_phase[i] = 0.0; }
+  for (int i = 0; i < 12; ++i) { out12[i] = c->prof_phase[i]; c->prof_phase[i] = 0.0; }
   return 0;
 }
 // SM cycles the persistent M-step kernel of the LAST per-task M step spent in objective evaluations (out2[0]) and in

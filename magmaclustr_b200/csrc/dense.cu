@@ -171,6 +171,23 @@ __global__ void __launch_bounds__(256) k_reduce_tree(int64_t count, int n, const
   }
 }
 
+// lower triangle := mirror image of the upper one, for `nmat` row-major U x U matrices `stride` doubles apart
+__global__ void __launch_bounds__(256) k_mirror_upper(double* m, int U, int nmat, int64_t stride) {
+  const int64_t tot = (int64_t)nmat * U * U;
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < tot; e += (int64_t)gridDim.x * 256) {
+    const int k = (int)(e / ((int64_t)U * U));
+    const int64_t r = e - (int64_t)k * U * U;
+    const int i = (int)(r / U), j = (int)(r - (int64_t)i * U);
+    if (i > j) m[(int64_t)k * stride + r] = m[(int64_t)k * stride + (int64_t)j * U + i];
+  }
+}
+cudaError_t launch_mirror_upper(double* m, int U, int nmat, int64_t stride, cudaStream_t st) {
+  int64_t blocks = ((int64_t)nmat * U * U + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_mirror_upper<<<(unsigned)blocks, 256, 0, st>>>(m, U, nmat, stride);
+  return cudaGetLastError();
+}
+
 // out[b] = sum_i v[b + i*stride] for block b: the reference's sapply(...) %>% sum() / rowSums().
 // R accumulates in long double; here every thread keeps a Neumaier-compensated partial over a strided
 // subset and thread 0 combines the 256 (sum, compensation) pairs in index order, which gives the

@@ -4,11 +4,12 @@
 //
 // The reference adds the tasks one after the other (em-magma.R:39-46).  Here the GLOBAL task list is cut into a fixed number
 // of LEAVES (contiguous task ranges, api.cu:leaf_count -- fixed by the number of tasks and the grid size alone, not by the
-// number of GPUs, SMs or CTAs); every leaf owns one accumulator and receives its tasks IN TASK ORDER: the CTAs that share a
-// leaf factorise their tasks concurrently and take turns at the accumulator through a ticket counter.  The leaf sums are then
-// added in a fixed binary tree (dense.cu:k_reduce_tree).  Results are therefore bit-identical whatever the launch geometry
-// and however the leaves are dealt to GPUs; there are no FP64 atomics.
-// With one accumulator per leaf (<= 128 x 323 KB at U = 201) the read-modify-write traffic stays in L2.
+// number of GPUs, SMs or CTAs); every leaf owns one accumulator and receives its tasks IN TASK ORDER: persistent CTAs
+// pull (leaf, position) items from a device counter, factorise concurrently and take turns at the leaf's accumulator through a
+// ticket counter.  The leaf sums are then added in a fixed binary tree (dense.cu:k_reduce_tree).  Results are therefore
+// bit-identical whatever the launch geometry and however the leaves are dealt to GPUs.  The adds inside the ordered section
+// are red.global.add.f64 -- one addend per element and ticket, so the order of the floating-point sums is still fixed.
+// With one accumulator per leaf (<= 128 x 323 KB at U = 201) that traffic stays in L2.
 #include "tasks3.cuh"
 
 extern __shared__ double4 task3_smem_raw[];
@@ -28,22 +29,42 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_inverse
   const Sm3 s = carve3<N8C>((double*)task3_smem_raw, D);
   const Ln L;
   const int tid = threadIdx.x;
-  // accumulating launches: CTA -> (leaf, lane within the leaf); the CTAs of a leaf deal its tasks round-robin.
-  // list_kern_to_inv launches (no accumulators): plain grid-stride walk.
+  // accumulating launches: the CTAs pull work items from an atomic counter, item g = (leaf g % n_leaves, position
+  // g / n_leaves in that leaf) -- consecutive items go to different leaves, the tasks of one leaf are handed out in task
+  // order, and whoever holds position p waits (ticket) for position p - 1, which was handed out EARLIER to a CTA that is
+  // running: no deadlock whatever the grid size, and a CTA that meets a slow task (jitter retries) or a busy SM simply takes
+  // fewer items.  list_kern_to_inv launches (no accumulators): plain grid-stride walk.
   int leaf = 0;
-  int64_t t_first, t_end, t_step, leaf_t0 = 0;
-  if (a.part_inv) {
-    leaf = blockIdx.x % a.n_leaves;
-    leaf_t0 = a.leaf_offs[leaf];
-    t_first = leaf_t0 + blockIdx.x / a.n_leaves;
-    t_end = a.leaf_offs[leaf + 1];
-    t_step = a.ctas_per_leaf;
-  } else {
-    t_first = blockIdx.x; t_end = a.db.n_tasks; t_step = gridDim.x;
-  }
-  double* pinv = a.part_inv ? a.part_inv + (size_t)leaf * a.part_stride : nullptr;
-  double* pw = a.part_inv ? a.part_w + (size_t)leaf * a.part_stride : nullptr;
-  for (int64_t task = t_first; task < t_end; task += t_step) {
+  int64_t leaf_t0 = 0;
+  int64_t stride_task = a.part_inv ? 0 : (int64_t)blockIdx.x;
+  double* pinv = nullptr;
+  double* pw = nullptr;
+  for (;;) {
+    int64_t task;
+    if (a.part_inv) {
+      int g;
+      if (a.queue) {
+        if (tid == 0) s.flag[2] = atomicAdd(a.queue, 1);
+        __syncthreads();
+        g = s.flag[2];
+        __syncthreads();
+      } else {   // static dealing (grid = n_leaves * ctas_per_leaf, all resident): CTA -> leaf, its positions round-robin
+        g = (int)stride_task * (int)gridDim.x + (int)blockIdx.x;
+        ++stride_task;
+      }
+      if (g >= a.n_leaves * a.leaf_max) break;
+      leaf = g % a.n_leaves;
+      const int pos = g / a.n_leaves;
+      leaf_t0 = a.leaf_offs[leaf];
+      if (pos >= (int)(a.leaf_offs[leaf + 1] - leaf_t0)) continue;
+      task = leaf_t0 + pos;
+      pinv = a.part_inv + (size_t)leaf * a.part_stride;
+      pw = a.part_w + (size_t)leaf * a.part_stride;
+    } else {
+      task = stride_task;
+      if (task >= a.db.n_tasks) break;
+      stride_task += gridDim.x;
+    }
     const int64_t row0 = a.db.offs[task];
     const int n = (int)(a.db.offs[task + 1] - row0);
     const int n8 = t3_n8(n), np = 8 * n8;
@@ -62,24 +83,53 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_inverse
     if (pinv) {
       double* al = s.vout;
       gemv3<N8C, 1>(s, n8, s.yv, al, L);
+      // The leaf's accumulator lives in L2; the ticket admits one task at a time and the grid positions of one task are
+      // distinct, so every accumulator element receives at most one addend per ticket: a fire-and-forget reduction
+      // (red.global.add.f64 -- no load round trip) adds exactly what a read-modify-write would, in the same order.
+      // Only the upper triangle is added (half the L2 reductions -- their rate is what bounds this kernel); the lower
+      // triangle of the final sum is its mirror image (api.cu: launch_mirror_upper), bit for bit what adding it would give.
+      // Values and target offsets of (the first) 32 elements per thread are prepared BEFORE the ticket wait, so that the
+      // ordered section -- a chain through all tasks of the leaf -- is at most 32 back-to-back reductions per thread, the
+      // fence that completes them, and the hand-over.
+      constexpr int CH = 32;
+      const int nn = n * n;
+      double xv[CH];
+      unsigned off[CH];
+      auto prep = [&](int base) {
+#pragma unroll
+        for (int q = 0; q < CH; ++q) {
+          const int e = base + tid + q * T3_THREADS;
+          off[q] = 0xffffffffu;
+          xv[q] = 0.0;
+          if (e < nn) {
+            const int i = e / n, j = e - i * n;
+            if (i <= j) {   // upper triangle only: A and the sums are exactly symmetric, the host mirrors the final sum
+              const unsigned gi = (unsigned)s.gi[i], gj = (unsigned)s.gi[j];
+              xv[q] = bad ? NAN : symA_at<N8C>(s.T1, i, j);
+              off[q] = (gi <= gj) ? gi * (unsigned)U + gj : gj * (unsigned)U + gi;
+            }
+          }
+        }
+      };
+      prep(0);
       // ---- ordered section: wait for the previous task of this leaf
       const int ticket = (int)(task - leaf_t0);
       if (tid == 0) {
-        while (ld_acquire_gpu(a.tickets + leaf) != ticket) __nanosleep(100);
+        while (ld_acquire_gpu(a.tickets + leaf) != ticket) __nanosleep(32);
       }
       __syncthreads();
+      for (int base = 0; base < nn; base += CH * T3_THREADS) {
+        if (base) prep(base);
+        for (int k = 0; k < K; ++k) {
+          const double tau = a.tau ? a.tau[task * K + k] : 1.0;
+          double* pk = pinv + (size_t)k * U * U;
+#pragma unroll
+          for (int q = 0; q < CH; ++q)
+            if (off[q] != 0xffffffffu) atomicAdd(pk + off[q], a.tau ? tau * xv[q] : xv[q]);
+        }
+      }
       for (int k = 0; k < K; ++k) {
         const double tau = a.tau ? a.tau[task * K + k] : 1.0;
-        double* pk = pinv + (size_t)k * U * U;
-        // The leaf's accumulator lives in L2; the ticket admits one task at a time and the grid positions of one task are
-        // distinct, so every accumulator element receives at most one addend per ticket: a fire-and-forget reduction
-        // (red.global.add.f64 -- no load round trip on the ordered section) adds exactly what a read-modify-write would,
-        // in the same order.  The fence below completes them before the ticket moves on.
-        for (int e = tid; e < n * n; e += T3_THREADS) {
-          const int i = e / n, j = e - i * n;
-          const double x = bad ? NAN : symA_at<N8C>(s.T1, i, j);
-          atomicAdd(pk + (size_t)s.gi[i] * U + s.gi[j], a.tau ? tau * x : x);
-        }
         double* wk = pw + (size_t)k * U;
         for (int i = tid; i < n; i += T3_THREADS) {
           const double v = bad ? NAN : al[i];
@@ -106,8 +156,7 @@ static cudaError_t launch_inv3_t(const TaskInvArgs& a, int n_ctas, cudaStream_t 
   return cudaGetLastError();
 }
 
-// n_ctas: with accumulators (a.part_inv) it must equal a.n_leaves * a.ctas_per_leaf and, when ctas_per_leaf > 1, fit the
-// device at once (the CTAs of a leaf wait for each other): see task3_max_ctas_per_sm().
+// n_ctas: any positive count; with accumulators (a.part_inv) the resident capacity (task3_max_ctas_per_sm()) is the useful one.
 cudaError_t launch_task_inverse3(TaskInvArgs a, int n_ctas, cudaStream_t st) {
   const bool small = a.db.nmax <= 64, d1 = a.db.D == 1;
   if (is_se(a.kd)) {

@@ -72,7 +72,8 @@ struct TaskInvArgs {       // E step / list_kern_to_inv
   int64_t part_stride;       // doubles between the accumulators of consecutive leaves
   const int64_t* leaf_offs;  // device, n_leaves + 1: first task of every leaf
   int n_leaves;
-  int ctas_per_leaf;         // CTAs that share one leaf (ticket-ordered)
+  int leaf_max;              // tasks in the longest leaf
+  int* queue;                // device, zero-initialised work counter: item g = (leaf g % n_leaves, position g / n_leaves)
   int* tickets;              // device, n_leaves, zero-initialised: tasks of the leaf already added
   double* inv_out;           // optional: all inverses, block t at inv_offs[t], column-major
   const int64_t* inv_offs;

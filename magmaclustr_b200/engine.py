@@ -276,11 +276,13 @@ class Context:
         check(L.lib().mb_profile_read_gaps(self._h, ptr(gaps)))
         out = np.zeros(3)
         check(L.lib().mb_profile_read(self._h, ptr(out)))
-        ph = np.zeros(4)
+        ph = np.zeros(12)
         check(L.lib().mb_profile_read_phases(self._h, ptr(ph)))
         return {"ms": out[0], "launches": int(out[1]), "evals": int(out[2]), "round_gap_ms": gaps[0],
                 "other_ms": gaps[1], "e_step_ms": ph[0], "m_step_ms": ph[1], "monitoring_ms": ph[2],
-                "persistent_kernel_ms": ph[3]}
+                "persistent_kernel_ms": ph[3],
+                "e_step_segments_ms": {"memset_and_task_kernel": ph[4], "wait_for_inv_0": ph[5], "leaf_reduction": ph[6],
+                                       "post_inverse_and_mean": ph[7], "retry_stats": ph[8]}}
 
     def mstep_cycles(self):
         out = np.zeros(2)

@@ -81,6 +81,44 @@ def _simu_db(M, N, K, common_input, seed, pool):
     return df, {"clusters": clusters, "means": means, "pool": pool}
 
 
+def simu_db_spectral(M=10, N=10, common_input=False, seed=0, pool=None, n_features=256):
+    """Same table, same hyper-parameter ranges and the same model as `simu_db` (one mean process, SE kernels), but every
+    Gaussian-process draw is a random-Fourier-feature sum  sqrt(2 e^v / F) sum_j cos(w_j x + b_j),  w_j ~ N(0, e^{-l}),
+    b_j ~ U(0, 2 pi)  -- the spectral representation of the SE kernel -- instead of a Cholesky factor times a normal vector.
+    O(N F) per task instead of O(N^3): what makes config 4 (256 tasks on a 4096-point grid) generable in seconds on the
+    benchmark box.  Element-wise numpy only, so every rank generates the same bits."""
+    rng = np.random.default_rng(seed)
+    if pool is None:
+        pool = np.round(np.arange(-1.0, 1.0 + 1e-9, 0.01), 2)
+    pool = np.asarray(pool, dtype=np.float64)
+
+    def gp_draw(x, v, l):
+        w = rng.standard_normal(n_features) * math.exp(-0.5 * l)
+        b = rng.uniform(0.0, 2.0 * math.pi, n_features)
+        out = np.zeros(len(x))
+        for j in range(n_features):          # fixed summation order
+            out += np.cos(w[j] * x + b[j])
+        return math.sqrt(2.0 * math.exp(v) / n_features) * out
+
+    a, b = _draw(rng, -50, 50), _draw(rng, -5, 5)
+    v0, l0 = _draw(rng, 0, math.log(3)), _draw(rng, math.log(1 / 300), math.log(1 / 200))
+    mean = a + b * pool + gp_draw(pool, v0, l0)
+    v = _draw(rng, 0, math.log(1.5), M)
+    l = _draw(rng, math.log(1 / 300), math.log(1 / 200), M)
+    s = _draw(rng, 0, 0.2, M)
+    shared_idx = np.sort(rng.choice(len(pool), size=N, replace=False)) if common_input else None
+    ids, xs, ys = [], [], []
+    for i in range(M):
+        idx = shared_idx if common_input else np.sort(rng.choice(len(pool), size=N, replace=False))
+        x = pool[idx]
+        y = mean[idx] + gp_draw(x, v[i], l[i]) + math.sqrt(s[i]) * rng.standard_normal(N)
+        ids += [str(i + 1)] * N
+        xs.append(x)
+        ys.append(y)
+    df = pd.DataFrame({"ID": ids, "Input": np.concatenate(xs), "Output": np.concatenate(ys)})
+    return df, {"means": [mean], "pool": pool}
+
+
 def ini_hp(kern, ids, shared, noise, seed):
     """Random initial hyper-parameters in hp()'s ranges, as a DataFrame with an ID
     column (one row per id; identical rows when `shared`)."""
