@@ -171,6 +171,39 @@ __global__ void __launch_bounds__(256) k_reduce_tree(int64_t count, int n, const
   }
 }
 
+// The same tree with eight threads per element: warp w of a 256-thread block sums the aligned subtree of 2^SLOG partials
+// number w (a node of the tree above) for 32 consecutive elements -- unit-stride 256-byte loads -- and the first warp adds the
+// eight nodes in tree order.  Same bits as k_reduce_tree; eight times the loads in flight (the leaf accumulators sit in L2,
+// one thread per element left the kernel latency bound: 38 -> 8.7 us for 128 x 323 KB = 4.8 TB/s).
+template <int SLOG>
+__global__ void __launch_bounds__(256) k_reduce_tree8(int64_t count, int n, const double* __restrict__ base,
+                                                      const double* __restrict__ part, int64_t part_stride,
+                                                      double* __restrict__ out) {
+  __shared__ double sv[8][32];
+  __shared__ int sh[8][32];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t e = (int64_t)blockIdx.x * 32 + lane;
+  double v = 0.0;
+  bool has = false;
+  if (e < count) has = tree_sum<SLOG>(part + e, part_stride, w << SLOG, n, v);
+  sv[w][lane] = v;
+  sh[w][lane] = has ? 1 : 0;
+  __syncthreads();
+  if (w == 0 && e < count) {
+    double a[8];
+    bool h[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { a[q] = sv[q][lane]; h[q] = sh[q][lane] != 0; }
+#pragma unroll
+    for (int step = 1; step < 8; step <<= 1)
+#pragma unroll
+      for (int q = 0; q < 8; q += 2 * step)
+        if (h[q + step]) { a[q] = a[q] + a[q + step]; }   // a missing right child passes the left one through
+    const double t = h[0] ? a[0] : 0.0;
+    out[e] = base ? base[e] + t : t;
+  }
+}
+
 // lower triangle := mirror image of the upper one, for `nmat` row-major U x U matrices `stride` doubles apart
 __global__ void __launch_bounds__(256) k_mirror_upper(double* m, int U, int nmat, int64_t stride) {
   const int64_t tot = (int64_t)nmat * U * U;
@@ -354,6 +387,20 @@ cudaError_t launch_retry_stats(const int32_t* retries, int64_t n, int* out2, cud
 cudaError_t launch_reduce_tree(int64_t count, int nparts, const double* base, const double* part, int64_t part_stride,
                                double* out, cudaStream_t st) {
   if (nparts < 1 || nparts > (1 << RT_MAX_LOG)) return cudaErrorInvalidValue;
+  if (count >= 4096 && nparts >= 8 && nparts <= 256) {
+    int slog = 0;
+    while ((8 << slog) < nparts) ++slog;          // eight subtrees of 2^slog partials cover all of them
+    const unsigned nb = (unsigned)((count + 31) / 32);
+    switch (slog) {
+      case 0: k_reduce_tree8<0><<<nb, 256, 0, st>>>(count, nparts, base, part, part_stride, out); break;
+      case 1: k_reduce_tree8<1><<<nb, 256, 0, st>>>(count, nparts, base, part, part_stride, out); break;
+      case 2: k_reduce_tree8<2><<<nb, 256, 0, st>>>(count, nparts, base, part, part_stride, out); break;
+      case 3: k_reduce_tree8<3><<<nb, 256, 0, st>>>(count, nparts, base, part, part_stride, out); break;
+      case 4: k_reduce_tree8<4><<<nb, 256, 0, st>>>(count, nparts, base, part, part_stride, out); break;
+      default: k_reduce_tree8<5><<<nb, 256, 0, st>>>(count, nparts, base, part, part_stride, out); break;
+    }
+    return cudaGetLastError();
+  }
   int64_t blocks = (count + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   k_reduce_tree<<<(unsigned)blocks, 256, 0, st>>>(count, nparts, base, part, part_stride, out);

@@ -322,11 +322,28 @@ class Context:
         check(L.lib().mb_bench_hbm(self._h, int(what), C.byref(ki), int(reps), ptr(ms), ptr(by)))
         return float(ms[0]), float(by[0])
 
+    @staticmethod
+    def _grid_guard(n_grid, grid_guard):
+        """The reference refuses hyper-posterior grids above 5000 points and warns above 2000 (R/prediction.R:583-594,
+        same guard in hyperposterior_clust): an O(n^3) inversion on its CPU path.  Mirrored here with the same thresholds
+        and wording; grid_guard=False lifts it (BASELINE config 5 asks for a 10 000-point grid, 0.06 s per inversion here)."""
+        if not grid_guard:
+            return
+        if n_grid > 5000:
+            raise ValueError("The hyper-posterior grid has %d points. Inverting a covariance of this size is O(n^3) and "
+                             "would be prohibitively slow (> 5000 points, typically > 10s). Please provide a coarser "
+                             "'grid_inputs' (recall it is replicated across every output)." % n_grid)
+        if n_grid > 2000:
+            import warnings
+            warnings.warn("The hyper-posterior grid has %d points; the O(n^3) inversion may be slow. Consider a coarser "
+                          "'grid_inputs'." % n_grid)
+
     def hyperposterior(self, k0, hp_0, ki, hp_i, grid_X, grid_index, m_0, pen_diag=1e-10,
-                       shared=False):
+                       shared=False, grid_guard=True):
         gX = f64(np.atleast_2d(np.asarray(grid_X, dtype=np.float64).T).T)
         gi = np.ascontiguousarray(grid_index, dtype=np.int32)
         u = gX.shape[0]
+        self._grid_guard(u, grid_guard)
         pm = np.zeros(u)
         pc = np.zeros((u, u))
         check(L.lib().mb_hyperposterior(self._h, C.byref(k0), ptr(f64(hp_0)), C.byref(ki),
@@ -459,11 +476,12 @@ class Context:
         return out.value
 
     def hyperposterior_clust(self, K, kk, hp_k, ki, hp_i, grid_X, grid_index, m_k, tau, pen_diag=1e-10, shared=False,
-                             host_out=True):
+                             host_out=True, grid_guard=True):
         """host_out=False (after hyperpost_keep(True)): the K x U x U result only stays on the device."""
         gX = f64(np.atleast_2d(np.asarray(grid_X, dtype=np.float64).T).T)
         gi = np.ascontiguousarray(grid_index, dtype=np.int32)
         u = gX.shape[0]
+        self._grid_guard(u, grid_guard)
         pm = np.zeros((K, u)) if host_out else None
         pc = np.zeros((K, u, u)) if host_out else None
         mk = f64(np.broadcast_to(np.asarray(m_k, dtype=np.float64).reshape(K, -1), (K, u)))

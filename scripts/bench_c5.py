@@ -59,10 +59,10 @@ out = {"config": "C5: pred_magmaclust, grid %dx%d = %d points, %d new tasks x %d
 ctx.upload_dataset(train.offs, train.X, train.y, train.grid_index, train.grid_X)
 ctx.hyperpost_keep(True)
 t0 = time.perf_counter()
-ctx.hyperposterior_clust(KC, kk, hp_k, ki, hp_i_tr, train.grid_X, train.grid_index, np.zeros((KC, 1)), mix, host_out=False)
+ctx.hyperposterior_clust(KC, kk, hp_k, ki, hp_i_tr, train.grid_X, train.grid_index, np.zeros((KC, 1)), mix, host_out=False, grid_guard=False)
 out["hyperposterior_clust_s"] = time.perf_counter() - t0
 t0 = time.perf_counter()
-ctx.hyperposterior_clust(KC, kk, hp_k, ki, hp_i_tr, train.grid_X, train.grid_index, np.zeros((KC, 1)), mix, host_out=False)
+ctx.hyperposterior_clust(KC, kk, hp_k, ki, hp_i_tr, train.grid_X, train.grid_index, np.zeros((KC, 1)), mix, host_out=False, grid_guard=False)
 out["hyperposterior_clust_warm_s"] = time.perf_counter() - t0
 out["hyperposterior_flops"] = 2.0 * KC * float(G) ** 3      # 2 K chol_inv_jitter of U x U at n^3 each
 out["hyperposterior_tflops_warm"] = out["hyperposterior_flops"] / out["hyperposterior_clust_warm_s"] / 1e12

@@ -235,7 +235,13 @@ def test_c5_hyperposterior_clust_on_2d_subgrid(ctx):
     U = len(prep.grid_keys)
     assert [k.decode() for k in prep.grid_keys] == ohyp["keys"] and U >= 2000
     ctx.upload_dataset(prep.offs, prep.X, prep.y, prep.grid_index, prep.grid_X)
-    pm, pc = ctx.hyperposterior_clust(KC, kk, hp_k, ki, hpi, prep.grid_X, prep.grid_index, np.zeros((KC, U)), mix)
+    if U > 2000:
+        with pytest.warns(UserWarning, match="hyper-posterior grid"):      # R/prediction.R:590-593
+            pm, pc = ctx.hyperposterior_clust(KC, kk, hp_k, ki, hpi, prep.grid_X, prep.grid_index, np.zeros((KC, U)), mix)
+    else:
+        pm, pc = ctx.hyperposterior_clust(KC, kk, hp_k, ki, hpi, prep.grid_X, prep.grid_index, np.zeros((KC, U)), mix)
+    with pytest.raises(ValueError, match="5000 points"):                   # R/prediction.R:584-589, before any GPU work
+        ctx.hyperposterior_clust(KC, kk, hp_k, ki, hpi, np.zeros((5001, 2)), np.zeros(1, dtype=np.int32), np.zeros((KC, 5001)), mix)
     rng2 = np.random.default_rng(6)
     pert = [dict(zip(L.hp_names(kk), ulp_perturb(hp_k[k], rng2))) for k in range(KC)]
     h2 = OC.hyperposterior_clust(odb, pert, o_hpi, "SE", kern_i, [0.0] * KC, mix, sub)

@@ -85,7 +85,7 @@ def test_c5_full_size_sampled_predictions(ctx):
     ctx.upload_dataset(train.offs, train.X, train.y, train.grid_index, train.grid_X)
     ctx.hyperpost_keep(True)
     pm, pc = ctx.hyperposterior_clust(KC, kk, hp_k, ki, np.tile(hp_i_row, (train.n_tasks, 1)), train.grid_X,
-                                      train.grid_index, np.zeros((KC, 1)), mix)
+                                      train.grid_index, np.zeros((KC, 1)), mix, grid_guard=False)   # 10 000 points
     ctx.hyperpost_keep(False)
     assert np.all(np.isfinite(pm)) and all(np.array_equal(pc[k], pc[k].T) for k in range(KC))
     new = make_tasks(T, NOBS, "nw", rng.integers(0, KC, size=T))
