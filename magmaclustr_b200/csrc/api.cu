@@ -1001,19 +1001,15 @@ static int dev_e_step(mb_context* c, int K, const mb_kernel* kern_k, const doubl
   a.part_inv = c->leafbuf.as<double>(); a.part_w = c->leafbuf.as<double>() + K * UU; a.part_stride = pstride;
   a.leaf_offs = c->d_lv_offs.as<int64_t>(); a.n_leaves = nl; a.tickets = c->tickets.as<int>();
   a.retries = c->retries.as<int32_t>();
+  { static const int diag = getenv("MB_ESTEP_DIAG") ? atoi(getenv("MB_ESTEP_DIAG")) : 0; a.diag_skip = diag; }   // timing decomposition only
   if (big) {
     MB_TRY(big_tasks_inverse(&c->big, a, c->h_offs.data(), nullptr, c->lv_offs.data(), c->st, &c->launches));
   } else {
-    // Dealing of the (leaf, position) items to persistent CTAs (estep3.cu).  Default: static -- CTA b serves leaf b % nl,
-    // positions b / nl, b / nl + per, ...; the CTAs of a leaf wait for each other, so the whole grid has to be resident.
-    // MB_ESTEP_DYNAMIC: items pulled in order from a device counter (any grid size is safe, all CTA slots used); measured
-    // 6 % slower at C2 (1.31 vs 1.23 ms, same box): more CTAs per leaf queue up behind the leaf's ordered section.
-    int64_t cap = (int64_t)c->sm_count * task_ctas_per_sm_any(c->db.nmax, c->db.D);
-    if (cap > c->db.n_tasks) cap = c->db.n_tasks;
-    int64_t longest = 1;
-    for (int l = 0; l < nl; ++l) if (c->lv_offs[l + 1] - c->lv_offs[l] > longest) longest = c->lv_offs[l + 1] - c->lv_offs[l];
-    a.leaf_max = (int)longest;
-    static const bool static_deal = getenv("MB_ESTEP_DYNAMIC") == nullptr;
+    // Dealing of the (leaf, position) items to persistent CTAs (estep3.cu).  Default: items pulled in order from a device
+    // counter -- any grid size is safe and every CTA slot is used.  MB_ESTEP_STATIC: CTA b serves leaf b % nl, positions
+    // b / nl, b / nl + per, ...; the CTAs of a leaf wait for each other, so the whole grid has to be resident.  Same bits
+    // and, at C2, the same time (0.83 ms) either way.
+    static const bool static_deal = getenv("MB_ESTEP_STATIC") != nullptr;
     int64_t per = cap / nl;
     if (static_deal && per >= 1) {
       if (per > longest) per = longest;

@@ -387,7 +387,7 @@ cudaError_t launch_retry_stats(const int32_t* retries, int64_t n, int* out2, cud
 cudaError_t launch_reduce_tree(int64_t count, int nparts, const double* base, const double* part, int64_t part_stride,
                                double* out, cudaStream_t st) {
   if (nparts < 1 || nparts > (1 << RT_MAX_LOG)) return cudaErrorInvalidValue;
-  if (count >= 4096 && nparts >= 8 && nparts <= 256) {
+  if (nparts >= 8 && nparts <= 256) {
     int slog = 0;
     while ((8 << slog) < nparts) ++slog;          // eight subtrees of 2^slog partials cover all of them
     const unsigned nb = (unsigned)((count + 31) / 32);

@@ -88,25 +88,35 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_inverse
       // (red.global.add.f64 -- no load round trip) adds exactly what a read-modify-write would, in the same order.
       // Only the upper triangle is added (half the L2 reductions -- their rate is what bounds this kernel); the lower
       // triangle of the final sum is its mirror image (api.cu: launch_mirror_upper), bit for bit what adding it would give.
-      // Values and target offsets of (the first) 32 elements per thread are prepared BEFORE the ticket wait, so that the
-      // ordered section -- a chain through all tasks of the leaf -- is at most 32 back-to-back reductions per thread, the
-      // fence that completes them, and the hand-over.
-      constexpr int CH = 32;
-      const int nn = n * n;
-      double xv[CH];
-      unsigned off[CH];
+      // Values and target offsets are prepared BEFORE the ticket wait, tile by tile in the fragment layout the inverse
+      // already sits in (one 16-byte shared-memory load per tile and lane, no index arithmetic beyond the job table), nine
+      // tiles per warp and pass -- the 36 upper tiles of a 64-point task in one pass: the ordered section, a chain through
+      // all tasks of the leaf, is at most 18 back-to-back reductions per thread, the fence that completes them, and the
+      // hand-over.
+      constexpr int TPW = 9;
+      const int ntri = t3_ntri(n8);
+      double xv[2 * TPW];
+      unsigned off[2 * TPW];
       auto prep = [&](int base) {
 #pragma unroll
-        for (int q = 0; q < CH; ++q) {
-          const int e = base + tid + q * T3_THREADS;
-          off[q] = 0xffffffffu;
-          xv[q] = 0.0;
-          if (e < nn) {
-            const int i = e / n, j = e - i * n;
-            if (i <= j) {   // upper triangle only: A and the sums are exactly symmetric, the host mirrors the final sum
-              const unsigned gi = (unsigned)s.gi[i], gj = (unsigned)s.gi[j];
-              xv[q] = bad ? NAN : symA_at<N8C>(s.T1, i, j);
-              off[q] = (gi <= gj) ? gi * (unsigned)U + gj : gj * (unsigned)U + gi;
+        for (int u = 0; u < TPW; ++u) {
+          const int idx = base + L.warp + NW3 * u;
+          off[2 * u] = 0xffffffffu; off[2 * u + 1] = 0xffffffffu;
+          xv[2 * u] = 0.0; xv[2 * u + 1] = 0.0;
+          if (idx < ntri) {
+            const int e = s.tab[idx], i = (e >> 4) & 15, j = e & 15;
+            const int r = 8 * i + L.g, c = 8 * j + 2 * L.t;
+            const double2 av = *reinterpret_cast<const double2*>(s.T1 + (size_t)(e >> 8) * 64 + L.o_c);
+            if (r < n) {
+              const unsigned gr = (unsigned)s.gi[r];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                if (c + h < n && c + h >= r) {   // upper triangle, diagonal included
+                  const unsigned gc = (unsigned)s.gi[c + h];
+                  xv[2 * u + h] = bad ? NAN : (h ? av.y : av.x);
+                  off[2 * u + h] = (gr <= gc) ? gr * (unsigned)U + gc : gc * (unsigned)U + gr;
+                }
+              }
             }
           }
         }
@@ -114,18 +124,18 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_inverse
       prep(0);
       // ---- ordered section: wait for the previous task of this leaf
       const int ticket = (int)(task - leaf_t0);
-      if (tid == 0) {
+      if (tid == 0 && !(a.diag_skip & 1)) {
         while (ld_acquire_gpu(a.tickets + leaf) != ticket) __nanosleep(32);
       }
       __syncthreads();
-      for (int base = 0; base < nn; base += CH * T3_THREADS) {
+      for (int base = 0; base < ntri; base += NW3 * TPW) {
         if (base) prep(base);
         for (int k = 0; k < K; ++k) {
           const double tau = a.tau ? a.tau[task * K + k] : 1.0;
           double* pk = pinv + (size_t)k * U * U;
 #pragma unroll
-          for (int q = 0; q < CH; ++q)
-            if (off[q] != 0xffffffffu) atomicAdd(pk + off[q], a.tau ? tau * xv[q] : xv[q]);
+          for (int q = 0; q < 2 * TPW; ++q)
+            if (off[q] != 0xffffffffu && !(a.diag_skip & 2)) atomicAdd(pk + off[q], a.tau ? tau * xv[q] : xv[q]);
         }
       }
       for (int k = 0; k < K; ++k) {

@@ -79,6 +79,7 @@ struct TaskInvArgs {       // E step / list_kern_to_inv
   const int64_t* inv_offs;
   int32_t* retries;
   int ld;
+  int diag_skip;             // diagnostics only (MB_ESTEP_DIAG): 1 = no ticket ordering, 2 = no accumulation (timing decomposition)
 };
 
 struct TaskPredArgs {      // pred_magma(clust) batched over the resident (new) tasks
