@@ -1009,6 +1009,11 @@ static int dev_e_step(mb_context* c, int K, const mb_kernel* kern_k, const doubl
     // counter -- any grid size is safe and every CTA slot is used.  MB_ESTEP_STATIC: CTA b serves leaf b % nl, positions
     // b / nl, b / nl + per, ...; the CTAs of a leaf wait for each other, so the whole grid has to be resident.  Same bits
     // and, at C2, the same time (0.83 ms) either way.
+    int64_t cap = (int64_t)c->sm_count * task_ctas_per_sm_any(c->db.nmax, c->db.D);
+    if (cap > c->db.n_tasks) cap = c->db.n_tasks;
+    int64_t longest = 1;
+    for (int l = 0; l < nl; ++l) if (c->lv_offs[l + 1] - c->lv_offs[l] > longest) longest = c->lv_offs[l + 1] - c->lv_offs[l];
+    a.leaf_max = (int)longest;
     static const bool static_deal = getenv("MB_ESTEP_STATIC") != nullptr;
     int64_t per = cap / nl;
     if (static_deal && per >= 1) {
