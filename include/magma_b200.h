@@ -74,7 +74,10 @@ const char* mb_kernel_hp_name(const mb_kernel* k, int p);
 int64_t mb_launch_count(mb_context* ctx);
 /* tuning / diagnostic switches of one context: "fused_below" (MB_FUSED_BELOW), "reserve_sms" (MB_RESERVE_SMS),
  * "dense_split" (0 = MB_DENSE_NOSPLIT), "logdet_chol" (0 = the reference's LU log-determinant, R/likelihoods.R:37-41,
- * like MB_LOGDET=lu; 1 = read off the Cholesky diagonal).  The environment variables are read once at mb_create. */
+ * like MB_LOGDET=lu; 1 = read off the Cholesky diagonal), "monitor_recompute" (MB_MONITOR_RECOMPUTE: 1 = mb_em_step* /
+ * mb_train_magma evaluate logL_monitoring from scratch; 0, the default = the per-task and mean-process values
+ * logL_GP_mod(new HPs) are taken from the M step's optimisers, which ended on exactly those values -- same numbers, one
+ * all-task launch less per EM iteration).  The environment variables are read once at mb_create. */
 int mb_set_option(mb_context* ctx, const char* name, int64_t value);
 
 /* optional sum-all-reduce over ranks of `count` doubles in DEVICE memory, called on the

@@ -101,7 +101,7 @@ cudaError_t launch_lbfgsb_advance(LbfgsbState* st, int64_t m, int n, const doubl
                                   const double* g, int* n_active, cudaStream_t s);
 cudaError_t launch_lbfgsb_mask(LbfgsbState* st, int64_t m, const int32_t* skip, cudaStream_t s);
 cudaError_t launch_lbfgsb_export(const LbfgsbState* st, int64_t m, int n, double* x,
-                                 int64_t x_stride, int* fail, int* nfgv, cudaStream_t s);
+                                 int64_t x_stride, int* fail, int* nfgv, double* fval, cudaStream_t s);
 
 // ---- errors -------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -190,6 +190,11 @@ struct mb_context {
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_single = nullptr;
   cudaEvent_t ev_ring[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_cp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // after a per-task M step of train_magma: f_t holds logL_GP_mod of every task at its new HPs and m_step_f0 the mean
+  // process's value at the new hp_0 -- exactly what logL_monitoring evaluates next (same functions, same hyper-posterior)
+  bool mstep_values_valid = false;
+  double m_step_f0 = 0.0;
+  bool monitor_recompute = false;   // MB_MONITOR_RECOMPUTE / "monitor_recompute": logL_monitoring re-evaluates everything
   bool prof_on = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
   size_t prof_used = 0;
@@ -504,6 +509,7 @@ extern "C" int mb_create(mb_context** out, int device) {
   const char* env = getenv("MB_LOGDET");
   c->logdet_chol = (env && env[0] == 'l' && env[1] == 'u') ? 0 : 1;
   if (const char* e = getenv("MB_FUSED_BELOW")) c->fused_below = atoll(e);
+  if (getenv("MB_MONITOR_RECOMPUTE")) c->monitor_recompute = true;
   if (const char* e = getenv("MB_RESERVE_SMS")) { c->reserve_sms = atoi(e); if (c->reserve_sms < 0) c->reserve_sms = 0; if (c->reserve_sms > c->sm_count / 2) c->reserve_sms = c->sm_count / 2; }
   c->single_blocking = getenv("MB_SINGLE_BLOCKING") != nullptr;
   c->split_lauum = getenv("MB_DENSE_NOSPLIT") == nullptr;
@@ -554,6 +560,7 @@ extern "C" int mb_set_option(mb_context* c, const char* name, int64_t value) {
   else if (n == "reserve_sms") c->reserve_sms = (int)(value < 0 ? 0 : (value > c->sm_count / 2 ? c->sm_count / 2 : value));   // MB_RESERVE_SMS
   else if (n == "dense_split") c->split_lauum = value != 0;       // MB_DENSE_NOSPLIT (inverted)
   else if (n == "logdet_chol") c->logdet_chol = value != 0;       // MB_LOGDET=lu <-> 0
+  else if (n == "monitor_recompute") c->monitor_recompute = value != 0;   // MB_MONITOR_RECOMPUTE
   else MB_FAIL(-1, "unknown option");
   return 0;
 }
@@ -1291,7 +1298,9 @@ static int optimise(mb_context* c, std::vector<SingleProblem>& singles, bool tas
   if (tasks_on) {
     MB_TRY(c->fails.ensure(M * 4));
     MB_TRY(c->nfgv.ensure(M * 4));
-    LAUNCH(c, launch_lbfgsb_export(c->lb.as<LbfgsbState>(), M, P_i, hp_i_dev, P_i, c->fails.as<int>(), c->nfgv.as<int>(), c->st));
+    // a.f <- the objective at the final iterate of every task (what a re-evaluation at the exported HPs would return)
+    LAUNCH(c, launch_lbfgsb_export(c->lb.as<LbfgsbState>(), M, P_i, hp_i_dev, P_i, c->fails.as<int>(), c->nfgv.as<int>(),
+                                   skip_dev ? nullptr : a.f, c->st));
     std::vector<int> hf(M), hn(M);
     MB_TRY(d2h(hf.data(), c->fails.p, M * 4, c->st));
     MB_TRY(d2h(hn.data(), c->nfgv.p, M * 4, c->st));
@@ -1672,8 +1681,11 @@ static int dev_m_step(mb_context* c, const mb_kernel* kern_0, double* hp_0, cons
   lb_init(&sp.s, kd0.n_hp, hp_0, 1e13, 0.0, 25);
   TaskObjArgs a = make_obj_args(c, kdi, hp_i_dev, kdi.n_hp, TK_OBJ_MOD, 1, pen, 1, pm_dev, pc_dev, nullptr,
                                 c->f_t.as<double>(), c->g_t.as<double>());
+  c->mstep_values_valid = false;
   if (!shared_hp) {
     MB_TRY(optimise(c, singles, true, a, hp_i_dev, kdi.n_hp, pen, stats));
+    c->mstep_values_valid = sp.evals > 0;
+    c->m_step_f0 = sp.s.f;
   } else {
     MB_TRY(optimise(c, singles, false, a, hp_i_dev, kdi.n_hp, pen, stats));
     // one optimisation of the summed objective (em-magma.R:172-196), HPs of the first task
@@ -1701,18 +1713,24 @@ static int dev_m_step(mb_context* c, const mb_kernel* kern_0, double* hp_0, cons
   return 0;
 }
 
+// reuse_m_step: the caller has just run the per-task M step on the SAME hyper-posterior and passes its results on: the
+// values logL_GP_mod(hp_i_new) and logL_GP_mod(hp_0_new) that likelihoods.R:262-300 evaluates again are the objective values
+// the optimisers ended with (lbfgsb.h keeps (x, f) consistent on every exit), so they are summed as they are instead of
+// being recomputed -- same numbers, one all-task launch and one union-grid evaluation less per EM iteration.
 static int dev_logL_monitoring(mb_context* c, const mb_kernel* kern_0, const double* hp_0,
                                const mb_kernel* kern_i, const double* hp_i_dev, int64_t stride,
                                const double* m0_dev, const double* pm_dev, const double* pc_dev,
-                               double pen, double* logL) {
+                               double pen, double* logL, bool reuse_m_step = false) {
   DevKern kd0 = make_devkern(kern_0), kdi = make_devkern(kern_i);
   double* hres = c->h_pin + 32;
   int* hinfo = c->h_pin_i + 8;
-  MB_TRY(dense_obj_enqueue(c, c->ws0, kd0, hp_0, c->d_gridX.as<double>(), c->U, c->db.D, pm_dev, m0_dev,
-                           pc_dev, pen, 0, c->st2, hres, hinfo));
   TaskObjArgs a = make_obj_args(c, kdi, hp_i_dev, stride, TK_OBJ_MOD, 0, pen, 1, pm_dev, pc_dev, nullptr,
                                 c->f_t.as<double>(), c->g_t.as<double>());
-  MB_TRY(launch_obj(c, a, (int)c->db.n_tasks, c->st));
+  if (!reuse_m_step) {
+    MB_TRY(dense_obj_enqueue(c, c->ws0, kd0, hp_0, c->d_gridX.as<double>(), c->U, c->db.D, pm_dev, m0_dev,
+                             pc_dev, pen, 0, c->st2, hres, hinfo));
+    MB_TRY(launch_obj(c, a, (int)c->db.n_tasks, c->st));
+  }
   MB_TRY(c->sums.ensure(64 * 8));
   MB_TRY(leaf_sum_columns(c, a.f, 1, c->sums.as<double>(), c->st));
   // det term: chol(post_cov) without jitter (likelihoods.R:303-307)
@@ -1722,7 +1740,7 @@ static int dev_logL_monitoring(mb_context* c, const mb_kernel* kern_0, const dou
   CU(cudaStreamSynchronize(c->st));
   CU(cudaStreamSynchronize(c->st2));
   if (c->h_pin_i[0] != 0) MB_FAIL(1, "chol(post_cov) failed in logL_monitoring (no jitter is applied there)");
-  double ll_0 = (hinfo[0] < 0) ? NAN : hres[0];
+  double ll_0 = reuse_m_step ? c->m_step_f0 : ((hinfo[0] < 0) ? NAN : hres[0]);
   *logL = -ll_0 - c->h_pin[0] + c->h_pin[8];
   return 0;
 }
@@ -1789,7 +1807,8 @@ static int dev_em_step(mb_context* c, const mb_kernel* kern_0, double* hp_0, con
                     c->pc.as<double>(), pen, stats));
   const double t2 = c->prof_on ? now() : 0.0;
   MB_TRY(dev_logL_monitoring(c, kern_0, hp_0, kern_i, hp_i_dev, kdi.n_hp, m0_dev, c->pm.as<double>(),
-                             c->pc.as<double>(), pen, logL));
+                             c->pc.as<double>(), pen, logL, c->mstep_values_valid && !c->monitor_recompute));
+  c->mstep_values_valid = false;
   if (c->prof_on) {
     const double t3 = now();
     c->prof_phase[0] += t1 - t0; c->prof_phase[1] += t2 - t1; c->prof_phase[2] += t3 - t2;

@@ -523,12 +523,14 @@ MB_HD int lb_formt(LbfgsbState* s) {
 // at its LAST ACCEPTED iterate (the start of the running line search; the initial point when the very first evaluation
 // fails), so that the caller neither trains on from the failing trial point nor loses the other tasks' work; the count of
 // such tasks is returned in stats[3] and their code by mb_last_task_status.
-MB_HD void lb_fail_nonfinite(LbfgsbState* s) {
+MB_HD void lb_fail_nonfinite(LbfgsbState* s, double f) {
   s->fail = 99;
   s->active = 0;
   if (s->stage == LB_STAGE_LNSRCH) {
     for (int i = 0; i < s->n; ++i) { s->x[i] = s->t[i]; s->g[i] = s->r[i]; }
     s->f = s->fold;
+  } else {
+    s->f = f;   // the initial point itself has no finite objective: s->f stays "the objective at s->x"
   }
 }
 
@@ -536,7 +538,7 @@ MB_HD void lb_fail_nonfinite(LbfgsbState* s) {
 MB_HD void lb_advance(LbfgsbState* s, double f, const double* g) {
   if (!s->active) return;
   const int n = s->n;
-  if (!isfinite(f)) { lb_fail_nonfinite(s); return; }
+  if (!isfinite(f)) { lb_fail_nonfinite(s, f); return; }
   s->f = f;
   for (int i = 0; i < n; ++i) s->g[i] = g[i];
   if (s->stage == LB_STAGE_START) {

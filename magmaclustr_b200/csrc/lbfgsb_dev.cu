@@ -216,7 +216,7 @@ __device__ __forceinline__ void lbw_advance(LbfgsbState* s, LbScratch* w, double
   if (lane == 0) {
     int code = 0;
     const int n = s->n;
-    if (!isfinite(f)) lb_fail_nonfinite(s);
+    if (!isfinite(f)) lb_fail_nonfinite(s, f);
     else {
       s->f = f;
       for (int i = 0; i < n; ++i) s->g[i] = g[i];
@@ -321,12 +321,13 @@ __device__ __noinline__ void lbw_advance_smem(int state_off, int scratch_off, do
 
 // x -> HP table; fail codes and evaluation counts out.
 __global__ void k_lbfgsb_export(const LbfgsbState* st, int64_t m, int n, double* x,
-                                int64_t x_stride, int* fail, int* nfgv) {
+                                int64_t x_stride, int* fail, int* nfgv, double* fval) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= m) return;
   for (int p = 0; p < n; ++p) x[t * x_stride + p] = st[t].x[p];
   if (fail) fail[t] = st[t].fail;
   if (nfgv) nfgv[t] = st[t].nfgv;
+  if (fval) fval[t] = st[t].f;   // the objective at the exported x (every exit of the state machine keeps the pair consistent)
 }
 
 cudaError_t launch_lbfgsb_init(LbfgsbState* st, int64_t m, int n, const double* x0,
@@ -363,8 +364,8 @@ cudaError_t launch_lbfgsb_mask(LbfgsbState* st, int64_t m, const int32_t* skip, 
 }
 
 cudaError_t launch_lbfgsb_export(const LbfgsbState* st, int64_t m, int n, double* x,
-                                 int64_t x_stride, int* fail, int* nfgv, cudaStream_t s) {
-  k_lbfgsb_export<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(st, m, n, x, x_stride, fail, nfgv);
+                                 int64_t x_stride, int* fail, int* nfgv, double* fval, cudaStream_t s) {
+  k_lbfgsb_export<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(st, m, n, x, x_stride, fail, nfgv, fval);
   return cudaGetLastError();
 }
 

@@ -367,6 +367,26 @@ def test_logdet_modes_agree_on_tasks(mode):
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
 
 
+def test_monitoring_reuses_m_step_values_bit_identically(ctx):
+    """mb_em_step's logL_monitoring takes logL_GP_mod(new hp_i) and logL_GP_mod(new hp_0) from the M step's optimisers (they
+    ended on exactly those values) instead of evaluating them again (likelihoods.R:262-300): the log-likelihood and the HPs
+    must have the same BITS as with "monitor_recompute", and a stand-alone mb_logL_monitoring at the new HPs agrees."""
+    case = make_case(12, 20, 5)
+    upload(ctx, case)
+    out = []
+    for rec in (0, 1):
+        ctx.set_option("monitor_recompute", rec)
+        hp0, hpi = case["hp0"].copy(), case["hpi"].copy()
+        ll, stats = ctx.em_step(case["k0"], hp0, case["ki"], hpi, np.zeros(ctx.U))
+        out.append((ll, hp0, hpi))
+    ctx.set_option("monitor_recompute", 0)
+    assert out[0][0] == out[1][0], (out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+    pm, pc, _ = ctx.e_step(case["k0"], case["hp0"], case["ki"], case["hpi"], np.zeros(ctx.U))
+    ll2 = ctx.logL_monitoring(case["k0"], out[0][1], case["ki"], out[0][2], np.zeros(ctx.U), pm, pc)
+    assert ll2 == out[0][0], (ll2, out[0][0])
+
+
 def test_chol_inv_jitter_split_product_is_bit_identical(ctx):
     """Union-grid sizes (n >= 128): the X X' product of chol2inv runs in a separate multi-CTA kernel; every entry must equal
     the single-CTA kernel's (same accumulation order), the result is exactly symmetric and matches LAPACK."""
