@@ -548,16 +548,20 @@ def main():
         line["hbm_kernels"] = hk
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count()
-        m_sample = args.cpu_sample
-        if not m_sample:                     # size the sample for ~15 s of CPU work on this box's cores
-            dt0, _, _ = oracle_sample_step(df, 512, cores)
-            m_sample = int(min(M_TASKS, max(512, 512 * 15.0 / max(dt0, 1e-3)))) // 256 * 256
-        dt, evals, _ = oracle_sample_step(df, m_sample, cores)
-        line["cpu_baseline"] = {
-            "value": 1.0 / (dt * M_TASKS / m_sample), "unit": "EM steps/s", "cores": cores,
-            "kind": "port",
-            "sample": "one EM step of the oracle (numpy/LAPACK restatement of the reference, one process per core) "
-                      "on the first %d of %d tasks (%.1f s), scaled linearly in M" % (m_sample, M_TASKS, dt)}
+        try:                                 # a side measurement: the headline line must survive whatever happens here
+            m_sample = args.cpu_sample
+            if not m_sample:                 # size the sample for ~15 s of CPU work on this box's cores
+                dt0, _, _ = oracle_sample_step(df, 512, cores)
+                m_sample = int(min(M_TASKS, max(512, 512 * 15.0 / max(dt0, 1e-3)))) // 256 * 256
+            dt, evals, _ = oracle_sample_step(df, m_sample, cores)
+            line["cpu_baseline"] = {
+                "value": 1.0 / (dt * M_TASKS / m_sample), "unit": "EM steps/s", "cores": cores,
+                "kind": "port",
+                "sample": "one EM step of the oracle (numpy/LAPACK restatement of the reference, one process per core) "
+                          "on the first %d of %d tasks (%.1f s), scaled linearly in M" % (m_sample, M_TASKS, dt)}
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": "EM steps/s", "cores": cores, "kind": "port",
+                                    "sample": "failed: %s" % str(e)[:200]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -194,6 +194,10 @@ struct mb_context {
   // process's value at the new hp_0 -- exactly what logL_monitoring evaluates next (same functions, same hyper-posterior)
   bool mstep_values_valid = false;
   double m_step_f0 = 0.0;
+  // same after a VM step of train_magmaclust: the task ELBO terms (per task in f_t, or their all-rank sum for a shared
+  // HP vector) and the cluster terms, as the optimisers left them
+  bool vm_valid = false, vm_tasks_in_f_t = false;
+  double vm_sum_ll_i = 0.0, vm_sum_ll_k = 0.0;
   bool monitor_recompute = false;   // MB_MONITOR_RECOMPUTE / "monitor_recompute": logL_monitoring re-evaluates everything
   bool prof_on = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
@@ -2577,10 +2581,13 @@ static int dev_vm_step(mb_context* c, int K, const mb_kernel* kern_k, double* hp
       lb_init(&sp.s, Pk, hp_k + (size_t)k * Pk, 1e13, 0.0, 25);
     }
   }
+  c->vm_valid = false;
   if (!shared_hp_i) {
     MB_TRY(optimise(c, singles, true, a, hp_i_dev, Pi, pen_diag, stats));
+    c->vm_tasks_in_f_t = true;
   } else {
     MB_TRY(optimise(c, singles, false, a, hp_i_dev, Pi, pen_diag, stats));
+    c->vm_tasks_in_f_t = false;
     LbfgsbState s;
     double x0[MB_MAX_HP];
     MB_TRY(d2h(x0, hp_i_dev, Pi * 8, c->st));     // block of the first task (:236-238): the same on every rank
@@ -2599,13 +2606,19 @@ static int dev_vm_step(mb_context* c, int K, const mb_kernel* kern_k, double* hp
     MB_TRY(h2d(hp_i_dev, tab.data(), tab.size() * 8, c->st));
     CU(cudaStreamSynchronize(c->st));
     if (stats) { stats[1] = evals; stats[2] = (int64_t)evals * M; stats[3] = (s.fail == 99); }
+    c->vm_sum_ll_i = s.f;
   }
+  bool k_ok = true;
   if (!shared_hp_k) {
     int ev = 0;
+    double sum_k = 0.0;
     for (int k = 0; k < K; ++k) {
       for (int p = 0; p < Pk; ++p) hp_k[(size_t)k * Pk + p] = singles[k].s.x[p];
       ev += singles[k].evals;
+      sum_k += singles[k].s.f;          // in cluster order, like elbo_monitoring_VEM's loop
+      if (singles[k].evals == 0) k_ok = false;
     }
+    c->vm_sum_ll_k = sum_k;
     if (stats) stats[0] = ev;
   } else {
     LbfgsbState s;
@@ -2620,7 +2633,9 @@ static int dev_vm_step(mb_context* c, int K, const mb_kernel* kern_k, double* hp
     for (int k = 0; k < K; ++k)
       for (int p = 0; p < Pk; ++p) hp_k[(size_t)k * Pk + p] = s.x[p];
     if (stats) stats[0] = evals;
+    c->vm_sum_ll_k = s.f;
   }
+  c->vm_valid = k_ok;
   return 0;
 }
 
@@ -2649,7 +2664,9 @@ extern "C" int mb_vm_step(mb_context* c, int n_clusters, const mb_kernel* kern_k
 // elbo_monitoring_VEM on device-resident state (c->pm / c->pc / c->tau / c->m0 = m_k); hp_i_dev with the given stride
 static int dev_elbo_monitoring(mb_context* c, int K, const mb_kernel* kern_k, const double* hp_k, const mb_kernel* kern_i,
                                const double* hp_i_dev, int64_t stride, const double* tau_host, const double* prop_mixture,
-                               double pen_diag, double* elbo) {
+                               double pen_diag, double* elbo, bool reuse_vm_step = false) {
+  // reuse_vm_step: called right after dev_vm_step on the same hyper-posterior and mixture -- the task and cluster terms
+  // (elbos.R:209-235) are the objective values the VM step's optimisers ended with (see dev_logL_monitoring)
   const int U = c->U;
   const int64_t M = c->db.n_tasks;
   const size_t UU = (size_t)U * U;
@@ -2658,12 +2675,17 @@ static int dev_elbo_monitoring(mb_context* c, int K, const mb_kernel* kern_k, co
   // task sum (elbos.R:221-235)
   TaskObjArgs a = make_obj_args(c, kdi, hp_i_dev, stride, TK_OBJ_ELBO, 0, pen_diag, K, c->pm.as<double>(),
                                 c->pc.as<double>(), c->tau.as<double>(), c->f_t.as<double>(), c->g_t.as<double>());
-  MB_TRY(launch_obj(c, a, (int)M, c->st));
-  MB_TRY(c->sums.ensure(64 * 8));
-  MB_TRY(leaf_sum_columns(c, a.f, 1, c->sums.as<double>(), c->st));
-  MB_TRY(d2h(c->h_pin, c->sums.p, 8, c->st));
-  CU(cudaStreamSynchronize(c->st));
-  const double sum_ll_i = c->h_pin[0];
+  double sum_ll_i;
+  if (reuse_vm_step && !c->vm_tasks_in_f_t) {
+    sum_ll_i = c->vm_sum_ll_i;
+  } else {
+    if (!reuse_vm_step) MB_TRY(launch_obj(c, a, (int)M, c->st));
+    MB_TRY(c->sums.ensure(64 * 8));
+    MB_TRY(leaf_sum_columns(c, a.f, 1, c->sums.as<double>(), c->st));
+    MB_TRY(d2h(c->h_pin, c->sums.p, 8, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    sum_ll_i = c->h_pin[0];
+  }
   // sum_i tau_ik log(pi_k / tau_ik) over the tasks of every rank (elbos.R:249-256)
   double sum_tau_k[MB_MAX_CLUSTERS];
   {
@@ -2679,12 +2701,15 @@ static int dev_elbo_monitoring(mb_context* c, int K, const mb_kernel* kern_k, co
   double sum_ll_k = 0.0, sum_corr = 0.0;
   double* hres = c->h_pin + 32;
   int* hinfo = c->h_pin_i + 8;
+  if (reuse_vm_step) sum_ll_k = c->vm_sum_ll_k;
   for (int k = 0; k < K; ++k) {
-    MB_TRY(dense_obj_enqueue(c, c->ws0, kdk, hp_k + (size_t)k * kdk.n_hp, c->d_gridX.as<double>(), U, c->db.D,
-                             c->pm.as<double>() + (size_t)k * U, c->m0.as<double>() + (size_t)k * U,
-                             c->pc.as<double>() + k * UU, pen_diag, 0, c->st2, hres, hinfo));
-    CU(cudaStreamSynchronize(c->st2));
-    sum_ll_k += (hinfo[0] < 0) ? NAN : hres[0];
+    if (!reuse_vm_step) {
+      MB_TRY(dense_obj_enqueue(c, c->ws0, kdk, hp_k + (size_t)k * kdk.n_hp, c->d_gridX.as<double>(), U, c->db.D,
+                               c->pm.as<double>() + (size_t)k * U, c->m0.as<double>() + (size_t)k * U,
+                               c->pc.as<double>() + k * UU, pen_diag, 0, c->st2, hres, hinfo));
+      CU(cudaStreamSynchronize(c->st2));
+      sum_ll_k += (hinfo[0] < 0) ? NAN : hres[0];
+    }
     LAUNCH(c, launch_chol_logdiag_any(c, c->ws1, c->pc.as<double>() + k * UU, U, c->ws1.info.as<int>(),
                                       c->sums.as<double>() + 8, c->st));
     MB_TRY(d2h(c->h_pin + 8, c->sums.as<double>() + 8, 8, c->st));
@@ -2799,7 +2824,9 @@ extern "C" int mb_train_magmaclust(mb_context* c, int n_clusters, const mb_kerne
     }
     if (bad) break;
     double new_elbo;
-    MB_TRY(dev_elbo_monitoring(c, K, kern_k, new_hp_k.data(), kern_i, nxt, Pi, post_mix.data(), new_prop, pen_diag, &new_elbo));
+    MB_TRY(dev_elbo_monitoring(c, K, kern_k, new_hp_k.data(), kern_i, nxt, Pi, post_mix.data(), new_prop, pen_diag, &new_elbo,
+                               c->vm_valid && !c->monitor_recompute));
+    c->vm_valid = false;
     double diff = new_elbo - elbo;
     if (isnan(diff)) diff = -INFINITY;
     for (size_t q = 0; q < new_hp_k.size(); ++q) hp_k[q] = new_hp_k[q];

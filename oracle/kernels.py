@@ -13,6 +13,17 @@ import math
 import numpy as np
 from scipy.linalg import lapack
 
+
+def _rexp(x):
+    """exp() with R's (IEEE) overflow behaviour: Inf instead of Python's OverflowError.  An optimiser trial point far outside
+    the sensible range then yields a non-finite objective, which optim reports as "L-BFGS-B needs finite values of 'fn'"
+    (oracle/lbfgsb.py raises FloatingPointError there) -- not a Python-specific exception from inside the kernel."""
+    try:
+        return math.exp(x)
+    except OverflowError:
+        return math.inf
+
+
 MAX_JITTER_RETRY = 40  # R has no cap (recursion until the C stack ends); see DESIGN.md
 
 
@@ -79,18 +90,18 @@ def cpp_noise(m1, m2, noise):
     diff = np.zeros((m1.shape[0], m2.shape[0]))
     for c in range(m1.shape[1]):
         diff += np.abs(m1[:, c][:, None] - m2[:, c][None, :])
-    return np.where(diff < 0.000001, math.exp(noise), 0.0)
+    return np.where(diff < 0.000001, _rexp(noise), 0.0)
 
 
 # ---- R/kernels.R ------------------------------------------------------------
 def se_kernel(x, y, hp, deriv=None):
     """kernels.R:164-196."""
     distance = cpp_dist(x, y)
-    top_term = math.exp(-hp["se_lengthscale"]) * 0.5 * distance
+    top_term = _rexp(-hp["se_lengthscale"]) * 0.5 * distance
     if deriv is None or deriv == "se_variance":
         return np.exp(hp["se_variance"] - top_term)
     if deriv == "se_lengthscale":
-        return math.exp(hp["se_variance"]) * top_term * np.exp(-top_term)
+        return _rexp(hp["se_variance"]) * top_term * np.exp(-top_term)
     raise ValueError("invalid deriv")
 
 
@@ -100,13 +111,13 @@ def perio_kernel(x, y, hp, deriv=None):
     sum_deriv = cpp_perio_deriv(x, y, hp["period"])
     v, l = hp["perio_variance"], hp["perio_lengthscale"]
     if deriv is None or deriv == "perio_variance":
-        return math.exp(v) * np.exp(-2 * math.exp(-l) * perio_term)
+        return _rexp(v) * np.exp(-2 * _rexp(-l) * perio_term)
     if deriv == "period":
-        return (math.exp(v) * np.exp(-2 * math.exp(-l) * perio_term)
-                * 2 * math.exp(-l) * sum_deriv)
+        return (_rexp(v) * np.exp(-2 * _rexp(-l) * perio_term)
+                * 2 * _rexp(-l) * sum_deriv)
     if deriv == "perio_lengthscale":
-        return (math.exp(v) * 2 * perio_term * math.exp(-l)
-                * np.exp(-2 * perio_term * math.exp(-l)))
+        return (_rexp(v) * 2 * perio_term * _rexp(-l)
+                * np.exp(-2 * perio_term * _rexp(-l)))
     raise ValueError("invalid deriv")
 
 
@@ -114,14 +125,14 @@ def rq_kernel(x, y, hp, deriv=None):
     """kernels.R:294-341 (rq_scale is used raw, not exponentiated)."""
     distance = cpp_dist(x, y)
     v, l, a = hp["rq_variance"], hp["rq_lengthscale"], hp["rq_scale"]
-    term = 1 + distance * math.exp(-l) / (2 * a)
+    term = 1 + distance * _rexp(-l) / (2 * a)
     if deriv is None or deriv == "rq_variance":
-        return math.exp(v) * term ** (-a)
+        return _rexp(v) * term ** (-a)
     if deriv == "rq_scale":
-        return (math.exp(v) * term ** (-a)
-                * (distance * math.exp(-l) / (2 * a * term) - np.log(term)))
+        return (_rexp(v) * term ** (-a)
+                * (distance * _rexp(-l) / (2 * a * term) - np.log(term)))
     if deriv == "rq_lengthscale":
-        return math.exp(v) * distance * 0.5 * math.exp(-l) * term ** (-a - 1)
+        return _rexp(v) * distance * 0.5 * _rexp(-l) * term ** (-a - 1)
     raise ValueError("invalid deriv")
 
 
@@ -129,11 +140,11 @@ def lin_kernel(x, y, hp, deriv=None):
     """kernels.R:364-398."""
     prod = cpp_prod(x, y)
     if deriv is None:
-        return math.exp(hp["lin_slope"]) * prod + math.exp(hp["lin_offset"])
+        return _rexp(hp["lin_slope"]) * prod + _rexp(hp["lin_offset"])
     if deriv == "lin_offset":
         return np.exp(hp["lin_offset"] * np.ones_like(prod))
     if deriv == "lin_slope":
-        return math.exp(hp["lin_slope"]) * prod
+        return _rexp(hp["lin_slope"]) * prod
     raise ValueError("invalid deriv")
 
 
@@ -240,14 +251,14 @@ def convolution_kernel(x, y, hp, n_outputs, deriv=None):
         mat = np.zeros((len(x), len(y)))
         if same_inputs:
             out_lab = int(deriv.split("_")[-1]) - 1
-            mat[np.arange(len(x)), np.arange(len(x))] = np.where(ox == out_lab, math.exp(hp[deriv]), 0.0)
+            mat[np.arange(len(x)), np.arange(len(x))] = np.where(ox == out_lab, _rexp(hp[deriv]), 0.0)
         return mat
     distance_sq = cpp_dist(xc, yc)
     l_t = np.array([hp["l_t_%d" % (o + 1)] for o in range(O)])
     S_t = np.array([hp["S_t_%d" % (o + 1)] for o in range(O)])
     l1, l2 = np.exp(l_t[ox]), np.exp(l_t[oy])
     S1, S2 = np.exp(S_t[ox]), np.exp(S_t[oy])
-    l_u = math.exp(hp["l_u_t"])
+    l_u = _rexp(hp["l_u_t"])
     denom = np.add.outer(l1, l2) + l_u
     K = np.multiply.outer(S1, S2) / ((2 * math.pi * denom) ** (input_dim / 2)) * np.exp(-0.5 * distance_sq / denom)
     if deriv is None:

@@ -120,6 +120,20 @@ def test_train_magmaclust_small(ctx):
     step = ctx.train_magmaclust_stepwise(KC, case["k0"], hp_k, case["ki"], case["hpi"], mix, True, True, n_iter_max=6)
     for key in ("seq_elbo", "hp_k", "hp_i", "m_k", "mixture", "prop_mixture", "post_mean", "post_cov"):
         assert np.array_equal(np.asarray(res[key]), np.asarray(step[key])), key
+    # ... also with per-task / per-cluster HPs.  The resident loop takes the ELBO's task and cluster terms from the VM step's
+    # optimisers instead of evaluating them again; the stepwise path always re-evaluates: same bits.
+    case2, mix2, hp_k2, _ = _setup(ctx, M=12, N=10, seed=4, shared_i=False)
+    res2 = ctx.train_magmaclust(KC, case2["k0"], hp_k2, case2["ki"], case2["hpi"], mix2, False, False, n_iter_max=4)
+    step2 = ctx.train_magmaclust_stepwise(KC, case2["k0"], hp_k2, case2["ki"], case2["hpi"], mix2, False, False, n_iter_max=4)
+    for key in ("seq_elbo", "hp_k", "hp_i", "m_k", "mixture", "prop_mixture"):
+        assert np.array_equal(np.asarray(res2[key]), np.asarray(step2[key])), key
+    ctx.set_option("monitor_recompute", 1)
+    try:
+        res3 = ctx.train_magmaclust(KC, case2["k0"], hp_k2, case2["ki"], case2["hpi"], mix2, False, False, n_iter_max=4)
+    finally:
+        ctx.set_option("monitor_recompute", 0)
+    assert np.array_equal(res3["seq_elbo"], res2["seq_elbo"])
+    case, mix, hp_k, o_hp_k = _setup(ctx, M=12, N=10, seed=4, shared_i=True)
     # fast_approx: one VE step, ELBO of the initial hyper-parameters (training.R:1633-1647)
     fa = ctx.train_magmaclust(KC, case["k0"], hp_k, case["ki"], case["hpi"], mix, True, True, fast_approx=True)
     assert len(fa["seq_elbo"]) == 1 and not fa["converged"] and np.array_equal(fa["hp_k"], hp_k)
