@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_optimis
         const double* hp_src = a.lb[task].x;
         double hp_pre[3] = {0.0, 0.0, 0.0};
         if (KS == KS_SE) { hp_pre[0] = hp_src[0]; hp_pre[1] = hp_src[1]; if (a.kd.has_noise) hp_pre[2] = hp_src[2]; }
-        task_objective_eval3<KS, N8C, D1, MODE_T>(a, task, KS == KS_SE ? hp_pre : hp_src, book_ll[1], book[1], s, L, first);
+        task_objective_eval3<KS, N8C, D1, MODE_T, false>(a, task, KS == KS_SE ? hp_pre : hp_src, book_ll[1], book[1], s, L, first);
       }
       first = false;
       __syncthreads();

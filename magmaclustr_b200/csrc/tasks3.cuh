@@ -555,7 +555,9 @@ __device__ __forceinline__ double gather_S3(const TaskObjArgs& a, int mode, int6
 // and job tables already sit in shared memory (they survive an evaluation: the fused M-step kernel loads them once per task).
 // MODE_T >= 0: the objective mode as a compile-time constant (the M step's TK_OBJ_MOD is instantiated that way: no
 // mode branches in the gather / product loops, the ELBO and mixture code is not in the binary); -1: mode at run time.
-template <int KS, int N8C, bool D1, int MODE_T>
+// DISCARD: drop the L2 lines of the kernel-value cache once the gradient has consumed them (the lock-step kernel; the
+// persistent M-step kernel re-evaluates the same task at once and rewrites them, and has no register to spare).
+template <int KS, int N8C, bool D1, int MODE_T, bool DISCARD = true>
 __device__ __forceinline__ void task_objective_eval3(const TaskObjArgs& a, const int64_t task, const double* hp_eff,
                                                      const int64_t row0, const int n, const Sm3& s, const Ln& L,
                                                      const bool do_load) {
@@ -771,5 +773,15 @@ __device__ __forceinline__ void task_objective_eval3(const TaskObjArgs& a, const
       if (tid == 0)
         for (int q = 0; q < 4 && p0 + q < P; ++q) a.g[task * P + p0 + q] = -0.5 * v[q];
     }
+  }
+  if (DISCARD && Cov<KS, D1>::CACHEABLE && a.kcache) {
+    // The cached kernel values have been consumed (every warp is past the barrier of the reduction above) and the next
+    // evaluation of this task overwrites them before it reads them: drop their L2 lines instead of letting 18 KB per
+    // evaluation be written back to HBM (130 MB per launch of 10 000 evaluations in round 1's ncu capture).
+    // (pointer and size are recomputed from the kernel arguments: keeping them live across the gradient phase spills)
+    const char* kcb = reinterpret_cast<const char*>(a.kcache + task * a.kcache_stride);
+    const int nbytes = t3_ntri(t3_n8(n)) * 512;
+    for (int off = (int)threadIdx.x * 128; off < nbytes; off += T3_THREADS * 128)
+      asm volatile("discard.global.L2 [%0], 128;" ::"l"(kcb + off) : "memory");
   }
 }
