@@ -792,6 +792,22 @@ extern "C" int mb_chol_inv_jitter(mb_context* c, const double* mat, int n, int l
   return 0;
 }
 
+// grid_index of the resident tasks: in range, and distinct within a task.  The E-step scatter adds one value per (task,
+// grid position) and relies on the positions of one task being distinct; the reference stops on such data
+// (R/training.R:703-714, "At least one individual have several Outputs on the same grid point").
+static int check_grid_index(const int64_t* offs, int64_t n_tasks, const int32_t* grid_index, int32_t n_grid) {
+  std::vector<int64_t> seen((size_t)(n_grid > 0 ? n_grid : 0), -1);
+  for (int64_t t = 0; t < n_tasks; ++t)
+    for (int64_t r = offs[t]; r < offs[t + 1]; ++r) {
+      const int32_t g = grid_index[r];
+      if (g < 0 || g >= n_grid) MB_FAIL(-1, "grid_index out of range");
+      if (seen[g] == t)
+        MB_FAIL(-1, "At least one individual have several Outputs on the same grid point (duplicate grid_index within a task)");
+      seen[g] = t;
+    }
+  return 0;
+}
+
 // ---- dataset -------------------------------------------------------------------------------------
 extern "C" int mb_upload_dataset(mb_context* c, int64_t n_tasks, const int64_t* offs, int d,
                                  const double* X, const double* y, const int32_t* grid_index,
@@ -805,9 +821,7 @@ extern "C" int mb_upload_dataset(mb_context* c, int64_t n_tasks, const int64_t* 
     if (n < 1) MB_FAIL(-1, "empty task");
     if (n > nmax) nmax = (int)n;
   }
-  if (grid_index)
-    for (int64_t r = 0; r < rows; ++r)
-      if (grid_index[r] < 0 || grid_index[r] >= n_grid) MB_FAIL(-1, "grid_index out of range");
+  if (grid_index) MB_TRY(check_grid_index(offs, n_tasks, grid_index, n_grid));
   MB_TRY(c->d_offs.ensure((n_tasks + 1) * 8));
   MB_TRY(c->d_X.ensure((size_t)rows * d * 8));
   MB_TRY(c->d_y.ensure((size_t)rows * 8));
@@ -1362,8 +1376,7 @@ static int hyperposterior_any(mb_context* c, int K, const mb_kernel* kern_k, con
       ((!post_mean || !post_cov) && !c->hpr_keep))
     MB_FAIL(-1, "bad argument");
   if (K < 1 || K > MB_MAX_CLUSTERS || (K > 1 && !tau)) MB_FAIL(-1, "bad cluster count / missing mixture");
-  for (int64_t r = 0; r < c->n_rows; ++r)
-    if (grid_index[r] < 0 || grid_index[r] >= n_grid) MB_FAIL(-1, "grid_index out of range");
+  MB_TRY(check_grid_index(c->h_offs.data(), c->db.n_tasks, grid_index, n_grid));
   const size_t UU = (size_t)n_grid * n_grid;
   DBuf gX, gi, pm, pc, m0, dtau;
   int rc = 0;

@@ -719,6 +719,13 @@ __device__ __forceinline__ void task_objective_eval3(const TaskObjArgs& a, const
     const SymRow<N8C> row(s.T1, i, L);
     const double* bb = s.T2 + (size_t)j * 64 + L.o_tg;   // B tile (k, j) at bb + k * N8C * 64
     double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+    // the cached kernel values of this job are requested before the product loop: their L2 round trip runs under the DMMAs
+    double2 kv[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
+    if (kc) {
+      const double2* kp = reinterpret_cast<const double2*>(kc + (size_t)(Lay<N8C>::tri(i) + j - i) * 64) + L.lane;
+      kv[0] = kp[0];
+      if (two) kv[1] = kp[32];
+    }
 #pragma unroll
     for (int k = 0; k < N8C; ++k) {
       if (k < n8) {
@@ -734,12 +741,6 @@ __device__ __forceinline__ void task_objective_eval3(const TaskObjArgs& a, const
     }
     const int r = 8 * i + L.g;
     const double* Arow = s.T1 + (size_t)(Lay<N8C>::tri(i) + j - i) * 64 + L.o_c;
-    double2 kv[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
-    if (kc) {
-      const double2* kp = reinterpret_cast<const double2*>(kc + (size_t)(Lay<N8C>::tri(i) + j - i) * 64) + L.lane;
-      kv[0] = kp[0];
-      if (two) kv[1] = kp[32];
-    }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       if (h == 0 || two) {

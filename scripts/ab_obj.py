@@ -30,7 +30,7 @@ def main():
         t_e.append(ctx.timer_stop_ms())
     ctx.set_state(k0, hp0, ki, hpi, m0)
     t_s = []
-    for r in range(6):
+    for r in range(14):
         ctx.flush_l2()
         ctx.timer_start()
         ll, st = ctx.em_step_resident(k0, ki, restart=True)

@@ -411,6 +411,22 @@ def test_chol_inv_jitter_split_product_is_bit_identical(ctx):
         ctx.chol_inv_jitter(bad, 1e-10)
 
 
+def test_upload_rejects_duplicate_grid_positions(ctx):
+    """A task with two outputs on the same grid point: the reference stops (R/training.R:703-714); the E-step scatter relies
+    on distinct positions within a task, so the C ABI refuses the dataset instead of summing wrongly."""
+    case = make_case(4, 6, 21)
+    p = case["prep"]
+    gi = p.grid_index.copy()
+    gi[p.offs[1] + 1] = gi[p.offs[1]]                       # task 1: rows 0 and 1 on the same grid point
+    with pytest.raises(L.MagmaError, match="several Outputs on the same grid point"):
+        ctx.upload_dataset(p.offs, p.X, p.y, gi, p.grid_X)
+    gi = p.grid_index.copy()
+    gi[0] = len(p.grid_X)
+    with pytest.raises(L.MagmaError, match="out of range"):
+        ctx.upload_dataset(p.offs, p.X, p.y, gi, p.grid_X)
+    upload(ctx, case)                                        # the same position in DIFFERENT tasks is the normal case
+
+
 # ---- multi-output convolution kernel (kernels.R:16-140) as a kernel type: "CONV<O>" -------------------------
 def _mo_case(seed=31, O=2, M=6, n=7):
     rng = np.random.default_rng(seed)
