@@ -77,8 +77,17 @@ int64_t mb_launch_count(mb_context* ctx);
  * like MB_LOGDET=lu; 1 = read off the Cholesky diagonal), "monitor_recompute" (MB_MONITOR_RECOMPUTE: 1 = mb_em_step* /
  * mb_train_magma evaluate logL_monitoring from scratch; 0, the default = the per-task and mean-process values
  * logL_GP_mod(new HPs) are taken from the M step's optimisers, which ended on exactly those values -- same numbers, one
- * all-task launch less per EM iteration).  The environment variables are read once at mb_create. */
+ * all-task launch less per EM iteration), "pair_tables" (MB_PAIR_TABLES: 1, the default = the SE kernel of a resident
+ * task is evaluated once per DISTINCT squared distance of the task and looked up per matrix element, see
+ * mb_pair_table_counts; 0 = element by element; same bits either way).  The environment variables are read once at
+ * mb_create. */
 int mb_set_option(mb_context* ctx, const char* name, int64_t value);
+/* Pair tables of the resident dataset (built by mb_upload_dataset for tasks of at most 96 points): counts[t] = number of
+ * distinct values of sum_q (x_rq - x_cq)^2 over the pairs of task t, or -1 when the task keeps the element-by-element
+ * evaluation (more than 1024 distinct values, or NaN inputs).  The reference evaluates every element (src/code.cpp:6-131
+ * under R/kernel-to-matrices.R:71-503); tasks observed on a common grid repeat the same distances many times.
+ * Returns -1 when no tables exist (no dataset, larger tasks, or the option switched off at upload). */
+int mb_pair_table_counts(mb_context* ctx, int32_t* counts);
 
 /* optional sum-all-reduce over ranks of `count` doubles in DEVICE memory, called on the
  * context's stream after it was synchronised (multi-GPU sharding).  The hook

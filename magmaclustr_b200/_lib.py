@@ -42,6 +42,7 @@ _SIGS = {
     "mb_kernel_parse": [C.c_char_p, C.c_int, _kp],
     "mb_launch_count": [_vp],
     "mb_set_option": [_vp, C.c_char_p, C.c_int64],
+    "mb_pair_table_counts": [_vp, _ip],
     "mb_set_allreduce": [_vp, ALLREDUCE_FN, _vp, C.c_int, C.c_int],
     "mb_cpp_dist": [_vp, _dp, C.c_int, _dp, C.c_int, C.c_int, _dp],
     "mb_cpp_prod": [_vp, _dp, C.c_int, _dp, C.c_int, C.c_int, _dp],

@@ -10,7 +10,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmagma_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
-UNITS = [("tasks.cu", []), ("tasks3.cu", []), ("estep3.cu", []), ("mstep3.cu", ["-rdc=true"]), ("covbuild.cu", []), ("hostprep.cu", []), ("dense.cu", []), ("dense3.cu", []), ("dense_big.cu", []), ("bigtasks.cu", []), ("api.cu", []), ("lbfgsb_dev.cu", ["-fmad=false", "-rdc=true", "-maxrregcount=128"])]
+UNITS = [("tasks.cu", []), ("tasks3.cu", []), ("estep3.cu", []), ("pairs3.cu", []), ("mstep3.cu", ["-rdc=true"]), ("covbuild.cu", []), ("hostprep.cu", []), ("dense.cu", []), ("dense3.cu", []), ("dense_big.cu", []), ("bigtasks.cu", []), ("api.cu", []), ("lbfgsb_dev.cu", ["-fmad=false", "-rdc=true", "-maxrregcount=128"])]
 
 
 def _newer(src_list, target):

@@ -32,6 +32,8 @@ cudaError_t launch_task_objective3(TaskObjArgs a, int n_launch, cudaStream_t st)
 cudaError_t launch_task_optimise3(TaskObjArgs a, int* queue, int sm_count, int reserve_sms, unsigned long long* cycles,
                                   cudaStream_t st);
 cudaError_t launch_task_inverse3(TaskInvArgs a, int n_ctas, cudaStream_t st);
+cudaError_t launch_task_pairs3(TaskData db, double* pair_d2, unsigned short* pair_idx, int32_t* pair_n, int pair_stride,
+                               cudaStream_t st);
 int task3_max_ctas_per_sm(int nmax, int D);
 
 struct BigTaskPool;
@@ -171,6 +173,11 @@ struct mb_context {
   int64_t n_rows = 0;
   int U = 0;
   DBuf d_offs, d_X, d_y, d_gidx, d_gridX;
+  // pair tables of the resident tasks (pairs3.cu), built by mb_upload_dataset for tasks of at most TK_MAXN points;
+  // option "pair_tables" / MB_PAIR_TABLES=0 keeps the per-task kernels on the element-by-element evaluation (same bits)
+  DBuf d_pair_d2, d_pair_idx, d_pair_n;
+  bool pair_tables = true, pairs_built = false;
+  int pair_stride = 0;
   std::vector<int64_t> h_offs;
   // workspaces
   DenseWs ws0, ws1;                 // ws0: mean/cluster process on st2 ; ws1: generic on st
@@ -517,6 +524,7 @@ extern "C" int mb_create(mb_context** out, int device) {
   if (const char* e = getenv("MB_RESERVE_SMS")) { c->reserve_sms = atoi(e); if (c->reserve_sms < 0) c->reserve_sms = 0; if (c->reserve_sms > c->sm_count / 2) c->reserve_sms = c->sm_count / 2; }
   c->single_blocking = getenv("MB_SINGLE_BLOCKING") != nullptr;
   c->split_lauum = getenv("MB_DENSE_NOSPLIT") == nullptr;
+  if (const char* e = getenv("MB_PAIR_TABLES")) c->pair_tables = atoi(e) != 0;
   *out = c;
   return 0;
 }
@@ -525,7 +533,7 @@ extern "C" int mb_destroy(mb_context* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  DBuf* bufs[] = {&c->d_offs, &c->d_X, &c->d_y, &c->d_gidx, &c->d_gridX, &c->hp_i, &c->hp_k, &c->f_t,
+  DBuf* bufs[] = {&c->d_offs, &c->d_X, &c->d_y, &c->d_gidx, &c->d_gridX, &c->d_pair_d2, &c->d_pair_idx, &c->d_pair_n, &c->hp_i, &c->hp_k, &c->f_t,
                   &c->g_t, &c->retries, &c->lb, &c->counters, &c->sums,
                   &c->pm, &c->pc, &c->m0, &c->tau, &c->inv0, &c->post_inv, &c->fails,
                   &c->nfgv, &c->scratch, &c->kcache, &c->d_lv_offs, &c->tickets, &c->leafbuf, &c->slotbuf, &c->leafsum};
@@ -557,6 +565,15 @@ extern "C" int mb_destroy(mb_context* c) {
 extern "C" int64_t mb_launch_count(mb_context* c) { return c ? c->launches : 0; }
 
 // Tuning / diagnostic switches of a context (the environment variables of the same meaning are read once at mb_create)
+// hand the pair tables to the per-task kernels (or not): every launch copies c->db into its argument block
+static void apply_pair_tables(mb_context* c) {
+  const bool on = c->pair_tables && c->pairs_built;
+  c->db.pair_d2 = on ? c->d_pair_d2.as<double>() : nullptr;
+  c->db.pair_idx = on ? c->d_pair_idx.as<unsigned short>() : nullptr;
+  c->db.pair_n = on ? c->d_pair_n.as<int32_t>() : nullptr;
+  c->db.pair_stride = on ? c->pair_stride : 0;
+}
+
 extern "C" int mb_set_option(mb_context* c, const char* name, int64_t value) {
   if (!c || !name) MB_FAIL(-1, "null argument");
   const std::string n(name);
@@ -565,6 +582,7 @@ extern "C" int mb_set_option(mb_context* c, const char* name, int64_t value) {
   else if (n == "dense_split") c->split_lauum = value != 0;       // MB_DENSE_NOSPLIT (inverted)
   else if (n == "logdet_chol") c->logdet_chol = value != 0;       // MB_LOGDET=lu <-> 0
   else if (n == "monitor_recompute") c->monitor_recompute = value != 0;   // MB_MONITOR_RECOMPUTE
+  else if (n == "pair_tables") { c->pair_tables = value != 0; apply_pair_tables(c); }   // MB_PAIR_TABLES
   else MB_FAIL(-1, "unknown option");
   return 0;
 }
@@ -792,19 +810,40 @@ extern "C" int mb_chol_inv_jitter(mb_context* c, const double* mat, int n, int l
   return 0;
 }
 
+extern "C" int mb_pair_table_counts(mb_context* c, int32_t* counts) {
+  MB_TRY(check_ctx(c));
+  if (!counts) MB_FAIL(-1, "null argument");
+  if (!c->have_db || !c->pairs_built) MB_FAIL(-1, "no pair tables for the resident dataset");
+  return d2h(counts, c->d_pair_n.p, (size_t)c->db.n_tasks * 4, c->st);
+}
+
 // grid_index of the resident tasks: in range, and distinct within a task.  The E-step scatter adds one value per (task,
 // grid position) and relies on the positions of one task being distinct; the reference stops on such data
 // (R/training.R:703-714, "At least one individual have several Outputs on the same grid point").
 static int check_grid_index(const int64_t* offs, int64_t n_tasks, const int32_t* grid_index, int32_t n_grid) {
-  std::vector<int64_t> seen((size_t)(n_grid > 0 ? n_grid : 0), -1);
-  for (int64_t t = 0; t < n_tasks; ++t)
+  std::vector<int64_t> seen;
+  for (int64_t t = 0; t < n_tasks; ++t) {
+    // rows are Reference-sorted like the grid (R/training.R:700), so the positions of a task normally increase strictly:
+    // one predictable comparison per row; only a task that breaks the order gets the general distinctness test
+    int32_t prev = -1, lo = 0, hi = n_grid - 1;
+    bool ordered = true;
     for (int64_t r = offs[t]; r < offs[t + 1]; ++r) {
       const int32_t g = grid_index[r];
-      if (g < 0 || g >= n_grid) MB_FAIL(-1, "grid_index out of range");
+      lo = g < lo ? g : lo;
+      hi = g > hi ? g : hi;
+      ordered &= g > prev;
+      prev = g;
+    }
+    if (lo < 0 || hi >= n_grid) MB_FAIL(-1, "grid_index out of range");
+    if (ordered) continue;
+    if (seen.empty()) seen.assign((size_t)n_grid, -1);
+    for (int64_t r = offs[t]; r < offs[t + 1]; ++r) {
+      const int32_t g = grid_index[r];
       if (seen[g] == t)
         MB_FAIL(-1, "At least one individual have several Outputs on the same grid point (duplicate grid_index within a task)");
       seen[g] = t;
     }
+  }
   return 0;
 }
 
@@ -836,8 +875,6 @@ extern "C" int mb_upload_dataset(mb_context* c, int64_t n_tasks, const int64_t* 
     MB_TRY(c->d_gridX.ensure((size_t)n_grid * d * 8));
     MB_TRY(h2d(c->d_gridX.p, grid_X, (size_t)n_grid * d * 8, c->st));
   }
-  CU(cudaStreamSynchronize(c->st));
-  c->h_offs.assign(offs, offs + n_tasks + 1);
   c->db.offs = c->d_offs.as<int64_t>();
   c->db.X = c->d_X.as<double>();
   c->db.y = c->d_y.as<double>();
@@ -845,6 +882,22 @@ extern "C" int mb_upload_dataset(mb_context* c, int64_t n_tasks, const int64_t* 
   c->db.D = d;
   c->db.n_tasks = n_tasks;
   c->db.nmax = nmax;
+  // pair tables: the distinct squared distances of every task and the index of each matrix element into them (pairs3.cu),
+  // enqueued behind the copies -- one launch, ~10 us per thousand tasks
+  c->pairs_built = false;
+  apply_pair_tables(c);
+  if (c->pair_tables && nmax <= TK_MAXN) {
+    c->pair_stride = (nmax <= 64 ? 36 : 78) * 64;
+    MB_TRY(c->d_pair_d2.ensure((size_t)n_tasks * MB_PAIR_CAP * 8));
+    MB_TRY(c->d_pair_idx.ensure((size_t)n_tasks * c->pair_stride * 2));
+    MB_TRY(c->d_pair_n.ensure((size_t)n_tasks * 4));
+    LAUNCH(c, launch_task_pairs3(c->db, c->d_pair_d2.as<double>(), c->d_pair_idx.as<unsigned short>(),
+                                 c->d_pair_n.as<int32_t>(), c->pair_stride, c->st));
+    c->pairs_built = true;
+    apply_pair_tables(c);
+  }
+  CU(cudaStreamSynchronize(c->st));
+  c->h_offs.assign(offs, offs + n_tasks + 1);
   c->n_rows = rows;
   c->U = n_grid;
   c->have_db = true;

@@ -68,12 +68,14 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_inverse
     const int64_t row0 = a.db.offs[task];
     const int n = (int)(a.db.offs[task + 1] - row0);
     const int n8 = t3_n8(n), np = 8 * n8;
-    load_task3<N8C>(s, a.db, row0, n, np);
     Cov<KS, D1> cov;
-    cov.init(a.kd, a.hp + task * a.hp_stride, s.xs, D);
+    cov.init(a.kd, a.hp + task * a.hp_stride, s.xs, D, s.red + 32);
+    cov.bind_pairs(a.db, task, s.flag + 3, true);
+    pairs_prefetch3<N8C>(s, cov, n8);
+    load_task3<N8C>(s, a.db, row0, n, np);
     double sumlog;
     T3_MARK_DECL;
-    const int retries = task_inverse3<N8C>(s, n, n8, cov, a.pen, &sumlog, L, nullptr T3_MARK_PASS);
+    const int retries = task_inverse3<N8C>(s, n, n8, cov, a.pen, &sumlog, L, nullptr, true T3_MARK_PASS);
     if (a.retries && tid == 0) a.retries[task] = retries;
     const bool bad = retries < 0;
     if (a.inv_out) {

@@ -23,7 +23,18 @@ struct TaskData {          // resident dataset (device pointers)
   int D;
   int64_t n_tasks;
   int nmax;                // largest task
+  // Pair tables (pairs3.cu, built once per upload; NULL = not built).  A stationary kernel sees a pair of points only through
+  // sum_q (x_rq - x_cq)^2, and tasks observed on a common grid have few DISTINCT values of it (C2: ~385 for 2080 pairs), so
+  // the SE fast path evaluates exp() once per distinct value and looks every matrix element up -- the same expression on
+  // the same operand, hence the same bits as the element-by-element evaluation.
+  const double* pair_d2 = nullptr;         // n_tasks x MB_PAIR_CAP: the task's distinct squared distances
+  const unsigned short* pair_idx = nullptr;// n_tasks x pair_stride: per element of the packed upper tiles (tile, lane, 2: the layout of
+                                 // the DMMA accumulator fragments) its index into pair_d2; bit 15 = the reference's
+                                 // coincidence test sum_q |x_rq - x_cq| < 1e-6 (noise term, kernel-to-matrices.R:481-487)
+  const int32_t* pair_n = nullptr;         // n_tasks: number of distinct values; -1 = more than MB_PAIR_CAP or NaN inputs (direct path)
+  int pair_stride = 0;               // 16-bit entries between tasks = 64 x packed upper tiles of the 8- or 12-tile layout
 };
+#define MB_PAIR_CAP 1024
 
 struct HyperPost {         // hyper-posterior on the U grid (K = 1 for Magma)
   int K;

@@ -161,20 +161,43 @@ template <int KS, bool D1> struct Cov;
 // single SE term (+ noise): kernels.R:182-189, kernel-to-matrices.R:481-487.  D1: one input column.
 template <bool D1> struct Cov<KS_SE, D1> {
   static constexpr int NG = 3;
-  double v, hel, en;
+  // v, hel = exp(-l) / 2 and en = exp(noise) (0 without a noise HP) live in three words of the CTA's shared memory, not in
+  // registers: they are needed before AND after the factorisation, whose panel step runs at the 128-register ceiling
+  const double* hs;
   int has_noise, D;
   const double* xs;
-  __device__ __forceinline__ void init(const DevKern& kd, const double* hp, const double* xs_, int D_) {
-    v = hp[0]; hel = exp(-hp[1]) * 0.5; has_noise = kd.has_noise; en = kd.has_noise ? exp(hp[2]) : 0.0;
+  // pair table of the task (tasks.cuh:TaskData::pair_*); its pointers are re-derived from the kernel parameters where they
+  // are used, the task's count of distinct values sits in Sm3::flag[3]
+  static constexpr bool TABLE = true;
+  const TaskData* pdb;
+  int64_t ptask;
+  // stash: three doubles of shared memory; a barrier must separate init() from the first use
+  __device__ __forceinline__ void init(const DevKern& kd, const double* hp, const double* xs_, int D_, double* stash) {
+    const double v_ = hp[0], hel_ = exp(-hp[1]) * 0.5, en_ = kd.has_noise ? exp(hp[2]) : 0.0;
+    if (threadIdx.x == 0) { stash[0] = v_; stash[1] = hel_; stash[2] = en_; }
+    hs = stash;
+    has_noise = kd.has_noise;
     xs = xs_; D = D_;
+    pdb = nullptr; ptask = 0;
   }
+  __device__ __forceinline__ double v() const { return hs[0]; }
+  __device__ __forceinline__ double hel() const { return hs[1]; }
+  __device__ __forceinline__ double en() const { return hs[2]; }
+  // nd_slot: a word of the CTA's shared memory (Sm3::flag[3]) that keeps the task's count of distinct values.  fetch = false
+  // when the slot still holds this task's count (the persistent M-step kernel evaluates the same task again).
+  __device__ __forceinline__ void bind_pairs(const TaskData& db, int64_t task, int* nd_slot, bool fetch) {
+    pdb = &db; ptask = task;
+    if (fetch && threadIdx.x == 0) *nd_slot = db.pair_n ? db.pair_n[task] : 0;
+  }
+  // sum of squared differences (one fused multiply-add per column, written out so that every kernel that evaluates it --
+  // including the pair-table builder -- rounds alike) and of absolute differences
   __device__ __forceinline__ void sums(int r, int c, double& d2, double& l1) const {
     if (D1) {
       const double df = xs[r] - xs[c];
       d2 = df * df; l1 = fabs(df);
     } else {
       d2 = 0.0; l1 = 0.0;
-      for (int q = 0; q < D; ++q) { double df = xs[r * D + q] - xs[c * D + q]; d2 += df * df; l1 += fabs(df); }
+      for (int q = 0; q < D; ++q) { double df = xs[r * D + q] - xs[c * D + q]; d2 = fma(df, df, d2); l1 += fabs(df); }
     }
   }
   static constexpr bool CACHEABLE = true;
@@ -182,29 +205,29 @@ template <bool D1> struct Cov<KS_SE, D1> {
   __device__ __forceinline__ double value(int r, int c, double& raw) const {
     double d2, l1;
     sums(r, c, d2, l1);
-    double k = exp(v - hel * d2);
+    double k = exp(v() - hel() * d2);
     raw = k;
-    if (l1 < 0.000001) k += en;   // en == 0 without a noise HP
+    if (l1 < 0.000001) k += en();   // en == 0 without a noise HP
     return k;
   }
   __device__ __forceinline__ void grad(double w, int r, int c, double* gacc) const {
     double d2, l1;
     sums(r, c, d2, l1);
-    const double top = hel * d2;
-    const double wk = w * exp(v - top);
+    const double top = hel() * d2;
+    const double wk = w * exp(v() - top);
     gacc[0] += wk;
     gacc[1] += wk * top;   // w * exp(v) * top * exp(-top) of the reference up to rounding
-    if (l1 < 0.000001) gacc[2] += w * en;
+    if (l1 < 0.000001) gacc[2] += w * en();
   }
   // same with exp(v - top) read back from the cache written by value() (bit-identical)
   __device__ __forceinline__ void grad_cached(double w, int r, int c, double raw, double* gacc) const {
     double d2, l1;
     sums(r, c, d2, l1);
-    const double top = hel * d2;
+    const double top = hel() * d2;
     const double wk = w * raw;
     gacc[0] += wk;
     gacc[1] += wk * top;
-    if (l1 < 0.000001) gacc[2] += w * en;
+    if (l1 < 0.000001) gacc[2] += w * en();
   }
 };
 
@@ -215,13 +238,15 @@ template <bool D1> struct Cov<KS_GEN, D1> {
   double hp[MB_MAX_HP], hpe[MB_MAX_HP];
   int D;
   const double* xs;
-  __device__ __forceinline__ void init(const DevKern& kd_, const double* hp_, const double* xs_, int D_) {
+  __device__ __forceinline__ void init(const DevKern& kd_, const double* hp_, const double* xs_, int D_, double*) {
     kd = &kd_;
     for (int p = 0; p < kd_.n_hp; ++p) hp[p] = hp_[p];
     prep_hp(kd_, hp, hpe);
     xs = xs_; D = D_;
   }
   static constexpr bool CACHEABLE = false;
+  static constexpr bool TABLE = false;
+  __device__ __forceinline__ void bind_pairs(const TaskData&, int64_t, int*, bool) {}
   __device__ __forceinline__ double value(int r, int c, double& raw) const {
     raw = 0.0;
     return cov_eval<false>(*kd, hp, hpe, xs + r * D, xs + c * D, D, true, nullptr);
@@ -255,10 +280,83 @@ __device__ __forceinline__ int t3_npair(int n8) {
 
 // ---- building blocks ---------------------------------------------------------------------------------
 // upper tiles of K + cumulative jitter (identity on the padding) into T1
-template <class CovT>
+// Asynchronous copies (cp.async, 16 bytes each, L2 only) of the task's pair table into T2: the first PAIR_PREFETCH distinct
+// values behind the MB_PAIR_CAP doubles reserved for the table of exponentials, the index words of the packed tiles behind
+// them.  Needs only the task's size, so the per-task kernels issue it before they load the task's rows.
+#define PAIR_PREFETCH 512
+template <int N8C, class CovT>
+__device__ __forceinline__ void pairs_prefetch3(const Sm3& s, const CovT& cov, int n8) {
+  if constexpr (CovT::TABLE) {
+    if (cov.pdb->pair_n) {
+      const char* gd = reinterpret_cast<const char*>(cov.pdb->pair_d2 + cov.ptask * MB_PAIR_CAP);
+      const char* gi = reinterpret_cast<const char*>(cov.pdb->pair_idx + cov.ptask * cov.pdb->pair_stride);
+      const unsigned sd = (unsigned)__cvta_generic_to_shared(s.T2 + MB_PAIR_CAP);
+      const unsigned si = (unsigned)__cvta_generic_to_shared(s.T2 + 2 * MB_PAIR_CAP);
+      for (int o = (int)threadIdx.x * 16; o < PAIR_PREFETCH * 8; o += T3_THREADS * 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sd + o), "l"(gd + o) : "memory");
+      // packed tiles of the task's own n8 rows are not contiguous in the N8C-strided layout: copy up to the last one used
+      const int nbytes = (Lay<N8C>::tri(n8 - 1) + 1) * 128;
+      for (int o = (int)threadIdx.x * 16; o < nbytes; o += T3_THREADS * 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(si + o), "l"(gi + o) : "memory");
+    }
+  }
+}
+
+template <int N8C, class CovT>
 __device__ inline void build_cov3(const Sm3& s, int n, int n8, const CovT& cov, double pen, int retries, const Ln& L,
-                                  double* kc = nullptr) {
+                                  double* kc = nullptr, bool prefetched = false) {
   const int ntri = t3_ntri(n8);
+  if constexpr (CovT::TABLE) {
+    if (cov.pdb->pair_n) {
+      // pair-table path: exp() once per DISTINCT squared distance of the task, every element looked up -- same
+      // expression, same operand, same bits.  T2 is free until the factorisation writes the diagonal-tile inverses: it
+      // receives the task's distinct values and index words by asynchronous copies (no registers, one global round trip,
+      // requested by pairs_prefetch3 before the task's rows are loaded) and holds the table of exponentials.
+      if (!prefetched) pairs_prefetch3<N8C>(s, cov, n8);
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncthreads();
+      const int nd = s.flag[3];
+      if (nd > 0) {
+        double* tb = s.T2;
+        const double* dvs = s.T2 + MB_PAIR_CAP;
+        const unsigned* pis = reinterpret_cast<const unsigned*>(s.T2 + 2 * MB_PAIR_CAP);
+        for (int u = threadIdx.x; u < nd; u += T3_THREADS) {
+          const double d2 = (u < PAIR_PREFETCH) ? dvs[u] : cov.pdb->pair_d2[cov.ptask * MB_PAIR_CAP + u];
+          tb[u] = exp(cov.v() - cov.hel() * d2);
+        }
+        __syncthreads();
+        for (int idx = L.warp; idx < ntri; idx += NW3) {
+          const int e = s.tab[idx], i = (e >> 4) & 15, j = e & 15, dst = e >> 8;
+          const unsigned pw = pis[dst * 32 + L.lane];
+          const int r = 8 * i + L.g;
+          double o[2], raw[2];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int c = 8 * j + 2 * L.t + q;
+            const unsigned h = (pw >> (16 * q)) & 0xffffu;
+            double v = 0.0;
+            raw[q] = 0.0;
+            if (r < n && c < n) {
+              raw[q] = tb[h & 0x7fffu];
+              v = raw[q];
+              if (h & 0x8000u) v += cov.en();   // en == 0 without a noise HP
+              if (r == c) {
+                double p = pen;
+                for (int k = 0; k <= retries; ++k) { v += p; p = 10 * p; }
+              }
+            } else if (r == c) {
+              v = 1.0;
+            }
+            o[q] = v;
+          }
+          *reinterpret_cast<double2*>(s.T1 + (size_t)dst * 64 + L.o_c) = make_double2(o[0], o[1]);
+          if (CovT::CACHEABLE && kc) reinterpret_cast<double2*>(kc + (size_t)dst * 64)[L.lane] = make_double2(raw[0], raw[1]);
+        }
+        __syncthreads();
+        return;
+      }
+    }
+  }
   // three tiles (six independent exponentials) per lane and iteration: the evaluation is latency bound
   for (int idx0 = L.warp; idx0 < ntri; idx0 += 3 * NW3) {
     double o[3][2], raw[3][2];
@@ -477,10 +575,10 @@ __device__ inline void lauum3(const Sm3& s, int n8, const Ln& L) {
 
 template <int N8C, class CovT>
 __device__ inline int task_inverse3(const Sm3& s, int n, int n8, const CovT& cov, double pen, double* sumlog, const Ln& L,
-                                    double* kc T3_MARK_ARG) {
+                                    double* kc, bool prefetched T3_MARK_ARG) {
   int retries = 0;
   for (;;) {
-    build_cov3(s, n, n8, cov, pen, retries, L, kc);
+    build_cov3<N8C>(s, n, n8, cov, pen, retries, L, kc, prefetched && retries == 0);
     T3_MARK(1);
     if (chol3<N8C>(s, n8, L) == 0) break;
     __syncthreads();
@@ -571,8 +669,11 @@ __device__ __forceinline__ void task_objective_eval3(const TaskObjArgs& a, const
   double* be = s.vout + np;
   T3_MARK_DECL;
   Cov<KS, D1> cov;
-  cov.init(a.kd, hp_eff, s.xs, D);
+  cov.init(a.kd, hp_eff, s.xs, D, s.red + 32);
+  cov.bind_pairs(a.db, task, s.flag + 3, do_load);
+  pairs_prefetch3<N8C>(s, cov, n8);
   if (do_load) load_task3<N8C>(s, a.db, row0, n, np);
+  else __syncthreads();   // the HP stash written by init()
   T3_MARK(0);
   for (int i = tid; i < np; i += T3_THREADS) {
     double r = 0.0, c = 0.0;
@@ -589,7 +690,7 @@ __device__ __forceinline__ void task_objective_eval3(const TaskObjArgs& a, const
   }
   double sumlog;
   double* kc = (Cov<KS, D1>::CACHEABLE && a.kcache && a.want_grad) ? a.kcache + task * a.kcache_stride : nullptr;
-  const int retries = task_inverse3<N8C>(s, n, n8, cov, a.pen, &sumlog, L, kc T3_MARK_PASS);
+  const int retries = task_inverse3<N8C>(s, n, n8, cov, a.pen, &sumlog, L, kc, true T3_MARK_PASS);
   if (a.retries && tid == 0) a.retries[task] = retries;
   if (retries < 0) {
     if (tid == 0) {

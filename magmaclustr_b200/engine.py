@@ -62,6 +62,12 @@ class Context:
     def set_option(self, name, value):
         check(L.lib().mb_set_option(self._h, name.encode(), int(value)))
 
+    def pair_table_counts(self):
+        """Distinct squared distances per resident task (-1: the task is evaluated element by element)."""
+        out = np.empty(self.n_tasks, dtype=np.int32)
+        check(L.lib().mb_pair_table_counts(self._h, out.ctypes.data_as(L._ip)))
+        return out
+
     def set_shard(self, first_task_global, n_tasks_global):
         """Position of the resident tasks in the global task list (multi-GPU: results independent of the GPU count)."""
         check(L.lib().mb_set_shard(self._h, int(first_task_global), int(n_tasks_global)))

@@ -427,6 +427,81 @@ def test_upload_rejects_duplicate_grid_positions(ctx):
     upload(ctx, case)                                        # the same position in DIFFERENT tasks is the normal case
 
 
+def _pair_case(kind, seed=5):
+    """Synthetic tasks for the pair-table tests: (ids, X, y) with inputs on a common grid (few distinct distances),
+    continuous inputs (all distances distinct: no table), two input columns, or tasks of more than 64 points."""
+    rng = np.random.default_rng(seed)
+    ids, X, y = [], [], []
+    M = 9
+    for t in range(M):
+        if kind == "grid":
+            n = int(rng.integers(20, 65))
+            pts = np.sort(rng.choice(np.round(np.arange(0, 10.0001, 0.05), 2), size=n, replace=False))[:, None]
+        elif kind == "grid_large":
+            n = int(rng.integers(66, 97))
+            pts = np.sort(rng.choice(np.round(np.arange(0, 10.0001, 0.05), 2), size=n, replace=False))[:, None]
+        elif kind == "continuous":
+            n = 64
+            pts = np.sort(rng.uniform(0, 10, size=n))[:, None]
+        else:   # "grid_2d"
+            n = int(rng.integers(20, 50))
+            cells = rng.choice(15 * 15, size=n, replace=False)
+            pts = np.column_stack([(cells // 15) * 0.25, (cells % 15) * 0.5])
+        ids += ["t%02d" % t] * n
+        X.append(pts)
+        y.append(np.sin(pts[:, 0]) + 0.1 * rng.normal(size=n) + 0.2 * t)
+    return ids, np.vstack(X), np.concatenate(y)
+
+
+@pytest.mark.parametrize("kind", ["grid", "grid_large", "continuous", "grid_2d"])
+def test_pair_tables_are_bit_identical(ctx, kind):
+    """The SE fast path evaluates exp() once per distinct squared distance of a task and looks the matrix elements up
+    (pairs3.cu): every result must have the BITS of the element-by-element evaluation -- with and without a noise HP, and
+    when the jitter escalates (third block: a length scale far beyond the grid makes K numerically singular)."""
+    ids, X, y = _pair_case(kind)
+    prep = Prepared(np.array(ids), X, y)
+    ctx.set_option("pair_tables", 1)
+    ctx.upload_dataset(prep.offs, prep.X, prep.y, prep.grid_index, prep.grid_X)
+    counts = ctx.pair_table_counts()
+    n_i = np.diff(prep.offs)
+    if kind == "continuous":
+        assert np.all(counts == -1)                                  # 2080 distinct values > 1024: direct evaluation
+    else:
+        assert np.all(counts > 0) and np.all(counts <= 1024)
+        assert np.all(counts < n_i * (n_i + 1) // 2)                 # the grid does repeat distances
+        # the count is the number of distinct bit patterns of the squared distances, as numpy computes them
+        t = 0
+        x = prep.X[prep.offs[t]:prep.offs[t + 1]]
+        if x.shape[1] == 1:
+            d = x[:, None, 0] - x[None, :, 0]
+            assert counts[t] == len(np.unique((d * d).view(np.uint64)))
+    rng = np.random.default_rng(3)
+    M, U = len(n_i), len(prep.grid_X)
+    pm = rng.normal(size=U)
+    a = rng.normal(size=(U, U + 5))
+    pc = a @ a.T / U + np.eye(U)
+    k0 = L.parse_kernel("SE", False)
+    for noise, pen in [(True, 1e-10), (False, 1e-10), (False, 1e-17)]:
+        ki = L.parse_kernel("SE", noise)
+        hpi = np.column_stack([rng.normal(0.5, 0.5, M), rng.normal(0.5, 0.7, M)] + ([rng.normal(-2, 0.5, M)] if noise else []))
+        if pen == 1e-17:
+            hpi[:, 1] = 6.0        # length scale >> the grid and a jitter below rounding: 2-3 escalations per task (LAPACK)
+        res = []
+        for on in (1, 0):
+            ctx.set_option("pair_tables", on)
+            f, g, retr = ctx.logL_GP_mod_tasks(ki, hpi, pm, pc, pen_diag=pen)
+            if pen == 1e-17:       # the E step of such tasks (precisions ~1e13) is not the point here
+                res.append((f, g, retr))
+                continue
+            pmo, pco, info = ctx.e_step(k0, np.array([1.0, 1.0]), ki, hpi, np.zeros(U), pen_diag=pen)
+            res.append((f, g, retr, pmo, pco, info))
+        ctx.set_option("pair_tables", 1)
+        for x1, x0 in zip(res[0], res[1]):
+            assert np.array_equal(x1, x0, equal_nan=True), (kind, noise, pen)
+        if pen == 1e-17:
+            assert 2 * np.count_nonzero(res[0][2] > 0) >= len(res[0][2])  # most tasks went through the retry path
+
+
 # ---- multi-output convolution kernel (kernels.R:16-140) as a kernel type: "CONV<O>" -------------------------
 def _mo_case(seed=31, O=2, M=6, n=7):
     rng = np.random.default_rng(seed)
