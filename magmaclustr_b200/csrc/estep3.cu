@@ -70,9 +70,9 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_inverse
     const int n8 = t3_n8(n), np = 8 * n8;
     Cov<KS, D1> cov;
     cov.init(a.kd, a.hp + task * a.hp_stride, s.xs, D, s.red + 32);
-    cov.bind_pairs(a.db, task, s.flag + 3, true);
+    const int nd_t0 = cov.bind_pairs(a.db, task, true);
     pairs_prefetch3<N8C>(s, cov, n8);
-    load_task3<N8C>(s, a.db, row0, n, np);
+    load_task3<N8C>(s, a.db, row0, n, np, nd_t0);
     double sumlog;
     T3_MARK_DECL;
     const int retries = task_inverse3<N8C>(s, n, n8, cov, a.pen, &sumlog, L, nullptr, true T3_MARK_PASS);

@@ -183,11 +183,13 @@ template <bool D1> struct Cov<KS_SE, D1> {
   __device__ __forceinline__ double v() const { return hs[0]; }
   __device__ __forceinline__ double hel() const { return hs[1]; }
   __device__ __forceinline__ double en() const { return hs[2]; }
-  // nd_slot: a word of the CTA's shared memory (Sm3::flag[3]) that keeps the task's count of distinct values.  fetch = false
-  // when the slot still holds this task's count (the persistent M-step kernel evaluates the same task again).
-  __device__ __forceinline__ void bind_pairs(const TaskData& db, int64_t task, int* nd_slot, bool fetch) {
+  // The task's count of distinct values is kept in a word of the CTA's shared memory (Sm3::flag[3]).  fetch = false when the
+  // slot still holds this task's count (the persistent M-step kernel evaluates the same task again).
+  // Returns the count as thread 0 read it (0 elsewhere); the caller stores it to the slot AFTER it has issued its other
+  // loads (load_task3 does, just before its barrier), so that thread 0 does not sit out a global round trip first.
+  __device__ __forceinline__ int bind_pairs(const TaskData& db, int64_t task, bool fetch) {
     pdb = &db; ptask = task;
-    if (fetch && threadIdx.x == 0) *nd_slot = db.pair_n ? db.pair_n[task] : 0;
+    return (fetch && threadIdx.x == 0 && db.pair_n) ? db.pair_n[task] : 0;
   }
   // sum of squared differences (one fused multiply-add per column, written out so that every kernel that evaluates it --
   // including the pair-table builder -- rounds alike) and of absolute differences
@@ -246,7 +248,7 @@ template <bool D1> struct Cov<KS_GEN, D1> {
   }
   static constexpr bool CACHEABLE = false;
   static constexpr bool TABLE = false;
-  __device__ __forceinline__ void bind_pairs(const TaskData&, int64_t, int*, bool) {}
+  __device__ __forceinline__ int bind_pairs(const TaskData&, int64_t, bool) { return 0; }
   __device__ __forceinline__ double value(int r, int c, double& raw) const {
     raw = 0.0;
     return cov_eval<false>(*kd, hp, hpe, xs + r * D, xs + c * D, D, true, nullptr);
@@ -621,14 +623,16 @@ __device__ inline void gemv3(const Sm3& s, int n8, const double* V, double* O, c
   __syncthreads();
 }
 
+// nd: the task's pair-table count as returned by Cov::bind_pairs (thread 0), stored to Sm3::flag[3] before the barrier
 template <int N8C>
-__device__ inline void load_task3(const Sm3& s, const TaskData& db, int64_t row0, int n, int np) {
+__device__ inline void load_task3(const Sm3& s, const TaskData& db, int64_t row0, int n, int np, int nd = 0) {
   for (int e = threadIdx.x; e < np * db.D; e += T3_THREADS) s.xs[e] = (e < n * db.D) ? db.X[row0 * db.D + e] : 0.0;
   for (int i = threadIdx.x; i < np; i += T3_THREADS) {
     s.yv[i] = (i < n) ? db.y[row0 + i] : 0.0;
     s.gi[i] = (i < n) ? (db.gidx ? db.gidx[row0 + i] : i) : 0;
   }
   build_tabs3<N8C>(s, np >> 3);
+  if (threadIdx.x == 0) s.flag[3] = nd;
   __syncthreads();
 }
 
@@ -670,9 +674,9 @@ __device__ __forceinline__ void task_objective_eval3(const TaskObjArgs& a, const
   T3_MARK_DECL;
   Cov<KS, D1> cov;
   cov.init(a.kd, hp_eff, s.xs, D, s.red + 32);
-  cov.bind_pairs(a.db, task, s.flag + 3, do_load);
+  const int nd_t0 = cov.bind_pairs(a.db, task, do_load);
   pairs_prefetch3<N8C>(s, cov, n8);
-  if (do_load) load_task3<N8C>(s, a.db, row0, n, np);
+  if (do_load) load_task3<N8C>(s, a.db, row0, n, np, nd_t0);
   else __syncthreads();   // the HP stash written by init()
   T3_MARK(0);
   for (int i = tid; i < np; i += T3_THREADS) {
