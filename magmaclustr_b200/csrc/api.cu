@@ -860,7 +860,7 @@ extern "C" int mb_upload_dataset(mb_context* c, int64_t n_tasks, const int64_t* 
     if (n < 1) MB_FAIL(-1, "empty task");
     if (n > nmax) nmax = (int)n;
   }
-  if (grid_index) MB_TRY(check_grid_index(offs, n_tasks, grid_index, n_grid));
+  c->have_db = false;   // the resident dataset is being replaced: an error below leaves none
   MB_TRY(c->d_offs.ensure((n_tasks + 1) * 8));
   MB_TRY(c->d_X.ensure((size_t)rows * d * 8));
   MB_TRY(c->d_y.ensure((size_t)rows * 8));
@@ -874,6 +874,12 @@ extern "C" int mb_upload_dataset(mb_context* c, int64_t n_tasks, const int64_t* 
   if (grid_X && n_grid > 0) {
     MB_TRY(c->d_gridX.ensure((size_t)n_grid * d * 8));
     MB_TRY(h2d(c->d_gridX.p, grid_X, (size_t)n_grid * d * 8, c->st));
+  }
+  // the host-side validation of grid_index runs while the copies are in flight (pinned source buffers: the copies above
+  // only enqueue); on failure the stream is drained and the context is left without a dataset
+  if (grid_index) {
+    const int rc = check_grid_index(offs, n_tasks, grid_index, n_grid);
+    if (rc) { cudaStreamSynchronize(c->st); return rc; }
   }
   c->db.offs = c->d_offs.as<int64_t>();
   c->db.X = c->d_X.as<double>();
@@ -1101,6 +1107,11 @@ static int dev_e_step(mb_context* c, int K, const mb_kernel* kern_k, const doubl
       LAUNCH(c, launch_task_inverse_any(a, (int)(nl * per), c->st));
     } else {
       a.queue = c->tickets.as<int>() + nl;
+      // a few SMs stay free for the inv_0 chain on st2 (union-grid kernels; the single-CTA factorisation needs a whole SM's
+      // shared memory and would otherwise wait for the persistent task CTAs to drain)
+      static const bool reserve = getenv("MB_ESTEP_NORESERVE") == nullptr;
+      if (reserve && c->reserve_sms > 0 && cap == (int64_t)c->sm_count * task_ctas_per_sm_any(c->db.nmax, c->db.D))
+        a.sm_limit = c->sm_count - c->reserve_sms;
       LAUNCH(c, launch_task_inverse_any(a, (int)cap, c->st));
     }
   }

@@ -29,6 +29,11 @@ __global__ void __launch_bounds__(T3_THREADS, (N8C <= 8) ? 4 : 2) k_task_inverse
   const Sm3 s = carve3<N8C>((double*)task3_smem_raw, D);
   const Ln L;
   const int tid = threadIdx.x;
+  if (a.sm_limit > 0 && a.queue) {   // dynamic dealing only: the remaining CTAs simply take more items
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if ((int)smid >= a.sm_limit) return;
+  }
   // accumulating launches: the CTAs pull work items from an atomic counter, item g = (leaf g % n_leaves, position
   // g / n_leaves in that leaf) -- consecutive items go to different leaves, the tasks of one leaf are handed out in task
   // order, and whoever holds position p waits (ticket) for position p - 1, which was handed out EARLIER to a CTA that is

@@ -91,6 +91,8 @@ struct TaskInvArgs {       // E step / list_kern_to_inv
   int32_t* retries;
   int ld;
   int diag_skip;             // diagnostics only (MB_ESTEP_DIAG): 1 = no ticket ordering, 2 = no accumulation (timing decomposition)
+  int sm_limit;              // > 0 with a work queue: CTAs that land on an SM with %smid >= sm_limit leave at once (SMs kept
+                             // free for the union-grid kernels of inv_0 running on the other stream); 0 = use every SM
 };
 
 struct TaskPredArgs {      // pred_magma(clust) batched over the resident (new) tasks
