@@ -866,6 +866,29 @@ extern "C" int mb_upload_dataset(mb_context* c, int64_t n_tasks, const int64_t* 
   MB_TRY(c->d_y.ensure((size_t)rows * 8));
   MB_TRY(h2d(c->d_offs.p, offs, (n_tasks + 1) * 8, c->st));
   MB_TRY(h2d(c->d_X.p, X, (size_t)rows * d * 8, c->st));
+  c->db.offs = c->d_offs.as<int64_t>();
+  c->db.X = c->d_X.as<double>();
+  c->db.D = d;
+  c->db.n_tasks = n_tasks;
+  c->db.nmax = nmax;
+  // pair tables: the distinct squared distances of every task and the index of each matrix element into them (pairs3.cu).
+  // They need the row offsets and the inputs only, so the kernel runs on the second stream behind those two copies while
+  // the outputs and grid indices are still on their way
+  c->pairs_built = false;
+  apply_pair_tables(c);
+  bool pairs_launched = false;
+  if (c->pair_tables && nmax <= TK_MAXN) {
+    c->pair_stride = (nmax <= 64 ? 36 : 78) * 64;
+    MB_TRY(c->d_pair_d2.ensure((size_t)n_tasks * MB_PAIR_CAP * 8));
+    MB_TRY(c->d_pair_idx.ensure((size_t)n_tasks * c->pair_stride * 2));
+    MB_TRY(c->d_pair_n.ensure((size_t)n_tasks * 4));
+    if (!c->ev_single) CU(cudaEventCreateWithFlags(&c->ev_single, cudaEventDisableTiming));
+    CU(cudaEventRecord(c->ev_single, c->st));
+    CU(cudaStreamWaitEvent(c->st2, c->ev_single, 0));
+    LAUNCH(c, launch_task_pairs3(c->db, c->d_pair_d2.as<double>(), c->d_pair_idx.as<unsigned short>(),
+                                 c->d_pair_n.as<int32_t>(), c->pair_stride, c->st2));
+    pairs_launched = true;
+  }
   MB_TRY(h2d(c->d_y.p, y, (size_t)rows * 8, c->st));
   if (grid_index) {
     MB_TRY(c->d_gidx.ensure((size_t)rows * 4));
@@ -876,29 +899,15 @@ extern "C" int mb_upload_dataset(mb_context* c, int64_t n_tasks, const int64_t* 
     MB_TRY(h2d(c->d_gridX.p, grid_X, (size_t)n_grid * d * 8, c->st));
   }
   // the host-side validation of grid_index runs while the copies are in flight (pinned source buffers: the copies above
-  // only enqueue); on failure the stream is drained and the context is left without a dataset
+  // only enqueue); on failure the streams are drained and the context is left without a dataset
   if (grid_index) {
     const int rc = check_grid_index(offs, n_tasks, grid_index, n_grid);
-    if (rc) { cudaStreamSynchronize(c->st); return rc; }
+    if (rc) { cudaStreamSynchronize(c->st); cudaStreamSynchronize(c->st2); return rc; }
   }
-  c->db.offs = c->d_offs.as<int64_t>();
-  c->db.X = c->d_X.as<double>();
   c->db.y = c->d_y.as<double>();
   c->db.gidx = grid_index ? c->d_gidx.as<int32_t>() : nullptr;
-  c->db.D = d;
-  c->db.n_tasks = n_tasks;
-  c->db.nmax = nmax;
-  // pair tables: the distinct squared distances of every task and the index of each matrix element into them (pairs3.cu),
-  // enqueued behind the copies -- one launch, ~10 us per thousand tasks
-  c->pairs_built = false;
-  apply_pair_tables(c);
-  if (c->pair_tables && nmax <= TK_MAXN) {
-    c->pair_stride = (nmax <= 64 ? 36 : 78) * 64;
-    MB_TRY(c->d_pair_d2.ensure((size_t)n_tasks * MB_PAIR_CAP * 8));
-    MB_TRY(c->d_pair_idx.ensure((size_t)n_tasks * c->pair_stride * 2));
-    MB_TRY(c->d_pair_n.ensure((size_t)n_tasks * 4));
-    LAUNCH(c, launch_task_pairs3(c->db, c->d_pair_d2.as<double>(), c->d_pair_idx.as<unsigned short>(),
-                                 c->d_pair_n.as<int32_t>(), c->pair_stride, c->st));
+  if (pairs_launched) {
+    CU(cudaStreamSynchronize(c->st2));
     c->pairs_built = true;
     apply_pair_tables(c);
   }

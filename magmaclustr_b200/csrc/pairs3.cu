@@ -16,7 +16,7 @@
 // race), the looked-up values cannot.
 #include "tasks3.cuh"
 
-#define PAIR_HCAP 2048                       /* hash slots: MB_PAIR_CAP distinct values + one in-flight insert per thread */
+#define PAIR_HCAP 2048                       /* hash slots (a power of two, < 2^15: slot numbers travel in 15 bits) */
 #define PAIR_EMPTY 0xffffffffffffffffull     /* a NaN pattern: never the bits of a squared distance that is inserted */
 
 extern __shared__ double4 pairs3_smem_raw[];
@@ -27,20 +27,17 @@ __device__ __forceinline__ unsigned pair_hash(unsigned long long k) {
   return (unsigned)(k >> 53);   // 11 bits = PAIR_HCAP slots
 }
 
-// tile number idx of the row-major enumeration of the upper tiles (the order of Sm3::tab) -> (i, j)
-__device__ __forceinline__ void pair_tile(int idx, int n8, int& i, int& j) {
-  i = 0;
-  while (idx >= n8 - i) { idx -= n8 - i; ++i; }
-  j = i + idx;
-}
+#define PAIR_MAX_PROBE 128   /* a longer probe sequence means a table far beyond MB_PAIR_CAP entries: give up on the task */
 
 template <int N8C, bool D1>
 __global__ void __launch_bounds__(T3_THREADS) k_task_pairs3(TaskData db, double* pair_d2, unsigned short* pair_idx, int32_t* pair_n,
                                                             int pair_stride) {
+  constexpr int TPW = (Lay<N8C>::NTRI + NW3 - 1) / NW3;   // tiles per warp
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(pairs3_smem_raw);
   unsigned short* ids = reinterpret_cast<unsigned short*>(keys + PAIR_HCAP);
-  int* ctl = reinterpret_cast<int*>(ids + PAIR_HCAP);   // [0] distinct values so far, [1] give up, [2..5] warp counts
-  double* xs = reinterpret_cast<double*>(ctl + 8);
+  int* ctl = reinterpret_cast<int*>(ids + PAIR_HCAP);   // [1] give up, [2..5] warp counts
+  unsigned short* tiles = reinterpret_cast<unsigned short*>(ctl + 8);   // upper tiles row by row: (i << 8) | j, NTRI entries
+  double* xs = reinterpret_cast<double*>(tiles + ((Lay<N8C>::NTRI + 3) & ~3));
   const int64_t task = blockIdx.x;
   const int64_t row0 = db.offs[task];
   const int n = (int)(db.offs[task + 1] - row0);
@@ -50,39 +47,46 @@ __global__ void __launch_bounds__(T3_THREADS) k_task_pairs3(TaskData db, double*
   for (int e = tid; e < np * D; e += T3_THREADS) xs[e] = (e < n * D) ? db.X[row0 * D + e] : 0.0;
   for (int h = tid; h < PAIR_HCAP; h += T3_THREADS) keys[h] = PAIR_EMPTY;
   if (tid < 8) ctl[tid] = 0;
+  if (tid < n8) {
+    int o = tid * n8 - ((tid * (tid - 1)) >> 1);
+    for (int j = tid; j < n8; ++j) tiles[o++] = (unsigned short)((tid << 8) | j);
+  }
   __syncthreads();
   Cov<KS_SE, D1> cov;      // only sums(): the very expression the matrix builders evaluate
   cov.xs = xs; cov.D = D;
-  volatile int* vctl = ctl;
-  // ---- pass 1: the set of distinct values
-  for (int idx = L.warp; idx < ntri; idx += NW3) {
-    int i, j;
-    pair_tile(idx, n8, i, j);
-    const int r = 8 * i + L.g;
+  // ---- pass 1: the set of distinct values; every element remembers the slot of its value (two 16-bit slots per tile)
+  unsigned slots[TPW];
+  bool giveup = false;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int c = 8 * j + 2 * L.t + q;
-      if (r < n && c < n && !vctl[1]) {
-        double d2, l1;
-        cov.sums(r, c, d2, l1);
-        if (!(d2 == d2)) { vctl[1] = 1; continue; }
-        const unsigned long long key = (unsigned long long)__double_as_longlong(d2);
-        unsigned h = pair_hash(key);
-        for (;;) {
-          unsigned long long old = keys[h];
-          if (old == PAIR_EMPTY) {
-            old = atomicCAS(keys + h, PAIR_EMPTY, key);
-            if (old == PAIR_EMPTY) {
-              if (atomicAdd(ctl, 1) >= MB_PAIR_CAP) vctl[1] = 1;
-              break;
-            }
+  for (int u = 0; u < TPW; ++u) {
+    const int idx = L.warp + u * NW3;
+    slots[u] = 0;
+    if (idx < ntri) {
+      const int i = tiles[idx] >> 8, j = tiles[idx] & 255;
+      const int r = 8 * i + L.g;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c = 8 * j + 2 * L.t + q;
+        if (r < n && c < n) {
+          double d2, l1;
+          cov.sums(r, c, d2, l1);
+          if (!(d2 == d2)) { giveup = true; continue; }
+          const unsigned long long key = (unsigned long long)__double_as_longlong(d2);
+          unsigned h = pair_hash(key);
+          int probes = 0;
+          for (;;) {
+            unsigned long long old = keys[h];
+            if (old == PAIR_EMPTY) old = atomicCAS(keys + h, PAIR_EMPTY, key);
+            if (old == PAIR_EMPTY || old == key) break;
+            h = (h + 1) & (PAIR_HCAP - 1);
+            if (++probes > PAIR_MAX_PROBE) { giveup = true; break; }
           }
-          if (old == key) break;
-          h = (h + 1) & (PAIR_HCAP - 1);
+          slots[u] |= (h | (l1 < 0.000001 ? 0x8000u : 0u)) << (16 * q);
         }
       }
     }
   }
+  if (giveup) ctl[1] = 1;
   __syncthreads();
   if (ctl[1]) {
     if (tid == 0) pair_n[task] = -1;
@@ -103,6 +107,11 @@ __global__ void __launch_bounds__(T3_THREADS) k_task_pairs3(TaskData db, double*
   __syncthreads();
   int base = incl - mine;
   for (int w = 0; w < L.warp; ++w) base += ctl[2 + w];
+  const int total = ctl[2] + ctl[3] + ctl[4] + ctl[5];
+  if (total > MB_PAIR_CAP) {   // uniform
+    if (tid == 0) pair_n[task] = -1;
+    return;
+  }
   double* dv = pair_d2 + task * MB_PAIR_CAP;
 #pragma unroll
   for (int k = 0; k < SPT; ++k) {
@@ -114,28 +123,25 @@ __global__ void __launch_bounds__(T3_THREADS) k_task_pairs3(TaskData db, double*
     }
   }
   __syncthreads();
-  // ---- pass 2: every element's index (two 16-bit entries per lane and tile, written as one word)
+  // ---- pass 2: slot -> index (two 16-bit entries per lane and tile, written as one word)
   unsigned* out = reinterpret_cast<unsigned*>(pair_idx + task * pair_stride);
-  for (int idx = L.warp; idx < ntri; idx += NW3) {
-    int i, j;
-    pair_tile(idx, n8, i, j);
-    const int r = 8 * i + L.g;
-    unsigned word = 0;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int c = 8 * j + 2 * L.t + q;
-      if (r < n && c < n) {
-        double d2, l1;
-        cov.sums(r, c, d2, l1);
-        const unsigned long long key = (unsigned long long)__double_as_longlong(d2);
-        unsigned h = pair_hash(key);
-        while (keys[h] != key) h = (h + 1) & (PAIR_HCAP - 1);
-        word |= ((unsigned)ids[h] | (l1 < 0.000001 ? 0x8000u : 0u)) << (16 * q);
+  for (int u = 0; u < TPW; ++u) {
+    const int idx = L.warp + u * NW3;
+    if (idx < ntri) {
+      const int i = tiles[idx] >> 8, j = tiles[idx] & 255;
+      const int r = 8 * i + L.g;
+      unsigned word = 0;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c = 8 * j + 2 * L.t + q;
+        const unsigned sl = (slots[u] >> (16 * q)) & 0xffffu;
+        if (r < n && c < n) word |= ((unsigned)ids[sl & 0x7fffu] | (sl & 0x8000u)) << (16 * q);
       }
+      out[(Lay<N8C>::tri(i) + j - i) * 32 + L.lane] = word;
     }
-    out[(Lay<N8C>::tri(i) + j - i) * 32 + L.lane] = word;
   }
-  if (tid == 0) pair_n[task] = ctl[0];
+  if (tid == 0) pair_n[task] = total;
 }
 
 // pair_stride: 16-bit entries per task = 64 x the packed upper tiles of the layout the per-task kernels will use for this
@@ -146,7 +152,7 @@ cudaError_t launch_task_pairs3(TaskData db, double* pair_d2, unsigned short* pai
   if (db.nmax > TK_MAXN) return cudaErrorInvalidValue;
   const bool small = db.nmax <= 64, d1 = db.D == 1;
   const int np = small ? 64 : 96;
-  const size_t smem = (size_t)PAIR_HCAP * (8 + 2) + 32 + (size_t)np * db.D * 8;
+  const size_t smem = (size_t)PAIR_HCAP * (8 + 2) + 32 + (size_t)(small ? 36 : 80) * 2 + (size_t)np * db.D * 8;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaSuccess;
 #define PAIRS_GO(N8C_, D1_)                                                                                                     \
