@@ -31,9 +31,11 @@ sys.path.insert(0, ROOT)
 
 M_TASKS, N_POINTS = 10000, 64
 DATA_SEED, HP0_SEED, HPI_SEED = 2024, 6, 106
-# dram__bytes_read.sum + dram__bytes_write.sum of one full-grid launch of the dominant kernel (10 000
-# evaluations), from the ncu --set full capture summarised in profiles/r2_final_k_task_objective3_ncu.txt (16.04 MB read + 3.01 MB written, with the L2 discard of the kernel-value cache; 145.5 MB before it)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 19044864
+# dram__bytes_read.sum + dram__bytes_write.sum of one full-grid launch of the dominant kernel (10 000 evaluations), from the
+# ncu --set full capture summarised in profiles/r2_final_k_task_objective3_ncu.txt: 100.65 MB read + 3.71 MB written.  Of the
+# reads 86 MB are the tasks' pair tables (8.6 KB per task: index words + distinct squared distances, pairs3.cu) -- they
+# replace 4/5 of the exponentials; 19.0 MB without them, 145.5 MB in round 1 (write-back of the kernel-value cache).
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 104357120
 METRIC = "train_magma EM steps/sec at M=10k,N=64"
 FLOPS_PER_EVAL = 5.0  # x N^3: chol+inverse N^3, S A and A (S A) 4 N^3; log-det read off the Cholesky diagonal
 

