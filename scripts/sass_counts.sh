@@ -5,7 +5,7 @@
 #   LDGSTS  = cp.async (Ampere-style staged copy);  ATOMG.E.ADD.F64 with destination RZ = fire-and-forget FP64 reduction (red.global.add.f64)
 # usage: scripts/sass_counts.sh > profiles/r2_sass_counts.txt   (after the library is built)
 cd "$(dirname "$0")/../magmaclustr_b200/lib" || exit 1
-for o in tasks3 estep3 mstep3 dense3 dense_big bigtasks covbuild; do
+for o in tasks3 estep3 mstep3 pairs3 dense3 dense_big bigtasks covbuild; do
   echo "== $o.o"
   cuobjdump -sass $o.o 2>/dev/null | awk '
     /Function :/ {fn=$3}
