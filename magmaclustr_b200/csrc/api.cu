@@ -2611,8 +2611,7 @@ static int shared_k_eval(mb_context* c, int K, const DevKern& kdk, const double*
   const size_t UU = (size_t)c->U * c->U;
   double* hres = c->h_pin + 32;
   int* hinfo = c->h_pin_i + 8;
-  double ll = 0.0, cor = 0.0;
-  (void)cor;
+  double ll = 0.0;
   *f = 0.0;
   for (int p = 0; p < kdk.n_hp; ++p) g[p] = 0.0;
   for (int k = 0; k < K; ++k) {

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(DSM_THREADS, 1) k_dense_cholinv_sm(const doubl
                                                                      double* __restrict__ inv, int n, double pen,
                                                                      int max_retry, int mode, int* info, double* out,
                                                                      double* __restrict__ xt_out) {
-  const int n8 = (n + 7) >> 3, np = 8 * n8, ntri = n8 * (n8 + 1) / 2;
+  const int n8 = (n + 7) >> 3, ntri = n8 * (n8 + 1) / 2;
   const SmD s = carve_d((double*)dense3_smem_raw, n8);
   const Ln L;
   for (int i = threadIdx.x; i < n8; i += DSM_THREADS)
