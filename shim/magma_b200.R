@@ -19,6 +19,9 @@
   t(as.matrix(hp[, setdiff(names(hp), c("ID", "prop_mixture")), drop = FALSE]))
 }
 .mb_input_cols <- function(db) setdiff(names(db), c("ID", "Output", "Reference"))
+## library switches (include/magma_b200.h: mb_set_option): magma_b200_option("logdet_chol", 0) evaluates log-determinants like
+## R/likelihoods.R:37-41 (LU of the explicit inverse); magma_b200_option("pair_tables", 0) evaluates the SE kernel element by element
+magma_b200_option <- function(name, value) invisible(.Call("mbR_set_option", as.character(name), as.double(value)))
 
 ## what e_step / m_step / ve_step / vm_step need from `db`: uploaded once per (db, grid)
 .mb_upload <- function(db, grid_inputs = NULL) {

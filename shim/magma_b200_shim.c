@@ -316,6 +316,12 @@ SEXP mbR_pred_magmaclust(SEXP kern, SEXP hp, SEXP x_obs, SEXP y_obs, SEXP x_pred
   UNPROTECT(4);
   return out;
 }
+/* tuning / parity switches of the library (include/magma_b200.h: mb_set_option), e.g. ("logdet_chol", 0) for the
+ * reference's LU log-determinant (R/likelihoods.R:37-41) or ("pair_tables", 0) for the element-by-element SE kernel */
+SEXP mbR_set_option(SEXP name, SEXP value) {
+  MB_CHECK(mb_set_option(ctx(), CHAR(STRING_ELT(name, 0)), (int64_t)Rf_asReal(value)));
+  return R_NilValue;
+}
 /* keep the next hyper-posterior on the device / install one (new-task path) */
 SEXP mbR_hyperpost_keep(SEXP keep) {
   MB_CHECK(mb_hyperpost_keep(ctx(), Rf_asLogical(keep)));
@@ -500,6 +506,7 @@ static const R_CallMethodDef CallEntries[] = {
     ENTRY(mbR_pred_magma, 13),
     ENTRY(mbR_hyperposterior_clust, 10),
     ENTRY(mbR_pred_magmaclust, 13),
+    ENTRY(mbR_set_option, 2),
     ENTRY(mbR_hyperpost_keep, 1),
     ENTRY(mbR_hyperpost_set, 2),
     ENTRY(mbR_logL_GP_tasks, 6),

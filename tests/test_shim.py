@@ -78,7 +78,7 @@ def test_shim_builds_and_registers_every_routine():
               "logL_GP_mod", "logL_GP_mod_tasks", "train_magma", "hyperposterior", "pred_magma", "hyperposterior_clust",
               "pred_magmaclust", "hyperpost_keep", "hyperpost_set", "logL_GP_tasks", "train_gp_tasks", "train_shared_gp",
               "train_gp_clust_tasks", "pred_magma_tasks", "ve_step", "update_mixture", "elbo_clust_tasks", "vm_step",
-              "elbo_monitoring", "train_magmaclust"):
+              "elbo_monitoring", "train_magmaclust", "set_option"):
         assert "mbR_" + r in reg, r
     # every routine of the table is a real symbol of the object, with the arity its definition has
     src = open(os.path.join(ROOT, "shim", "magma_b200_shim.c")).read()
@@ -125,6 +125,14 @@ def test_shim_routines_match_the_c_abi(ctx):
     ll = _call(l, "mbR_logL_monitoring", l.mock_str(b"SE"), _real(l, case["hp0"]), l.mock_str(b"SE"), _real(l, case["hpi"]),
                l.mock_lgl(0), _real(l, np.zeros(U)), _real(l, pm), _real(l, pc), _real(l, [1e-10]))
     assert _values(l, ll)[0] == ctx.logL_monitoring(case["k0"], case["hp0"], case["ki"], case["hpi"], np.zeros(U), pm, pc)
+    # library switches through the shim: the element-by-element SE kernel gives the bits of the pair-table path
+    _call(l, "mbR_set_option", l.mock_str(b"pair_tables"), _real(l, [0.0]))
+    res0 = _call(l, "mbR_e_step", l.mock_str(b"SE"), _real(l, case["hp0"]), l.mock_str(b"SE"), _real(l, case["hpi"]),
+                 l.mock_lgl(0), _real(l, np.zeros(U)), _real(l, [1e-10]))
+    assert np.array_equal(_values(l, l.mock_list_get(res0, b"cov"), (U, U)), pc)
+    _call(l, "mbR_set_option", l.mock_str(b"pair_tables"), _real(l, [1.0]))
+    with pytest.raises(RuntimeError, match="unknown option"):
+        _call(l, "mbR_set_option", l.mock_str(b"no_such_switch"), _real(l, [1.0]))
     # a library failure surfaces as an R error with the library's message
     with pytest.raises(RuntimeError, match="magma_b200"):
         _call(l, "mbR_kern_to_cov", l.mock_str(b"SE * * RQ"), l.mock_lgl(1), _real(l, hp), _real(l, m1, True), l.mock_nil(),
