@@ -46,6 +46,32 @@ def _task_ll(i):
     return M.logL_GP_mod(hp_i[i], Xi, yi, mi, kern_i, Si, pen)
 
 
+def _task_inv(i):
+    db, hp_i, kern_i, pen = (_G[k] for k in ("db", "hp_i", "kern_i", "pen"))
+    _, Xi, _ = db.tasks[i]
+    return M.K.chol_inv_jitter(M.K.kern_to_cov(Xi, kern_i, hp_i[i]), pen)
+
+
+def e_step(db, m_0, kern_0, kern_i, hp_0, hp_i, pen_diag, pool, chunksize):
+    """oracle.magma.e_step with the per-task chol_inv_jitter spread over the pool; the inverses are added in task order by
+    the parent, exactly as the sequential loop does (em-magma.R:39-46).  Same operations in the same order; the last bits
+    can differ from oracle.magma.e_step because OpenBLAS blocks dpotrf / dpotri differently with one thread (workers) than
+    with several (a stand-alone call).  Timing baseline only -- the parity tests use oracle.magma."""
+    U = db.grid_X.shape[0]
+    m_0 = M._mean_vec(m_0, U)
+    inv_0 = M.K.chol_inv_jitter(M.K.kern_to_cov(db.grid_X, kern_0, hp_0), pen_diag)
+    post_inv = inv_0.copy()
+    weighted_0 = inv_0 @ m_0
+    list_inv = dict(zip(db.ids, pool.map(_task_inv, db.ids, chunksize=chunksize)))
+    for i in db.ids:
+        idx = db.index[i]
+        post_inv[np.ix_(idx, idx)] += list_inv[i]
+    post_cov = M.K.chol_inv_jitter(post_inv, pen_diag)
+    for i in db.ids:
+        weighted_0[db.index[i]] += list_inv[i] @ db.tasks[i][2]
+    return post_cov @ weighted_0, post_cov
+
+
 def em_step(db, m_0, kern_0, kern_i, hp_0, hp_i, pen_diag=1e-10, procs=None):
     """One iteration of train_magma's loop body (training.R:905-1030), shared_hp = FALSE.
     Returns (new_hp_0, new_hp_i, logL, n_task_evals)."""
@@ -53,9 +79,12 @@ def em_step(db, m_0, kern_0, kern_i, hp_0, hp_i, pen_diag=1e-10, procs=None):
     _limit_blas_threads()       # 64 x 64 matrices: BLAS threads only add overhead, and the pool below already uses every core
     U = db.grid_X.shape[0]
     m0 = M._mean_vec(m_0, U)
-    pm, pc = M.e_step(db, m0, kern_0, kern_i, hp_0, hp_i, pen_diag)
-    _G.update(db=db, hp_i=hp_i, kern_i=kern_i, pm=pm, pc=pc, pen=pen_diag)
     ctx = mp.get_context("fork")
+    chunk = max(1, len(db.ids) // (4 * procs))
+    _G.update(db=db, hp_i=hp_i, kern_i=kern_i, pen=pen_diag)
+    with ctx.Pool(procs, initializer=_limit_blas_threads) as pool:
+        pm, pc = e_step(db, m0, kern_0, kern_i, hp_0, hp_i, pen_diag, pool, chunk)
+    _G.update(pm=pm, pc=pc)
     with ctx.Pool(procs, initializer=_limit_blas_threads) as pool:
         fut = pool.map_async(_task_opt, db.ids, chunksize=max(1, len(db.ids) // (4 * procs)))
         new_hp_0, _ = M._optim(
