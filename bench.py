@@ -329,6 +329,13 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        # one BLAS thread per process from the very start (the pool already uses every core): OpenBLAS sizes its thread pool
+        # when numpy is imported, so the variables have to be in the environment before this interpreter starts -- torchrun
+        # sets OMP_NUM_THREADS=1 itself, a plain `python bench.py --impl reference` did not, and the two differed
+        if rank == 0 and os.environ.get("OPENBLAS_NUM_THREADS") != "1" and not os.environ.get("MB_BENCH_REEXEC"):
+            env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", MB_BENCH_REEXEC="1")
+            sys.stdout.flush()
+            os.execve(sys.executable, [sys.executable] + sys.argv, env)
         try:
             run_reference(args, rank)
         except Exception as e:               # never leave the driver without a line
