@@ -263,3 +263,28 @@ def test_native_prepare_rows_rejects_duplicates():
     with pytest.raises(L.MagmaError) as e:
         DP.prepare_rows_native(ids, X, np.zeros(3))
     assert e.value.args[0] == 3 or "several Outputs" in str(e.value)
+
+
+def test_cpu_baseline_pool_matches_sequential_oracle():
+    """oracle/parallel.py (the all-cores driver behind bench.py's cpu_baseline / --impl reference) runs the SAME EM step as the
+    sequential oracle: hyper-posterior to rounding (OpenBLAS blocks differently with one thread), identical optimiser
+    evaluation counts, log-likelihood to 1e-9."""
+    import multiprocessing as mp
+    from helpers import make_case
+    from oracle import magma as OM, parallel as OP
+    case = make_case(12, 10, 23)
+    db, h0, hi = case["odb"], case["o_hp0"], case["o_hpi"]
+    pm, pc = OM.e_step(db, 0.0, "SE", "SE", h0, hi, 1e-10)
+    OP._G.update(db=db, hp_i=hi, kern_i="SE", pen=1e-10)
+    with mp.get_context("fork").Pool(2, initializer=OP._limit_blas_threads) as pool:
+        pm2, pc2 = OP.e_step(db, 0.0, "SE", "SE", h0, hi, 1e-10, pool, 2)
+    assert np.max(np.abs(pc2 - pc)) <= 1e-9 * np.max(np.abs(pc)) and np.max(np.abs(pm2 - pm)) <= 1e-7 * np.max(np.abs(pm))
+    stats = {}
+    n0, ni = OM.m_step(db, 0.0, "SE", "SE", h0, hi, pm, pc, False, 1e-10, stats)
+    ll = OM.logL_monitoring(n0, ni, db, 0.0, "SE", "SE", pm, pc, 1e-10)
+    _, ni2, ll2, evals = OP.em_step(db, 0.0, "SE", "SE", h0, hi, 1e-10, procs=2)
+    assert evals == sum(r["counts"] for r in stats["tasks"].values())
+    assert abs(ll2 - ll) <= 1e-6 * abs(ll)
+    for i in db.ids:
+        for k in ni[i]:
+            assert abs(ni2[i][k] - ni[i][k]) <= 1e-4 * max(1.0, abs(ni[i][k]))    # observed 4e-6 (factr = 1e13 stops early)
