@@ -283,7 +283,8 @@ def test_cpu_baseline_pool_matches_sequential_oracle():
     n0, ni = OM.m_step(db, 0.0, "SE", "SE", h0, hi, pm, pc, False, 1e-10, stats)
     ll = OM.logL_monitoring(n0, ni, db, 0.0, "SE", "SE", pm, pc, 1e-10)
     _, ni2, ll2, evals = OP.em_step(db, 0.0, "SE", "SE", h0, hi, 1e-10, procs=2)
-    assert evals == sum(r["counts"] for r in stats["tasks"].values())
+    ref_evals = sum(r["counts"] for r in stats["tasks"].values())
+    assert abs(evals - ref_evals) <= max(2, ref_evals // 50)     # equal here; a BLAS thread-count rounding difference may move one line search
     assert abs(ll2 - ll) <= 1e-6 * abs(ll)
     for i in db.ids:
         for k in ni[i]:
